@@ -1,0 +1,116 @@
+/*
+ * dexdeform_mpm.h -- C ABI of libmaniskill_mpm.so as built by dexdeform_b200 (sm_100a).
+ *
+ * Part 1 ("ABI-1") is, symbol for symbol and argument for argument, the interface the reference binds with
+ * ctypes in mpm/types.py:103-290 and implements in mpm/csrc/integrator.cu:1616-2125.  Dropping this library at
+ * mpm/libmaniskill_mpm.so (mpm/types.py:12-19) replaces the reference's native backend without touching its Python.
+ *   - all pointers are raw device pointers owned by the caller (mpm/types.py:294-312); kernels never allocate
+ *   - vec3 = 3 floats, mat3 = 9 floats row-major, quat = (w,x,y,z), ivec3 = 3 ints (mpm/types.py:25-75)
+ *   - `const int *grid_dim` is the reference's `ivec3 const&` (pointer to 3 ints)
+ *   - outputs are accumulated into caller-zeroed buffers (mpm/simulator.py:72-85)
+ *   - no return codes; CUDA errors are printed as "CUDA Error: ..." and execution continues (mpm/csrc/common.h:29-34)
+ *
+ * Part 2 ("ABI-2", dd_* symbols) is the fused, batched engine the new Python host classes drive; see DESIGN.md.
+ */
+#ifndef DEXDEFORM_MPM_H
+#define DEXDEFORM_MPM_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+/* ------------------------------------------------------------------------------------------------ ABI-1 */
+
+/* integrator.cu:1619-1625 -- dynamic grid origin (never called by the reference's substep; kept for the ABI) */
+void compute_grid_lower(void *particle_x, float dx, float inv_dx, void *grid_lower, int dim, cudaStream_t stream);
+
+/* integrator.cu:1627-1638 -- newF = (I + dt C) F ; (U, sig, V) = svd(newF) */
+void compute_svd(void *F, void *C, void *newF, void *U, void *V, void *sig, float dt, int dim, cudaStream_t stream);
+
+/* integrator.cu:1640-1657 -- adjoint of compute_svd; adds into F_grad, C_grad, overwrites newF_grad with the total */
+void compute_svd_grad(void *F, void *C, void *U, void *V, void *sig, void *newF_grad, void *U_grad, void *V_grad, void *sig_grad,
+                      void *F_grad, void *C_grad, float dt, int dim, cudaStream_t stream);
+
+/* integrator.cu:1659-1690 -- return mapping, stress, APIC scatter of mass and momentum; writes out_particle_F */
+void p2g(void *particle_x, void *particle_v, void *particle_m, void *particle_vol, void *particle_F, void *particle_U, void *particle_sig,
+         void *particle_V, void *particle_C, void *particle_mu_lam_yield, void *grid_lower, const int *grid_dim, float dx, float inv_dx,
+         float dt, void *out_particle_F, void *out_grid_mv, void *out_grid_m, int dim, cudaStream_t stream);
+
+/* integrator.cu:1692-1742 -- adjoint of p2g */
+void p2g_grad(void *particle_x, void *particle_v, void *particle_m, void *particle_vol, void *particle_F, void *particle_U, void *particle_sig,
+              void *particle_V, void *particle_C, void *particle_mu_lam_yield, void *grid_lower, const int *grid_dim, float dx, float inv_dx,
+              float dt, void *out_particle_F, void *out_grid_mv, void *out_grid_m, void *particle_x_grad, void *particle_v_grad,
+              void *particle_F_grad, void *particle_C_grad, void *particle_U_grad, void *particle_sig_grad, void *particle_V_grad,
+              void *out_particle_F_grad, void *out_grid_v_grad, void *out_grid_m_grad, int dim, cudaStream_t stream);
+
+/* integrator.cu:1754-1779 -- normalise, gravity, sequential SDF contact against n_bodies primitives, boundary conditions */
+void grid_op_v2(void *grid_m, void *grid_v_in, void *grid_body_v_in, void *grid_lower, void *gravity, void *body_pos, void *body_rot,
+                void *next_body_pos, void *next_body_rot, void *body_type_friction_softness_round, void *body_args, float dx, float inv_dx,
+                float dt, float ground_friction, void *out_grid_v, const int *grid_dim, int n_bodies, cudaStream_t stream);
+
+/* integrator.cu:1781-1819 -- adjoint of grid_op_v2 incl. pose gradients at t and t+1 */
+void grid_op_v2_grad(void *grid_m, void *grid_v_in, void *grid_body_v_in, void *grid_lower, void *gravity, void *body_pos, void *body_rot,
+                     void *next_body_pos, void *next_body_rot, void *body_type_friction_softness_round, void *body_args, void *grid_m_grad,
+                     void *grid_v_in_grad, void *body_pos_grad, void *body_rot_grad, void *next_body_pos_grad, void *next_body_rot_grad,
+                     float dx, float inv_dx, float dt, float ground_friction, void *out_grid_v, void *out_grid_v_grad, const int *grid_dim,
+                     int n_bodies, cudaStream_t stream);
+
+/* integrator.cu:1821-1835 -- APIC gather, advection, position clamp */
+void g2p(void *particle_x, void *grid_v, void *grid_lower, float dx, float inv_dx, float dt, const int *grid_dim, void *out_particle_v,
+         float ground_height, void *out_particle_C, void *out_particle_x, int dim, cudaStream_t stream);
+
+/* integrator.cu:1837-1861 -- adjoint of g2p */
+void g2p_grad(void *particle_x, void *grid_v, void *grid_lower, float dx, float inv_dx, float dt, const int *grid_dim, void *out_particle_v,
+              float ground_height, void *out_particle_C, void *out_particle_x, int dim, void *particle_x_grad, void *grid_v_grad,
+              void *out_particle_v_grad, void *out_particle_C_grad, void *out_particle_x_grad, cudaStream_t stream);
+
+/* integrator.cu:1935-1960 -- particle-to-primitive signed distances (N, n_bodies) and their adjoint */
+void compute_dist(void *particle_x, void *body_pos, void *body_rot, void *body_type_friction_softness_round, void *body_args, void *dist,
+                  int n_bodies, void *particle_x_grad, void *body_pos_grad, void *body_rot_grad, void *dist_grad, int compute_grad, int dim,
+                  cudaStream_t stream);
+
+/* integrator.cu:1962-1984 -- density-grid observation of object `id` (-1 = all) and its adjoint */
+void particle2mass(void *particle_x, void *particle_m, void *grid_lower, const int *grid_dim, float dx, float inv_dx, void *out_grid_m,
+                   void *out_grid_m_grad, void *particle_x_grad, void *particle_ids, int id, int compute_grad, int dim, cudaStream_t stream);
+
+/* integrator.cu:1990-2072 -- device memory and stream helpers used by mpm/types.py:294-400 */
+void *cuda_alloc(size_t size);
+void cuda_free(void *ptr);
+void print_memory_info(void);
+cudaStream_t cuda_stream_create(void);
+void cuda_stream_destroy(cudaStream_t stream);
+void cuda_stream_sync(cudaStream_t stream);
+void cuda_upload(void *device_ptr, void *host_ptr, size_t size);
+void cuda_download(void *host_ptr, void *device_ptr, size_t size);
+void cuda_copy(void *dst, void *src, size_t size);
+void cuda_copy2d(void *dst, size_t dpitch, void *src, size_t spitch, size_t width, size_t height);
+void cuda_zero(void *ptr, size_t size);
+void cuda_zero_async(void *ptr, size_t size, cudaStream_t stream);
+void cuda_upload_async(void *device_ptr, void *host_ptr, size_t size, cudaStream_t stream);
+void cuda_download_async(void *host_ptr, void *device_ptr, size_t size, cudaStream_t stream);
+void cuda_copy_async(void *dst, void *src, size_t size, cudaStream_t stream);
+
+/* integrator.cu:1863-1933, 2074-2124 -- renderer entry points.  Outside the hot path: exported as no-ops so that
+ * mpm/types.py can still set their argtypes. */
+typedef struct { void *array; unsigned long long texture; } dd_texture_resources;
+#ifdef __cplusplus
+void render(void *sdf_volume, void *box_min, void *box_max, void *color_volume, void *body_pos, void *body_rot, void *tfsr, void *body_args,
+            void *camera_rot, void *camera_pos, void *camera_intrinsic, void *color_buffer, void *depth_buffer, float sdf_threshold,
+            const int *grid_dim, int n_bodies, bool visualize_shape, const int *image_dim, int max_ray_depth, int spp, float ground_height,
+            int seed, void *light_direction, cudaStream_t stream);
+#endif
+void particle_sdf(void *volume, void *particle_x, void *particle_color, void *bbox_min, void *bbox_max, int bake_size, const int *grid_dim,
+                  float inv_dx, void *sdf, void *color, void *sdf_tmp, int n_particles, cudaStream_t stream);
+dd_texture_resources create_volume(float *data, int x, int y, int z);
+void destroy_volume(dd_texture_resources tex);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEXDEFORM_MPM_H */
