@@ -26,7 +26,7 @@ def _qmul(a, b):
 def hand_like_bodies(rng, center, extent, nb=19, scale=1.5):
     """tfsr (type, friction, softness=666, round) and args per primitive + initial poses around ``center``."""
     types = np.array([1] * nb, np.float32)
-    types[[1, 2, 12][: max(0, min(3, nb - 1))]] = 0.0  # palm boxes + LF metacarpal box (robot.xml:18-19,99)
+    types[[i for i in (1, 2, 12) if i < nb]] = 0.0  # palm boxes + LF metacarpal box (robot.xml:18-19,99)
     tfsr = np.stack([types, np.full(nb, 0.9, np.float32), np.full(nb, 666.0, np.float32), np.zeros(nb, np.float32)], 1)
     args = np.zeros((nb, 4), np.float32)
     for b in range(nb):

@@ -1,0 +1,60 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b| (L-inf relative to the reference magnitude)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def cosine(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle import build
+    from oracle.oracle_lib import OracleLib
+    build.build(verbose=False)
+    return OracleLib()
+
+
+@pytest.fixture(scope="session")
+def ref_cpu():
+    from oracle.oracle_lib import REF_CPU, load_ref_cpu
+    if not os.path.isfile(REF_CPU):
+        pytest.skip("oracle/_ref/libmaniskill_mpm_cpu.so not built (needs /root/reference; run oracle/build_ref.sh)")
+    return load_ref_cpu()
+
+
+@pytest.fixture(scope="session")
+def ref_gpu():
+    from oracle.oracle_lib import REF_GPU, load_ref_gpu
+    if not os.path.isfile(REF_GPU):
+        pytest.skip("oracle/_ref/libmaniskill_mpm.so not built")
+    return load_ref_gpu()
+
+
+@pytest.fixture(scope="session")
+def product_lib():
+    from dexdeform_b200.types import load_library
+    return load_library()
