@@ -12,9 +12,11 @@ from parity_util import check_against_golden, golden_cases
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("name", golden_cases("_gpu"))
 def test_product_matches_reference_golden(product_lib, name):
-    check_against_golden(product_lib, name)
+    # fixtures produced on a B200 by the reference's own CUDA build (same FMA contraction as any nvcc build);
+    # the host-build fixtures differ from these by up to 2e-4 in grid_v_in at rest because g++ does not contract
+    check_against_golden(product_lib, name, "_gpu")
 
 
 def test_kernel_by_kernel_vs_reference_cuda(product_lib, ref_gpu):
