@@ -1,0 +1,1059 @@
+// engine.cu -- fused, batched MLS-MPM substep + adjoint for sm_100a (ABI-2, dd_* symbols in include/dexdeform_mpm.h).
+//
+// What differs from the reference pipeline (mpm/simulator.py:561-585, integrator.cu):
+//   * particle state lives in float4 SoA planes, one checkpoint slot per substep (x,v,C | F), E environments batched
+//   * compute_svd + p2g are one kernel; U, V, sigma, F~ never touch HBM (the reference writes/reads 120 B/particle)
+//   * a grid node is one float4 (mv.xyz, m), scattered with one red.global.add.v4.f32 instead of four scalar atomics
+//   * the per-body input velocities (grid_body_v_in, (nb+1)*12 B per node) are not stored: the adjoint re-derives them
+//     from a contact bit-mask (contacts are velocity independent) by replaying the few contacting bodies
+//   * p2g_grad + compute_svd_grad are one kernel; gradients of state t are written once (ping-pong grad slots)
+//   * S substeps (or their reverse) are captured into one CUDA graph; poses for all substeps are device resident
+#include "mpm_math.cuh"
+#include "../../include/dexdeform_mpm.h"
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using namespace dd;
+
+namespace {
+
+thread_local std::string g_last_error;
+int fail(const std::string &msg) { g_last_error = msg; return 1; }
+#define DD_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+constexpr int kT = 256;
+constexpr int kPlaneFloats = 25;  // 16 (x,v,C + pad) + 9 (F)
+
+struct KP {            // kernel parameters shared by all kernels
+  int E, N, EN, nb, G, gx, gy, gz;
+  float dx, inv_dx, dt, gf, gh;
+  float g0, g1, g2;    // gravity (already scaled as the caller wants it)
+};
+
+// ---- particle planes ----------------------------------------------------------------------------------------
+// slot layout (floats): [0,4EN) P0=(x.x,x.y,x.z,v.x)  [4EN,8EN) P1=(v.y,v.z,C00,C01)  [8EN,12EN) P2=(C02,C10,C11,C12)
+//                       [12EN,16EN) P3=(C20,C21,C22,0) [16EN,20EN) F0=(F00..F10) [20EN,24EN) F1=(F11..F21) [24EN,25EN) F2=F22
+struct XVC { V3 x, v; M3 C; };
+DD_DEV const float4 *plane4(const float *slot, int EN, int k) { return reinterpret_cast<const float4 *>(slot + (size_t)4 * k * EN); }
+DD_DEV float4 *plane4(float *slot, int EN, int k) { return reinterpret_cast<float4 *>(slot + (size_t)4 * k * EN); }
+DD_DEV float4 ldg_stream(const float4 *p) {  // streaming 128-bit load that does not pollute L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+DD_DEV XVC load_xvc(const float *slot, int EN, int p) {
+  float4 a = ldg_stream(plane4(slot, EN, 0) + p), b = ldg_stream(plane4(slot, EN, 1) + p), c = ldg_stream(plane4(slot, EN, 2) + p),
+         d = ldg_stream(plane4(slot, EN, 3) + p);
+  XVC r;
+  r.x = v3(a.x, a.y, a.z);
+  r.v = v3(a.w, b.x, b.y);
+  r.C = m3(b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z);
+  return r;
+}
+DD_DEV void store_xvc(float *slot, int EN, int p, V3 x, V3 v, const M3 &C) {
+  plane4(slot, EN, 0)[p] = make_float4(x.x, x.y, x.z, v.x);
+  plane4(slot, EN, 1)[p] = make_float4(v.y, v.z, C.a00, C.a01);
+  plane4(slot, EN, 2)[p] = make_float4(C.a02, C.a10, C.a11, C.a12);
+  plane4(slot, EN, 3)[p] = make_float4(C.a20, C.a21, C.a22, 0.f);
+}
+DD_DEV M3 load_F(const float *slot, int EN, int p) {
+  float4 a = ldg_stream(plane4(slot, EN, 4) + p), b = ldg_stream(plane4(slot, EN, 5) + p);
+  float c = __ldg(slot + (size_t)24 * EN + p);
+  return m3(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c);
+}
+DD_DEV void store_F(float *slot, int EN, int p, const M3 &F) {
+  plane4(slot, EN, 4)[p] = make_float4(F.a00, F.a01, F.a02, F.a10);
+  plane4(slot, EN, 5)[p] = make_float4(F.a11, F.a12, F.a20, F.a21);
+  slot[(size_t)24 * EN + p] = F.a22;
+}
+DD_DEV void red_add_v4(float4 *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+DD_DEV int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// stencil with the base clamped into the grid (identical to the reference for every in-domain particle)
+DD_DEV Stencil make_stencil_safe(V3 x, const KP &kp) {
+  Stencil s = make_stencil(x, kp.inv_dx);
+  int bx = clampi(s.bx, 0, kp.gx - 3), by = clampi(s.by, 0, kp.gy - 3), bz = clampi(s.bz, 0, kp.gz - 3);
+  if (bx != s.bx || by != s.by || bz != s.bz) {  // out-of-domain input: keep memory safe, weights follow the clamped base
+    s.bx = bx; s.by = by; s.bz = bz;
+  }
+  return s;
+}
+
+// Constitutive update shared by forward and adjoint: F~ = (I + dt C) F, SVD, return mapping, affine matrix.
+struct Constit {
+  M3 Ft, U, Vm, nF, r, affine;
+  V3 sigma;
+  Plastic pl;
+  float J, scale;
+};
+template <int SVD>
+DD_DEV void constitutive(const XVC &s, const M3 &F, float4 m0, float yield, const KP &kp, Constit &c) {
+  c.Ft = mul(mdiag(1.f) + s.C * kp.dt, F);
+  if (SVD == 0) svd3_f64(c.Ft, c.U, c.sigma, c.Vm); else svd3_f32(c.Ft, c.U, c.sigma, c.Vm);
+  c.J = von_mises(c.Ft, c.U, c.sigma, c.Vm, yield, m0.z, c.nF, c.pl);
+  c.r = mul_nt(c.U, c.Vm);
+  c.scale = -kp.dt * m0.y * 4.f * kp.inv_dx * kp.inv_dx;
+  c.affine = c.scale * fixed_corotated(c.nF, c.r, c.J, m0.z, m0.w) + m0.x * s.C;
+}
+
+// ---- forward kernels -------------------------------------------------------------------------------------------
+// compute_svd + p2g (integrator.cu:84-100, 313-394) fused
+template <int SVD, bool WRITE_F>
+__global__ void __launch_bounds__(kT) k_p2g(KP kp, const float *__restrict__ cur, float *__restrict__ nxt, const float4 *__restrict__ mat0,
+                                            const float *__restrict__ yield, float4 *__restrict__ grid) {
+  int p = blockIdx.x * kT + threadIdx.x;
+  if (p >= kp.EN) return;
+  XVC s = load_xvc(cur, kp.EN, p);
+  M3 F = load_F(cur, kp.EN, p);
+  float4 m0 = __ldg(mat0 + p);
+  Constit c;
+  constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c);
+  if (WRITE_F) store_F(nxt, kp.EN, p, c.nF);
+  Stencil st = make_stencil_safe(s.x, kp);
+  float m = m0.x;
+  V3 mv = m * s.v;
+  // affine * dpos is separable: dpos = (offset - fx) * dx
+  V3 c0 = v3(c.affine.a00, c.affine.a10, c.affine.a20), c1 = v3(c.affine.a01, c.affine.a11, c.affine.a21), c2 = v3(c.affine.a02, c.affine.a12, c.affine.a22);
+  float4 *g = grid + (size_t)(p / kp.N) * kp.G;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float wi = pick(st.w0, st.w1, st.w2, i, 0);
+    V3 ai = mv + c0 * (((float)i - st.fx.x) * kp.dx);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float wij = wi * pick(st.w0, st.w1, st.w2, j, 1);
+      V3 aij = ai + c1 * (((float)j - st.fx.y) * kp.dx);
+      int row = ((st.bx + i) * kp.gy + st.by + j) * kp.gz + st.bz;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float w = wij * pick(st.w0, st.w1, st.w2, k, 2);
+        V3 a = (aij + c2 * (((float)k - st.fx.z) * kp.dx)) * w;
+        red_add_v4(g + row + k, a.x, a.y, a.z, m * w);
+      }
+    }
+  }
+}
+
+struct BodyTables {  // device pointers; poses are per (slot, env, body), shapes shared by all envs
+  const float4 *pos, *rot, *npos, *nrot;  // already offset to the slot; index env*nb + b
+  const float4 *tfsr, *args;
+  const float *cull;                      // conservative activation radius per body
+};
+DD_DEV Q4 q4f(float4 t) { Q4 q; q.w = t.x; q.x = t.y; q.y = t.z; q.z = t.w; return q; }
+DD_DEV V3 v3f(float4 t) { return v3(t.x, t.y, t.z); }
+
+struct Hit {
+  V3 gxb, un, rn, nrm, bv, rel, vt_in, vt;
+  float dist, infl, nc, vtn;
+  bool has_fric;
+};
+// geometric part of the contact test (velocity independent), integrator.cu:705-710
+DD_DEV bool contact_geom(V3 gx, V3 bx, Q4 bq, Q4 tfsr, Q4 sargs, float cull, Hit &h) {
+  V3 d = gx - bx;
+  if (dot(d, d) > cull * cull) return false;  // cannot be within the influence band
+  h.gxb = qrot(qconj(bq), d);
+  h.dist = shape_sdf(tfsr, sargs, h.gxb);
+  return contact_active(h.dist, tfsr.y, h.infl);
+}
+// velocity part, integrator.cu:714-729
+DD_DEV V3 contact_apply(V3 gx, V3 v, Q4 bq, V3 npos, Q4 nrot, Q4 tfsr, Q4 sargs, float dt, Hit &h) {
+  h.un = shape_grad(tfsr, sargs, h.gxb);
+  h.rn = normalized(h.un);
+  h.nrm = qrot(bq, h.rn);
+  h.bv = (xform(npos, nrot, h.gxb) - gx) / dt;
+  h.rel = v - h.bv;
+  h.nc = dot(h.rel, h.nrm);
+  h.vt_in = h.rel - fminf(h.nc, 0.f) * h.nrm;
+  h.has_fric = h.nc < 0.f && (double)dot(h.vt_in, h.vt_in) > 1e-30;
+  h.vtn = length30(h.vt_in);
+  h.vt = h.vt_in;
+  if (h.has_fric) h.vt = h.vt_in * (1.f / h.vtn) * fmaxf(0.f, h.vtn + h.nc * tfsr.x);
+  return h.bv + h.rel * (1 - h.infl) + h.vt * h.infl;
+}
+DD_DEV V3 apply_bc(V3 v, int gx_, int gy_, int gz_, const KP &kp) {  // integrator.cu:734-774
+  const int bound = 3;
+  if (gx_ < bound && v.x < 0) v.x = 0;
+  if (gx_ > kp.gx - bound && v.x > 0) v.x = 0;
+  if (gy_ < bound && v.y < 0) {
+    if (kp.gf > 0.f) {
+      if (kp.gf < 99.f) {
+        float lin = v.y;
+        V3 vit = v3(v.x, 0.f, v.z);
+        float lit = sqrtf(dot(vit, vit) + 1e-8f);
+        v = vit * fmaxf((float)(1. + (double)(kp.gf * lin / lit)), 0.f);
+      } else {
+        v = vzero();
+      }
+    }
+    v.y = 0;
+  }
+  if (gy_ > kp.gy - bound && v.y > 0) v.y = 0;
+  if (gz_ < bound && v.z < 0) v.z = 0;
+  if (gz_ > kp.gz - bound && v.z > 0) v.z = 0;
+  return v;
+}
+
+// grid_op_v2 (integrator.cu:647-777) on float4 nodes; dense over E*G nodes
+__global__ void __launch_bounds__(kT) k_grid(KP kp, const float4 *__restrict__ grid, float4 *__restrict__ grid_v, BodyTables bt) {
+  int node = blockIdx.x * kT + threadIdx.x;
+  if (node >= kp.E * kp.G) return;
+  float4 mm = grid[node];
+  if (!(mm.w > 1e-12)) {
+    grid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  int env = node / kp.G, cell = node - env * kp.G;
+  int gx_ = cell / kp.gz / kp.gy, gy_ = (cell / kp.gz) % kp.gy, gz_ = cell % kp.gz;
+  V3 v = v3(mm.x, mm.y, mm.z) * (1.f / mm.w) + kp.dt * v3(kp.g0, kp.g1, kp.g2);
+  V3 gx = v3((float)gx_, (float)gy_, (float)gz_) * kp.dx;
+  for (int b = 0; b < kp.nb; ++b) {
+    int pb = env * kp.nb + b;
+    Hit h;
+    Q4 bq = q4f(bt.rot[pb]), tfsr = q4f(bt.tfsr[b]), sargs = q4f(bt.args[b]);
+    if (contact_geom(gx, v3f(bt.pos[pb]), bq, tfsr, sargs, bt.cull[b], h))
+      v = contact_apply(gx, v, bq, v3f(bt.npos[pb]), q4f(bt.nrot[pb]), tfsr, sargs, kp.dt, h);
+  }
+  v = apply_bc(v, gx_, gy_, gz_, kp);
+  grid_v[node] = make_float4(v.x, v.y, v.z, 0.f);
+}
+
+// g2p (integrator.cu:1059-1109)
+__global__ void __launch_bounds__(kT) k_g2p(KP kp, const float *__restrict__ cur, float *__restrict__ nxt, const float4 *__restrict__ grid_v) {
+  int p = blockIdx.x * kT + threadIdx.x;
+  if (p >= kp.EN) return;
+  float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
+  V3 x = v3(a.x, a.y, a.z);
+  Stencil st = make_stencil_safe(x, kp);
+  const float4 *g = grid_v + (size_t)(p / kp.N) * kp.G;
+  V3 nv = vzero();
+  M3 nC = mzero();
+  float s4 = kp.inv_dx * 4.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float wi = pick(st.w0, st.w1, st.w2, i, 0);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float wij = wi * pick(st.w0, st.w1, st.w2, j, 1);
+      int row = ((st.bx + i) * kp.gy + st.by + j) * kp.gz + st.bz;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float w = wij * pick(st.w0, st.w1, st.w2, k, 2);
+        V3 dpos = v3((float)i, (float)j, (float)k) - st.fx;
+        float4 t = __ldg(g + row + k);
+        V3 v = v3(t.x, t.y, t.z);
+        nv += v * w;
+        nC += outer(v, dpos) * (w * s4);
+      }
+    }
+  }
+  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+  float lo = kp.gh * kp.dx;
+  V3 t = x + nv * kp.dt;
+  store_xvc(nxt, kp.EN, p, v3(fmaxf(fminf(t.x, hi.x), lo), fmaxf(fminf(t.y, hi.y), lo), fmaxf(fminf(t.z, hi.z), lo)), nv, nC);
+}
+
+// ---- adjoint kernels -------------------------------------------------------------------------------------------
+// g2p_grad (integrator.cu:1527-1614).  gin = gradients of state t+1, gout = gradients of state t (partial gx written)
+__global__ void __launch_bounds__(kT) k_g2p_grad(KP kp, const float *__restrict__ cur, const float *__restrict__ nxt,
+                                                 const float4 *__restrict__ grid_v, const float *__restrict__ gin, float *__restrict__ gout,
+                                                 float4 *__restrict__ ggrid_v) {
+  int p = blockIdx.x * kT + threadIdx.x;
+  if (p >= kp.EN) return;
+  float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
+  V3 x = v3(a.x, a.y, a.z);
+  float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
+  V3 nvel = v3(n0.w, n1.x, n1.y);
+  XVC g = load_xvc(gin, kp.EN, p);  // (gx', gv', gC')
+  V3 gx = g.x, gnv = g.v;
+  V3 nx = x + nvel * kp.dt;
+  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+  float lo = kp.gh * kp.dx;
+  if (nx.x > hi.x || nx.x < lo) gx.x = 0;
+  if (nx.y > hi.y || nx.y < lo) gx.y = 0;
+  if (nx.z > hi.z || nx.z < lo) gx.z = 0;
+  gnv += gx * kp.dt;
+  Stencil st = make_stencil_safe(x, kp);
+  V3 d0, d1, d2;
+  stencil_dw(st, kp.inv_dx, d0, d1, d2);
+  size_t goff = (size_t)(p / kp.N) * kp.G;
+  float s4 = kp.inv_dx * 4.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      int row = ((st.bx + i) * kp.gy + st.by + j) * kp.gz + st.bz;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float wx = pick(st.w0, st.w1, st.w2, i, 0), wy = pick(st.w0, st.w1, st.w2, j, 1), wz = pick(st.w0, st.w1, st.w2, k, 2);
+        float w = wx * wy * wz;
+        V3 dpos = v3((float)i, (float)j, (float)k) - st.fx;
+        float4 t = __ldg(grid_v + goff + row + k);
+        V3 v = v3(t.x, t.y, t.z);
+        float xx = w * s4;
+        V3 cd = mul(g.C, dpos);
+        V3 ggv = w * gnv + cd * xx;
+        red_add_v4(ggrid_v + goff + row + k, ggv.x, ggv.y, ggv.z, 0.f);
+        gx += (-kp.inv_dx * xx) * mul_t(g.C, v);
+        float gw = dot(gnv, v) + s4 * dot(v, cd);
+        gx += v3(pick(d0, d1, d2, i, 0) * wy * wz, wx * pick(d0, d1, d2, j, 1) * wz, wx * wy * pick(d0, d1, d2, k, 2)) * gw;
+      }
+    }
+  }
+  plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
+}
+
+DD_DEV float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// grid_op_v2_grad (integrator.cu:779-1057) without the stored per-body velocities
+__global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restrict__ grid, const float4 *__restrict__ ggrid_v,
+                                                  float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos, float4 *grot, float4 *gnpos,
+                                                  float4 *gnrot) {
+  int node = blockIdx.x * kT + threadIdx.x;
+  bool inr = node < kp.E * kp.G;
+  float4 mm = inr ? grid[node] : make_float4(0.f, 0.f, 0.f, 0.f);
+  bool live = inr && mm.w > 1e-12;
+  // a whole warp of empty nodes leaves early (the common case)
+  if (!__any_sync(0xffffffffu, live)) {
+    if (inr) ggrid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  int env = 0, gx_ = 0, gy_ = 0, gz_ = 0;
+  V3 gv = vzero(), mv = vzero(), gx = vzero(), v0 = vzero();
+  unsigned long long mask = 0ull;
+  if (live) {
+    env = node / kp.G;
+    int cell = node - env * kp.G;
+    gx_ = cell / kp.gz / kp.gy; gy_ = (cell / kp.gz) % kp.gy; gz_ = cell % kp.gz;
+    mv = v3(mm.x, mm.y, mm.z);
+    v0 = mv * (1.f / mm.w) + kp.dt * v3(kp.g0, kp.g1, kp.g2);
+    gx = v3((float)gx_, (float)gy_, (float)gz_) * kp.dx;
+    // forward replay: contact mask + velocity after all bodies
+    V3 v = v0;
+    for (int b = 0; b < kp.nb; ++b) {
+      int pb = env * kp.nb + b;
+      Hit h;
+      Q4 bq = q4f(bt.rot[pb]), tfsr = q4f(bt.tfsr[b]), sargs = q4f(bt.args[b]);
+      if (contact_geom(gx, v3f(bt.pos[pb]), bq, tfsr, sargs, bt.cull[b], h)) {
+        mask |= 1ull << b;
+        v = contact_apply(gx, v, bq, v3f(bt.npos[pb]), q4f(bt.nrot[pb]), tfsr, sargs, kp.dt, h);
+      }
+    }
+    V3 vv = v;
+    float4 t = ggrid_v[node];
+    gv = v3(t.x, t.y, t.z);
+    // boundary-condition adjoint (integrator.cu:829-893)
+    V3 vin = vv;
+    const int bound = 3;
+    if (gx_ > kp.gx - bound && vv.x > 0) vin.x = 0;
+    if (gx_ < bound && vv.x < 0) vin.x = 0;
+    float lin = 0.f, lit = 1.f;
+    V3 vit = vzero();
+    bool hit_ground = gy_ < bound && vin.y < 0;
+    if (hit_ground) {
+      lin = vin.y;
+      vit = v3(vin.x, 0.f, vin.z);
+      lit = sqrtf(dot(vit, vit) + 1e-8f);
+      float flag = (float)(1. + (double)(kp.gf * lin / lit));
+      vin = vit * fmaxf(flag, 0.f);
+    }
+    if (gz_ > kp.gz - bound && vin.z > 0) gv.z = 0;
+    if (gz_ < bound && vin.z < 0) gv.z = 0;
+    if (gy_ > kp.gy - bound && vin.y > 0) gv.y = 0;
+    if (hit_ground) {
+      gv.y = 0;
+      float flag = (float)(1. + (double)(kp.gf * lin / lit));
+      if (flag >= 0.f) {
+        V3 g_vit = flag * gv;
+        float g_lin = kp.gf / lit * dot(vit, gv);
+        float g_lit = -kp.gf * lin / lit / lit * dot(vit, gv);
+        g_vit += g_lit * (vit / lit);
+        gv = v3(g_vit.x, g_lin, g_vit.z);
+      } else {
+        gv = vzero();
+      }
+    }
+    if (gx_ > kp.gx - bound && vv.x > 0) gv.x = 0;
+    if (gx_ < bound && vv.x < 0) gv.x = 0;
+  }
+  // bodies in reverse; all lanes take part in the warp reductions
+  unsigned long long wmask = mask;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmask |= __shfl_xor_sync(0xffffffffu, wmask, o);
+  while (wmask) {
+    int b = 63 - __clzll((long long)wmask);
+    wmask &= ~(1ull << b);
+    V3 g_bx = vzero(), g_np = vzero();
+    Q4 g_bq, g_nq;
+    g_bq.w = g_bq.x = g_bq.y = g_bq.z = 0.f;
+    g_nq = g_bq;
+    if (live && (mask >> b & 1ull)) {
+      // input velocity of stage b: replay the contacting bodies before it
+      V3 v = v0;
+      unsigned long long lower = mask & ((1ull << b) - 1ull);
+      while (lower) {
+        int c = __ffsll((long long)lower) - 1;
+        lower &= lower - 1ull;
+        int pc = env * kp.nb + c;
+        Hit hc;
+        Q4 cq = q4f(bt.rot[pc]), ct = q4f(bt.tfsr[c]), ca = q4f(bt.args[c]);
+        contact_geom(gx, v3f(bt.pos[pc]), cq, ct, ca, bt.cull[c], hc);
+        v = contact_apply(gx, v, cq, v3f(bt.npos[pc]), q4f(bt.nrot[pc]), ct, ca, kp.dt, hc);
+      }
+      int pb = env * kp.nb + b;
+      V3 bx = v3f(bt.pos[pb]);
+      Q4 bq = q4f(bt.rot[pb]), nrot = q4f(bt.nrot[pb]), tfsr = q4f(bt.tfsr[b]), sargs = q4f(bt.args[b]);
+      Hit h;
+      contact_geom(gx, bx, bq, tfsr, sargs, bt.cull[b], h);
+      contact_apply(gx, v, bq, v3f(bt.npos[pb]), nrot, tfsr, sargs, kp.dt, h);
+      float friction = tfsr.x, softness = tfsr.y;
+      float g_nc = 0.f;
+      V3 g_bv = gv, g_rel = gv * (1 - h.infl), g_vt = gv * h.infl;
+      float g_infl = dot(h.vt - h.rel, gv);
+      if (h.has_fric) {
+        float bf = h.vtn + h.nc * friction;
+        if (bf > 0.f) {
+          g_nc += dot(h.vt_in, g_vt) * friction / h.vtn;
+          float g_vtn = -h.nc * g_nc / h.vtn;
+          g_vt = g_vt * (float)(1. / (double)h.vtn) * bf + g_vtn * h.vt_in / h.vtn;
+        } else {
+          g_vt = vzero();
+        }
+      }
+      V3 g_n = vzero();
+      g_rel += g_vt;
+      if (h.nc < 0.f) {
+        g_nc += -dot(h.nrm, g_vt);
+        g_n += (-h.nc) * g_vt;
+      }
+      g_rel += h.nrm * g_nc;
+      g_n += h.rel * g_nc;
+      gv = g_rel;
+      g_bv = g_bv - g_rel;
+      V3 g_gxb = vzero();
+      xform_adj(nrot, h.gxb, g_bv * (1.f / kp.dt), g_np, g_nq, g_gxb);
+      V3 g_rn = vzero();
+      qrot_adj(bq, h.rn, g_n, g_bq, g_rn);
+      g_gxb += shape_grad_adj(tfsr, sargs, h.gxb, normalized_adj(h.un, g_rn));
+      float expdist = expf(-h.dist * softness);
+      if (expdist <= 1) g_gxb += h.un * (-softness * expdist * g_infl);
+      V3 g_tmp = vzero();
+      xform_inv_adj(bx, bq, gx, g_gxb, g_bx, g_bq, g_tmp);
+    }
+    // NOTE: a warp may straddle two environments only if G is not a multiple of 32; grids are multiples of 4^3
+    float r[14] = {g_np.x, g_np.y, g_np.z, g_nq.w, g_nq.x, g_nq.y, g_nq.z, g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z};
+#pragma unroll
+    for (int i = 0; i < 14; ++i) r[i] = warp_sum(r[i]);
+    if ((threadIdx.x & 31) == 0) {
+      int wenv = (blockIdx.x * kT + (threadIdx.x & ~31)) / kp.G;
+      int pb = wenv * kp.nb + b;
+      atomicAdd(&gnpos[pb].x, r[0]); atomicAdd(&gnpos[pb].y, r[1]); atomicAdd(&gnpos[pb].z, r[2]);
+      atomicAdd(&gnrot[pb].x, r[3]); atomicAdd(&gnrot[pb].y, r[4]); atomicAdd(&gnrot[pb].z, r[5]); atomicAdd(&gnrot[pb].w, r[6]);
+      atomicAdd(&gpos[pb].x, r[7]); atomicAdd(&gpos[pb].y, r[8]); atomicAdd(&gpos[pb].z, r[9]);
+      atomicAdd(&grot[pb].x, r[10]); atomicAdd(&grot[pb].y, r[11]); atomicAdd(&grot[pb].z, r[12]); atomicAdd(&grot[pb].w, r[13]);
+    }
+  }
+  if (inr) {
+    if (live) {
+      V3 o = gv * (float)(1. / (double)mm.w);
+      ggrid[node] = make_float4(o.x, o.y, o.z, (-1.f / mm.w / mm.w) * dot(mv, gv));
+    } else {
+      ggrid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// p2g_grad + compute_svd_grad (integrator.cu:396-627, 110-186) fused; writes the complete gradient of state t
+template <int SVD>
+__global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict__ cur, const float4 *__restrict__ mat0,
+                                                 const float *__restrict__ yield, const float4 *__restrict__ ggrid,
+                                                 const float *__restrict__ gin, float *__restrict__ gout) {
+  int p = blockIdx.x * kT + threadIdx.x;
+  if (p >= kp.EN) return;
+  XVC s = load_xvc(cur, kp.EN, p);
+  M3 F = load_F(cur, kp.EN, p);
+  float4 m0 = __ldg(mat0 + p);
+  float yl = __ldg(yield + p);
+  Constit c;
+  constitutive<SVD>(s, F, m0, yl, kp, c);
+  float mu = m0.z, lam = m0.w, m_p = m0.x;
+  Stencil st = make_stencil_safe(s.x, kp);
+  V3 d0, d1, d2;
+  stencil_dw(st, kp.inv_dx, d0, d1, d2);
+  const float4 *gg = ggrid + (size_t)(p / kp.N) * kp.G;
+  M3 g_stress = mzero(), g_C = mzero();
+  V3 g_x = vzero(), g_v = vzero();
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      int row = ((st.bx + i) * kp.gy + st.by + j) * kp.gz + st.bz;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float wx = pick(st.w0, st.w1, st.w2, i, 0), wy = pick(st.w0, st.w1, st.w2, j, 1), wz = pick(st.w0, st.w1, st.w2, k, 2);
+        float N = wx * wy * wz;
+        V3 dpos = (v3((float)i, (float)j, (float)k) - st.fx) * kp.dx;
+        float4 t = __ldg(gg + row + k);
+        V3 ogv = v3(t.x, t.y, t.z);
+        V3 gN = v3(pick(d0, d1, d2, i, 0) * wy * wz, wx * pick(d0, d1, d2, j, 1) * wz, wx * wy * pick(d0, d1, d2, k, 2));
+        M3 tmp = outer(ogv, dpos);
+        g_stress += (N * c.scale) * tmp;
+        g_C += (N * m_p) * tmp;
+        g_v += (N * m_p) * ogv;
+        g_x += (t.w * m_p) * gN;
+        g_x += (dot(s.v, ogv) * m_p) * gN;
+        g_x += (-N) * mul_t(c.affine, ogv) + dot(mul(c.affine, dpos), ogv) * gN;
+      }
+    }
+  }
+  float4 part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by k_g2p_grad
+  g_x += v3(part.x, part.y, part.z);
+  M3 gF_next = load_F(gin, kp.EN, p);
+  M3 g_r = (-2.f * mu) * mul(g_stress, c.nF);
+  M3 g_U = mul(g_r, c.Vm);
+  M3 g_V = mul_tn(g_r, c.U);
+  M3 g_nF = gF_next + (2.f * mu) * (mul_tn(g_stress, c.nF - c.r) + mul(g_stress, c.nF));
+  float g_J = ((2 * c.J - 1) * lam) * trace(g_stress);
+  V3 g_sig = vzero();
+  M3 G = mzero();  // dL/dF~ accumulated directly
+  if (c.pl.plastic) {
+    const Plastic &pl = c.pl;
+    g_U += mul_diag(mul(g_nF, c.Vm), pl.ee);
+    g_V += mul_diag(mul_tn(g_nF, c.U), pl.ee);
+    V3 Fpart = diag(mul(mul_tn(c.U, g_nF), c.Vm));
+    V3 Jpart = v3(g_J * pl.ee.y * pl.ee.z, g_J * pl.ee.x * pl.ee.z, g_J * pl.ee.x * pl.ee.y);
+    V3 g_eps = pl.ee * (Jpart + Fpart);
+    V3 g_eh = (-pl.dg / pl.ehn) * g_eps;
+    float g_ehn = -dot(pl.eh / pl.ehn, g_eps) * (yl / (2 * mu)) / pl.ehn;
+    g_eh += (pl.eh / pl.ehn) * g_ehn;
+    float mean_g = (float)((double)(g_eh.x + g_eh.y + g_eh.z) / 3.);
+    g_eps += v3(g_eh.x - mean_g, g_eh.y - mean_g, g_eh.z - mean_g);
+    if (c.sigma.x >= 0.05) g_sig.x += g_eps.x / c.sigma.x;
+    if (c.sigma.y >= 0.05) g_sig.y += g_eps.y / c.sigma.y;
+    if (c.sigma.z >= 0.05) g_sig.z += g_eps.z / c.sigma.z;
+  } else {
+    g_sig += v3(g_J * c.sigma.y * c.sigma.z, g_J * c.sigma.x * c.sigma.z, g_J * c.sigma.x * c.sigma.y);
+    G = g_nF;
+  }
+  G += svd_adj(c.U, c.sigma, c.Vm, g_U, g_sig, g_V);
+  g_C += kp.dt * mul_nt(G, F);
+  M3 g_F = mul_tn(mdiag(1.f) + kp.dt * s.C, G);
+  store_xvc(gout, kp.EN, p, g_x, g_v, g_C);
+  store_F(gout, kp.EN, p, g_F);
+}
+
+// ---- layout conversion (original AoS order <-> sorted planes) --------------------------------------------------------
+__global__ void k_pack(int EN, const int *__restrict__ perm, const float *__restrict__ x, const float *__restrict__ v, const float *__restrict__ F,
+                       const float *__restrict__ C, float *slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= EN) return;
+  int s = perm[i];
+  if (x && v && C) {
+    store_xvc(slot, EN, i, ld_v3(x, s), ld_v3(v, s), ld_m3(C, s));
+  }
+  if (F) store_F(slot, EN, i, ld_m3(F, s));
+}
+__global__ void k_unpack(int EN, const int *__restrict__ perm, const float *__restrict__ slot, float *x, float *v, float *F, float *C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= EN) return;
+  int s = perm[i];
+  XVC a = load_xvc(slot, EN, i);
+  if (x) st_v3(x, s, a.x);
+  if (v) st_v3(v, s, a.v);
+  if (C) st_m3(C, s, a.C);
+  if (F) st_m3(F, s, load_F(slot, EN, i));
+}
+// slot += packed(values) for whichever of gx, gv, gF, gC is given
+__global__ void k_add_grad(int EN, const int *__restrict__ perm, const float *__restrict__ gx, const float *__restrict__ gv,
+                           const float *__restrict__ gF, const float *__restrict__ gC, float *slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= EN) return;
+  int s = perm[i];
+  XVC a = load_xvc(slot, EN, i);
+  if (gx) a.x += ld_v3(gx, s);
+  if (gv) a.v += ld_v3(gv, s);
+  if (gC) a.C += ld_m3(gC, s);
+  store_xvc(slot, EN, i, a.x, a.v, a.C);
+  if (gF) store_F(slot, EN, i, load_F(slot, EN, i) + ld_m3(gF, s));
+}
+__global__ void k_pack_mat(int EN, const int *__restrict__ perm, const float *__restrict__ mass, const float *__restrict__ vol,
+                           const float *__restrict__ mly, float4 *mat0, float *yield) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= EN) return;
+  int s = perm[i];
+  mat0[i] = make_float4(mass[s], vol[s], mly[3 * s], mly[3 * s + 1]);
+  yield[i] = mly[3 * s + 2];
+}
+__global__ void k_pad4(int n, const float *__restrict__ src, int w, float4 *dst) {  // (n, w<=4) floats -> float4
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < w; ++k) t[k] = src[(size_t)i * w + k];
+  dst[i] = make_float4(t[0], t[1], t[2], t[3]);
+}
+__global__ void k_unpad4(int n, const float4 *__restrict__ src, int w, float *dst, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 t = src[i];
+  float a[4] = {t.x, t.y, t.z, t.w};
+  for (int k = 0; k < w; ++k) dst[(size_t)i * w + k] = accumulate ? dst[(size_t)i * w + k] + a[k] : a[k];
+}
+__global__ void k_add4(int n, const float *__restrict__ src, int w, float4 *dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < w; ++k) t[k] = src[(size_t)i * w + k];
+  float4 d = dst[i];
+  dst[i] = make_float4(d.x + t[0], d.y + t[1], d.z + t[2], d.w + t[3]);
+}
+
+// compute_dist (integrator.cu:188-237) on the engine layout; dist is (E*N, nb) in ORIGINAL particle order
+__global__ void __launch_bounds__(kT) k_dist(KP kp, const int *__restrict__ perm, const float *__restrict__ slot, BodyTables bt, float *dist,
+                                             const float *__restrict__ gdist, float *gslot, float4 *gpos, float4 *grot, int need_grad) {
+  int p = blockIdx.x * kT + threadIdx.x;
+  bool live = p < kp.EN;
+  int env = live ? p / kp.N : 0, src = live ? perm[p] : 0;
+  V3 xp = vzero();
+  if (live) {
+    float4 a = plane4(slot, kp.EN, 0)[p];
+    xp = v3(a.x, a.y, a.z);
+  }
+  V3 g_x = vzero();
+  for (int b = 0; b < kp.nb; ++b) {
+    int pb = env * kp.nb + b;
+    V3 bx = v3f(bt.pos[pb]);
+    Q4 bq = q4f(bt.rot[pb]), tfsr = q4f(bt.tfsr[b]), sargs = q4f(bt.args[b]);
+    V3 gxb = xform_inv(bx, bq, xp);
+    if (!need_grad) {
+      if (live) dist[(size_t)src * kp.nb + b] = shape_sdf(tfsr, sargs, gxb);
+    } else {
+      V3 g_bx = vzero();
+      Q4 g_bq;
+      g_bq.w = g_bq.x = g_bq.y = g_bq.z = 0.f;
+      if (live) xform_inv_adj(bx, bq, xp, shape_grad(tfsr, sargs, gxb) * gdist[(size_t)src * kp.nb + b], g_bx, g_bq, g_x);
+      float r[7] = {g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z};
+      int env0 = __shfl_sync(0xffffffffu, env, 0);
+      if (__all_sync(0xffffffffu, !live || env == env0)) {  // whole warp in one environment: reduce, one atomic set
+#pragma unroll
+        for (int i = 0; i < 7; ++i) r[i] = warp_sum(r[i]);
+        if ((threadIdx.x & 31) == 0 && live) {
+          atomicAdd(&gpos[pb].x, r[0]); atomicAdd(&gpos[pb].y, r[1]); atomicAdd(&gpos[pb].z, r[2]);
+          atomicAdd(&grot[pb].x, r[3]); atomicAdd(&grot[pb].y, r[4]); atomicAdd(&grot[pb].z, r[5]); atomicAdd(&grot[pb].w, r[6]);
+        }
+      } else if (live) {
+        atomicAdd(&gpos[pb].x, r[0]); atomicAdd(&gpos[pb].y, r[1]); atomicAdd(&gpos[pb].z, r[2]);
+        atomicAdd(&grot[pb].x, r[3]); atomicAdd(&grot[pb].y, r[4]); atomicAdd(&grot[pb].z, r[5]); atomicAdd(&grot[pb].w, r[6]);
+      }
+    }
+  }
+  if (need_grad && live) {
+    float4 *o = plane4(gslot, kp.EN, 0) + p;
+    float4 t = *o;
+    *o = make_float4(t.x + g_x.x, t.y + g_x.y, t.z + g_x.z, t.w);
+  }
+}
+
+inline int nblk(long long n) { return (int)((n + kT - 1) / kT); }
+
+}  // namespace
+
+// ======================================================================================================= host side
+struct dd_sim {
+  dd_sim_config cfg;
+  KP kp;
+  int slots;                 // max_steps + 1
+  size_t slot_floats;        // 25 * ENp
+  float *ckpt = nullptr;     // slots * slot_floats
+  float *grad[2] = {nullptr, nullptr};
+  int grad_holds[2] = {-1, -1};
+  float4 *mat0 = nullptr;
+  float *yield = nullptr;
+  float4 *grid = nullptr, *grid_v = nullptr, *ggrid_v = nullptr, *ggrid = nullptr;
+  float4 *pos = nullptr, *rot = nullptr, *gpos = nullptr, *grot = nullptr;  // slots * E * nb
+  float4 *tfsr = nullptr, *args = nullptr;
+  float *cull = nullptr;
+  int *perm = nullptr;
+  float *stage = nullptr;    // 24 * EN floats (x|v|F|C in original AoS order) or E*N*nb for dist
+  size_t stage_floats = 0;
+  std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;
+  long long launches = 0;    // kernels launched (or replayed through graphs) since creation
+
+  float *slot(int f) const { return ckpt + (size_t)f * slot_floats; }
+  BodyTables tables(int f) const {
+    BodyTables bt;
+    size_t o = (size_t)f * kp.E * kp.nb, o1 = (size_t)(f + 1 < slots ? f + 1 : f) * kp.E * kp.nb;
+    bt.pos = pos + o; bt.rot = rot + o; bt.npos = pos + o1; bt.nrot = rot + o1;
+    bt.tfsr = tfsr; bt.args = args; bt.cull = cull;
+    return bt;
+  }
+};
+
+namespace {
+
+template <int SVD>
+void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st) {
+  const KP &kp = s->kp;
+  cudaMemsetAsync(s->grid, 0, sizeof(float4) * (size_t)kp.E * kp.G, st);
+  k_p2g<SVD, true><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
+  k_grid<<<nblk((long long)kp.E * kp.G), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
+  k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v);
+  s->launches += 3;
+}
+template <int SVD>
+void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st) {
+  const KP &kp = s->kp;
+  float *gin = s->grad[(f + 1) & 1], *gout = s->grad[f & 1];
+  size_t eg = (size_t)kp.E * kp.G, ep = (size_t)kp.E * kp.nb;
+  cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st);
+  cudaMemsetAsync(s->ggrid_v, 0, sizeof(float4) * eg, st);
+  k_p2g<SVD, false><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
+  k_grid<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
+  k_g2p_grad<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v, gin, gout, s->ggrid_v);
+  k_grid_grad<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->ggrid_v, s->ggrid, s->tables(f), s->gpos + (size_t)f * ep, s->grot + (size_t)f * ep,
+                                                   s->gpos + (size_t)(f + 1) * ep, s->grot + (size_t)(f + 1) * ep);
+  k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->mat0, s->yield, s->ggrid, gin, gout);
+  s->launches += 5;
+}
+
+// run `body` either directly or as a cached CUDA graph keyed by (kind, f0, n)
+template <class Fn>
+int run_graphed(dd_sim *s, int kind, int f0, int n, cudaStream_t st, long long launches_per_call, Fn body) {
+  if (!s->cfg.use_graphs) {
+    body(st);
+    DD_CUDA(cudaGetLastError());
+    return 0;
+  }
+  auto key = std::make_tuple(kind, f0, n);
+  auto it = s->graphs.find(key);
+  if (it == s->graphs.end()) {
+    cudaStream_t cap = st;
+    cudaStream_t tmp = nullptr;
+    if (cap == nullptr) {  // the legacy default stream cannot be captured
+      DD_CUDA(cudaStreamCreateWithFlags(&tmp, cudaStreamNonBlocking));
+      cap = tmp;
+    }
+    long long before = s->launches;
+    DD_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    body(cap);
+    cudaGraph_t graph = nullptr;
+    DD_CUDA(cudaStreamEndCapture(cap, &graph));
+    s->launches = before;
+    cudaGraphExec_t exec = nullptr;
+    DD_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    DD_CUDA(cudaGraphDestroy(graph));
+    if (tmp) DD_CUDA(cudaStreamDestroy(tmp));
+    it = s->graphs.emplace(key, exec).first;
+  }
+  DD_CUDA(cudaGraphLaunch(it->second, st));
+  s->launches += launches_per_call;
+  return 0;
+}
+
+int check_range(dd_sim *s, int f0, int n, const char *what) {
+  if (!s) return fail(std::string(what) + ": null simulator");
+  if (f0 < 0 || n < 0 || f0 + n >= s->slots) return fail(std::string(what) + ": substep range [" + std::to_string(f0) + ", " + std::to_string(f0 + n) + "] exceeds max_steps=" + std::to_string(s->slots - 1));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *dd_last_error(void) { return g_last_error.c_str(); }
+
+int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
+  if (!cfg || !out) return fail("dd_sim_create: null argument");
+  if (cfg->n_envs < 1 || cfg->n_particles < 1 || cfg->max_steps < 1) return fail("dd_sim_create: n_envs, n_particles, max_steps must be >= 1");
+  if (cfg->n_bodies < 0 || cfg->n_bodies > 64) return fail("dd_sim_create: n_bodies must be in [0, 64]");
+  if (cfg->grid_x < 8 || cfg->grid_y < 8 || cfg->grid_z < 8) return fail("dd_sim_create: grid must be at least 8^3");
+  if (((long long)cfg->grid_x * cfg->grid_y * cfg->grid_z) % 32 != 0) return fail("dd_sim_create: grid size must be a multiple of 32 nodes");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail("dd_sim_create: no CUDA device (dexdeform_b200 has no CPU fallback)");
+  dd_sim *s = new dd_sim();
+  s->cfg = *cfg;
+  KP &kp = s->kp;
+  kp.E = cfg->n_envs; kp.N = cfg->n_particles; kp.EN = kp.E * kp.N; kp.nb = cfg->n_bodies;
+  kp.gx = cfg->grid_x; kp.gy = cfg->grid_y; kp.gz = cfg->grid_z; kp.G = kp.gx * kp.gy * kp.gz;
+  kp.dx = cfg->dx; kp.inv_dx = 1.0f / cfg->dx; kp.dt = cfg->dt; kp.gf = cfg->ground_friction; kp.gh = cfg->ground_height;
+  kp.g0 = cfg->gravity[0]; kp.g1 = cfg->gravity[1]; kp.g2 = cfg->gravity[2];
+  s->slots = cfg->max_steps + 1;
+  size_t ENp = ((size_t)kp.EN + 3) / 4 * 4;
+  if (ENp != (size_t)kp.EN) { delete s; return fail("dd_sim_create: n_envs * n_particles must be a multiple of 4"); }
+  s->slot_floats = kPlaneFloats * ENp;
+  size_t eg = (size_t)kp.E * kp.G, ep = (size_t)kp.E * (kp.nb > 0 ? kp.nb : 1) * s->slots;
+#define DD_ALLOC(ptr, bytes)                                                                                   \
+  do {                                                                                                         \
+    cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                                                     \
+    if (e_ != cudaSuccess) { dd_sim_destroy(s); return fail(std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); } \
+    cudaMemset((ptr), 0, (bytes));                                                                             \
+  } while (0)
+  DD_ALLOC(s->ckpt, sizeof(float) * s->slot_floats * s->slots);
+  DD_ALLOC(s->grad[0], sizeof(float) * s->slot_floats);
+  DD_ALLOC(s->grad[1], sizeof(float) * s->slot_floats);
+  DD_ALLOC(s->mat0, sizeof(float4) * ENp);
+  DD_ALLOC(s->yield, sizeof(float) * ENp);
+  DD_ALLOC(s->grid, sizeof(float4) * eg);
+  DD_ALLOC(s->grid_v, sizeof(float4) * eg);
+  DD_ALLOC(s->ggrid_v, sizeof(float4) * eg);
+  DD_ALLOC(s->ggrid, sizeof(float4) * eg);
+  DD_ALLOC(s->pos, sizeof(float4) * ep);
+  DD_ALLOC(s->rot, sizeof(float4) * ep);
+  DD_ALLOC(s->gpos, sizeof(float4) * ep);
+  DD_ALLOC(s->grot, sizeof(float4) * ep);
+  DD_ALLOC(s->tfsr, sizeof(float4) * 64);
+  DD_ALLOC(s->args, sizeof(float4) * 64);
+  DD_ALLOC(s->cull, sizeof(float) * 64);
+  DD_ALLOC(s->perm, sizeof(int) * ENp);
+  s->stage_floats = (size_t)kp.EN * (24 > kp.nb ? 24 : kp.nb);
+  DD_ALLOC(s->stage, sizeof(float) * s->stage_floats);
+#undef DD_ALLOC
+  std::vector<int> ident(kp.EN);
+  for (int i = 0; i < kp.EN; ++i) ident[i] = i;
+  cudaMemcpy(s->perm, ident.data(), sizeof(int) * kp.EN, cudaMemcpyHostToDevice);
+  *out = s;
+  return 0;
+}
+
+void dd_sim_destroy(dd_sim *s) {
+  if (!s) return;
+  for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
+  void *ptrs[] = {s->ckpt, s->grad[0], s->grad[1], s->mat0, s->yield, s->grid, s->grid_v, s->ggrid_v, s->ggrid, s->pos, s->rot, s->gpos, s->grot,
+                  s->tfsr, s->args, s->cull, s->perm, s->stage};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  delete s;
+}
+
+long long dd_sim_launch_count(dd_sim *s) { return s ? s->launches : 0; }
+
+int dd_sim_set_material(dd_sim *s, const float *mass, const float *vol, const float *mu_lam_yield, cudaStream_t st) {
+  if (!s || !mass || !vol || !mu_lam_yield) return fail("dd_sim_set_material: null argument");
+  int EN = s->kp.EN;
+  float *a = s->stage, *b = a + EN, *c = b + EN;
+  DD_CUDA(cudaMemcpyAsync(a, mass, sizeof(float) * EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemcpyAsync(b, vol, sizeof(float) * EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemcpyAsync(c, mu_lam_yield, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  k_pack_mat<<<nblk(EN), kT, 0, st>>>(EN, s->perm, a, b, c, s->mat0, s->yield);
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dd_sim_set_bodies(dd_sim *s, const float *tfsr, const float *args) {
+  if (!s) return fail("dd_sim_set_bodies: null simulator");
+  int nb = s->kp.nb;
+  if (nb == 0) return 0;
+  if (!tfsr || !args) return fail("dd_sim_set_bodies: null argument");
+  std::vector<float> t(4 * nb), a(4 * nb), cull(nb);
+  DD_CUDA(cudaMemcpy(t.data(), tfsr, sizeof(float) * 4 * nb, cudaMemcpyDefault));
+  DD_CUDA(cudaMemcpy(a.data(), args, sizeof(float) * 4 * nb, cudaMemcpyDefault));
+  for (int b = 0; b < nb; ++b) {
+    // a node can only be active if dist < ln(10)/softness (or <= 0); dist >= |p| - R_bound - round
+    float type = t[4 * b], soft = t[4 * b + 2], round = t[4 * b + 3];
+    float rb = ((int)floorf(type + 0.1f) == 0) ? sqrtf(a[4 * b] * a[4 * b] + a[4 * b + 1] * a[4 * b + 1] + a[4 * b + 2] * a[4 * b + 2])
+                                               : fabsf(a[4 * b]) + fabsf(a[4 * b + 1]);
+    cull[b] = (rb + fabsf(round) + (soft > 0 ? 2.5f / soft : 0.f)) * 1.001f + 1e-5f;
+  }
+  DD_CUDA(cudaMemcpy(s->tfsr, t.data(), sizeof(float) * 4 * nb, cudaMemcpyHostToDevice));
+  DD_CUDA(cudaMemcpy(s->args, a.data(), sizeof(float) * 4 * nb, cudaMemcpyHostToDevice));
+  DD_CUDA(cudaMemcpy(s->cull, cull.data(), sizeof(float) * nb, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const float *F, const float *C, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_set_state")) return 1;
+  if (!x || !v || !F || !C) return fail("dd_sim_set_state: x, v, F, C are all required");
+  int EN = s->kp.EN;
+  float *sx = s->stage, *sv = sx + 3 * (size_t)EN, *sF = sv + 3 * (size_t)EN, *sC = sF + 9 * (size_t)EN;
+  DD_CUDA(cudaMemcpyAsync(sx, x, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemcpyAsync(sv, v, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemcpyAsync(sF, F, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemcpyAsync(sC, C, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  k_pack<<<nblk(EN), kT, 0, st>>>(EN, s->perm, sx, sv, sF, sC, s->slot(f));
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dd_sim_get_state(dd_sim *s, int f, float *x, float *v, float *F, float *C, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_get_state")) return 1;
+  int EN = s->kp.EN;
+  float *sx = s->stage, *sv = sx + 3 * (size_t)EN, *sF = sv + 3 * (size_t)EN, *sC = sF + 9 * (size_t)EN;
+  k_unpack<<<nblk(EN), kT, 0, st>>>(EN, s->perm, s->slot(f), x ? sx : nullptr, v ? sv : nullptr, F ? sF : nullptr, C ? sC : nullptr);
+  DD_CUDA(cudaGetLastError());
+  if (x) DD_CUDA(cudaMemcpyAsync(x, sx, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  if (v) DD_CUDA(cudaMemcpyAsync(v, sv, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  if (F) DD_CUDA(cudaMemcpyAsync(F, sF, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  if (C) DD_CUDA(cudaMemcpyAsync(C, sC, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dd_sim_set_poses(dd_sim *s, int f0, int count, const float *pos, const float *rot, cudaStream_t st) {
+  if (!s) return fail("dd_sim_set_poses: null simulator");
+  if (s->kp.nb == 0 || count == 0) return 0;
+  if (f0 < 0 || count < 0 || f0 + count > s->slots) return fail("dd_sim_set_poses: slot range out of bounds");
+  if (!pos || !rot) return fail("dd_sim_set_poses: null argument");
+  size_t n = (size_t)count * s->kp.E * s->kp.nb;
+  if (7 * n > s->stage_floats) return fail("dd_sim_set_poses: too many poses for the staging buffer; upload in smaller chunks");
+  float *sp = s->stage, *sr = sp + 3 * n;
+  DD_CUDA(cudaMemcpyAsync(sp, pos, sizeof(float) * 3 * n, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemcpyAsync(sr, rot, sizeof(float) * 4 * n, cudaMemcpyDefault, st));
+  size_t o = (size_t)f0 * s->kp.E * s->kp.nb;
+  k_pad4<<<nblk((long long)n), kT, 0, st>>>((int)n, sp, 3, s->pos + o);
+  k_pad4<<<nblk((long long)n), kT, 0, st>>>((int)n, sr, 4, s->rot + o);
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dd_sim_forward(dd_sim *s, int f0, int n, cudaStream_t st) {
+  if (check_range(s, f0, n, "dd_sim_forward")) return 1;
+  if (n == 0) return 0;
+  size_t ep = (size_t)s->kp.E * s->kp.nb;
+  auto body = [&](cudaStream_t q) {
+    // reference: states[f+i+1].clear_grad in the forward pass (mpm/simulator.py:570-571) -- pose gradients only here,
+    // particle gradients are overwritten, not accumulated, by the adjoint kernels
+    if (ep) {
+      cudaMemsetAsync(s->gpos + (size_t)(f0 + 1) * ep, 0, sizeof(float4) * ep * n, q);
+      cudaMemsetAsync(s->grot + (size_t)(f0 + 1) * ep, 0, sizeof(float4) * ep * n, q);
+    }
+    for (int f = f0; f < f0 + n; ++f) {
+      if (s->cfg.svd_mode == 0) enqueue_forward_substep<0>(s, f, q); else enqueue_forward_substep<1>(s, f, q);
+    }
+  };
+  return run_graphed(s, 0, f0, n, st, 3LL * n, body);
+}
+
+int dd_sim_zero_grad(dd_sim *s, int f, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_zero_grad")) return 1;
+  size_t ep = (size_t)s->kp.E * s->kp.nb;
+  DD_CUDA(cudaMemsetAsync(s->grad[f & 1], 0, sizeof(float) * s->slot_floats, st));
+  s->grad_holds[f & 1] = f;
+  if (ep) {
+    DD_CUDA(cudaMemsetAsync(s->gpos + (size_t)f * ep, 0, sizeof(float4) * ep, st));
+    DD_CUDA(cudaMemsetAsync(s->grot + (size_t)f * ep, 0, sizeof(float4) * ep, st));
+  }
+  return 0;
+}
+
+int dd_sim_add_state_grad(dd_sim *s, int f, const float *gx, const float *gv, const float *gF, const float *gC, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_add_state_grad")) return 1;
+  if (s->grad_holds[f & 1] != f) return fail("dd_sim_add_state_grad: gradient slot does not hold state " + std::to_string(f) + " (call dd_sim_zero_grad or run the backward pass down to it first)");
+  int EN = s->kp.EN;
+  float *sx = s->stage, *sv = sx + 3 * (size_t)EN, *sF = sv + 3 * (size_t)EN, *sC = sF + 9 * (size_t)EN;
+  if (gx) DD_CUDA(cudaMemcpyAsync(sx, gx, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  if (gv) DD_CUDA(cudaMemcpyAsync(sv, gv, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  if (gF) DD_CUDA(cudaMemcpyAsync(sF, gF, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  if (gC) DD_CUDA(cudaMemcpyAsync(sC, gC, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  k_add_grad<<<nblk(EN), kT, 0, st>>>(EN, s->perm, gx ? sx : nullptr, gv ? sv : nullptr, gF ? sF : nullptr, gC ? sC : nullptr, s->grad[f & 1]);
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dd_sim_get_state_grad(dd_sim *s, int f, float *gx, float *gv, float *gF, float *gC, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_get_state_grad")) return 1;
+  if (s->grad_holds[f & 1] != f) return fail("dd_sim_get_state_grad: gradient slot does not hold state " + std::to_string(f));
+  int EN = s->kp.EN;
+  float *sx = s->stage, *sv = sx + 3 * (size_t)EN, *sF = sv + 3 * (size_t)EN, *sC = sF + 9 * (size_t)EN;
+  k_unpack<<<nblk(EN), kT, 0, st>>>(EN, s->perm, s->grad[f & 1], gx ? sx : nullptr, gv ? sv : nullptr, gF ? sF : nullptr, gC ? sC : nullptr);
+  DD_CUDA(cudaGetLastError());
+  if (gx) DD_CUDA(cudaMemcpyAsync(gx, sx, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  if (gv) DD_CUDA(cudaMemcpyAsync(gv, sv, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
+  if (gF) DD_CUDA(cudaMemcpyAsync(gF, sF, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  if (gC) DD_CUDA(cudaMemcpyAsync(gC, sC, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dd_sim_backward(dd_sim *s, int f0, int n, cudaStream_t st) {
+  if (check_range(s, f0, n, "dd_sim_backward")) return 1;
+  if (n == 0) return 0;
+  if (s->grad_holds[(f0 + n) & 1] != f0 + n) return fail("dd_sim_backward: no gradient seeded for state " + std::to_string(f0 + n) + " (dd_sim_zero_grad + dd_sim_add_state_grad)");
+  auto body = [&](cudaStream_t q) {
+    for (int f = f0 + n - 1; f >= f0; --f) {
+      if (s->cfg.svd_mode == 0) enqueue_backward_substep<0>(s, f, q); else enqueue_backward_substep<1>(s, f, q);
+    }
+  };
+  int rc = run_graphed(s, 1, f0, n, st, 5LL * n, body);
+  if (rc) return rc;
+  s->grad_holds[f0 & 1] = f0;
+  s->grad_holds[(f0 + 1) & 1] = n >= 1 ? f0 + 1 : s->grad_holds[(f0 + 1) & 1];
+  return 0;
+}
+
+int dd_sim_get_pose_grads(dd_sim *s, int f0, int count, float *gpos, float *grot, cudaStream_t st) {
+  if (!s) return fail("dd_sim_get_pose_grads: null simulator");
+  if (s->kp.nb == 0 || count == 0) return 0;
+  if (f0 < 0 || count < 0 || f0 + count > s->slots) return fail("dd_sim_get_pose_grads: slot range out of bounds");
+  size_t n = (size_t)count * s->kp.E * s->kp.nb, o = (size_t)f0 * s->kp.E * s->kp.nb;
+  if (7 * n > s->stage_floats) return fail("dd_sim_get_pose_grads: too many poses for the staging buffer; download in smaller chunks");
+  float *sp = s->stage, *sr = sp + 3 * n;
+  k_unpad4<<<nblk((long long)n), kT, 0, st>>>((int)n, s->gpos + o, 3, sp, 0);
+  k_unpad4<<<nblk((long long)n), kT, 0, st>>>((int)n, s->grot + o, 4, sr, 0);
+  DD_CUDA(cudaGetLastError());
+  if (gpos) DD_CUDA(cudaMemcpyAsync(gpos, sp, sizeof(float) * 3 * n, cudaMemcpyDefault, st));
+  if (grot) DD_CUDA(cudaMemcpyAsync(grot, sr, sizeof(float) * 4 * n, cudaMemcpyDefault, st));
+  DD_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dd_sim_add_pose_grads(dd_sim *s, int f, const float *gpos, const float *grot, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_add_pose_grads")) return 1;
+  if (s->kp.nb == 0) return 0;
+  size_t n = (size_t)s->kp.E * s->kp.nb, o = (size_t)f * n;
+  float *sp = s->stage, *sr = sp + 3 * n;
+  if (gpos) {
+    DD_CUDA(cudaMemcpyAsync(sp, gpos, sizeof(float) * 3 * n, cudaMemcpyDefault, st));
+    k_add4<<<nblk((long long)n), kT, 0, st>>>((int)n, sp, 3, s->gpos + o);
+  }
+  if (grot) {
+    DD_CUDA(cudaMemcpyAsync(sr, grot, sizeof(float) * 4 * n, cudaMemcpyDefault, st));
+    k_add4<<<nblk((long long)n), kT, 0, st>>>((int)n, sr, 4, s->grot + o);
+  }
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dd_sim_compute_dist(dd_sim *s, int f, float *dist, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_compute_dist")) return 1;
+  if (s->kp.nb == 0) return 0;
+  if (!dist) return fail("dd_sim_compute_dist: null output");
+  size_t n = (size_t)s->kp.EN * s->kp.nb;
+  k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->tables(f), s->stage, nullptr, nullptr, nullptr, nullptr, 0);
+  DD_CUDA(cudaGetLastError());
+  DD_CUDA(cudaMemcpyAsync(dist, s->stage, sizeof(float) * n, cudaMemcpyDefault, st));
+  DD_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dd_sim_compute_dist_grad(dd_sim *s, int f, const float *dist_grad, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_compute_dist_grad")) return 1;
+  if (s->kp.nb == 0) return 0;
+  if (!dist_grad) return fail("dd_sim_compute_dist_grad: null argument");
+  if (s->grad_holds[f & 1] != f) return fail("dd_sim_compute_dist_grad: gradient slot does not hold state " + std::to_string(f));
+  size_t n = (size_t)s->kp.EN * s->kp.nb, ep = (size_t)s->kp.E * s->kp.nb;
+  DD_CUDA(cudaMemcpyAsync(s->stage, dist_grad, sizeof(float) * n, cudaMemcpyDefault, st));
+  k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->tables(f), nullptr, s->stage, s->grad[f & 1], s->gpos + (size_t)f * ep,
+                                        s->grot + (size_t)f * ep, 1);
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dd_sim_sync(dd_sim *s, cudaStream_t st) {
+  if (!s) return fail("dd_sim_sync: null simulator");
+  DD_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -271,7 +271,7 @@ DD_DEV void qr_givens64(double a1, double a2, double &ch, double &sh) {
   double w = rsqrt(ch * ch + sh * sh);
   ch *= w; sh *= w;
 }
-__device__ __noinline__ void svd3_f64(const M3 &A, M3 &U, V3 &sig, M3 &Vo) {
+static __device__ __noinline__ void svd3_f64(const M3 &A, M3 &U, V3 &sig, M3 &Vo) {
   double a11 = A.a00, a12 = A.a01, a13 = A.a02, a21 = A.a10, a22 = A.a11, a23 = A.a12, a31 = A.a20, a32 = A.a21, a33 = A.a22;
   double s11 = a11 * a11 + a21 * a21 + a31 * a31, s21 = a12 * a11 + a22 * a21 + a32 * a31, s22 = a12 * a12 + a22 * a22 + a32 * a32;
   double s31 = a13 * a11 + a23 * a21 + a33 * a31, s32 = a13 * a12 + a23 * a22 + a33 * a32, s33 = a13 * a13 + a23 * a23 + a33 * a33;
@@ -330,6 +330,109 @@ __device__ __noinline__ void svd3_f64(const M3 &A, M3 &U, V3 &sig, M3 &Vo) {
   U.a22 = (float)((-1 + 2 * sh22) * (-1 + 2 * sh32));
   Vo = m3((float)v11, (float)v12, (float)v13, (float)v21, (float)v22, (float)v23, (float)v31, (float)v32, (float)v33);
   sig = v3((float)b11, (float)r22, (float)r33);
+}
+
+// (2) svd3_f32: the production SVD.  Same structure (Jacobi on A^T A with quaternion accumulation, column sort,
+//     Givens QR) but entirely in fp32 registers with hardware rsqrt, NSWEEP sweeps, and a re-normalised quaternion.
+//     Accuracy is measured in tests (|U S V^T - A|, orthogonality, sigma vs fp64) -- a few fp32 ulp for the
+//     well-conditioned deformation gradients of this path.  ~3.5x fewer instructions than (1) and none of them fp64.
+#ifdef __CUDA_ARCH__
+#define DD_RSQRT(x) rsqrtf(x)
+#else
+#define DD_RSQRT(x) (1.0f / sqrtf(x))
+#endif
+#define DD_HD __host__ __device__ __forceinline__
+DD_HD void jacobi32(float &s11, float &s21, float &s22, float &s31, float &s32, float &s33, float &qx, float &qy, float &qz, float &qw) {
+  // approximate Givens half-angle (McAdams et al. 2011, Alg. 2): (ch, sh) ~ (2(s11 - s22), s21), clamped to pi/8 steps
+  float ch = 2.f * (s11 - s22), sh = s21;
+  bool b = 5.82842712474619f * sh * sh < ch * ch;
+  float w = DD_RSQRT(ch * ch + sh * sh);
+  ch = b ? w * ch : 0.9238795325112867f;
+  sh = b ? w * sh : 0.3826834323650897f;
+  // rotation (a, b) = (cos, sin) of the full angle; (ch, sh) is a unit vector so no rescale is needed
+  float a = ch * ch - sh * sh, bb = 2.f * sh * ch;
+  float t1 = -bb * s11 + a * s21, t2 = -bb * s21 + a * s22, u1 = a * s11 + bb * s21, u2 = a * s21 + bb * s22;
+  float n11 = a * u1 + bb * u2, n21 = a * t1 + bb * t2, n22 = -bb * t1 + a * t2;
+  float n31 = a * s31 + bb * s32, n32 = -bb * s31 + a * s32, n33 = s33;
+  float tx = qx * sh, ty = qy * sh, tz = qz * sh;
+  sh *= qw;
+  qx *= ch; qy *= ch; qz *= ch; qw *= ch;
+  qz += sh; qw -= tz; qx += ty; qy -= tx;
+  s11 = n22; s21 = n32; s22 = n33; s31 = n21; s32 = n31; s33 = n11;
+}
+DD_HD void cswap32(bool c, float &x, float &y) { float z = x; x = c ? y : x; y = c ? z : y; }
+DD_HD void cnswap32(bool c, float &x, float &y) { float z = -x; x = c ? y : x; y = c ? z : y; }
+DD_HD void qr_givens32(float a1, float a2, float &ch, float &sh) {
+  float r2 = a1 * a1 + a2 * a2;
+  float rho = r2 * DD_RSQRT(fmaxf(r2, 1e-37f));
+  sh = rho > 1e-6f ? a2 : 0.f;
+  ch = fabsf(a1) + fmaxf(rho, 1e-6f);
+  cswap32(a1 < 0.f, sh, ch);
+  float w = DD_RSQRT(ch * ch + sh * sh);
+  ch *= w; sh *= w;
+}
+template <int NSWEEP = 5>
+DD_HD void svd3_f32(const M3 &A, M3 &U, V3 &sig, M3 &Vo) {
+  float s11 = A.a00 * A.a00 + A.a10 * A.a10 + A.a20 * A.a20, s21 = A.a01 * A.a00 + A.a11 * A.a10 + A.a21 * A.a20;
+  float s22 = A.a01 * A.a01 + A.a11 * A.a11 + A.a21 * A.a21, s31 = A.a02 * A.a00 + A.a12 * A.a10 + A.a22 * A.a20;
+  float s32 = A.a02 * A.a01 + A.a12 * A.a11 + A.a22 * A.a21, s33 = A.a02 * A.a02 + A.a12 * A.a12 + A.a22 * A.a22;
+  float qx = 0.f, qy = 0.f, qz = 0.f, qw = 1.f;
+#pragma unroll
+  for (int it = 0; it < NSWEEP; ++it) {
+    jacobi32(s11, s21, s22, s31, s32, s33, qx, qy, qz, qw);
+    jacobi32(s11, s21, s22, s31, s32, s33, qy, qz, qx, qw);
+    jacobi32(s11, s21, s22, s31, s32, s33, qz, qx, qy, qw);
+  }
+  {
+    float n = DD_RSQRT(qx * qx + qy * qy + qz * qz + qw * qw);
+    qx *= n; qy *= n; qz *= n; qw *= n;
+  }
+  float qxx = qx * qx, qyy = qy * qy, qzz = qz * qz, qxz = qx * qz, qxy = qx * qy, qyz = qy * qz, qwx = qw * qx, qwy = qw * qy, qwz = qw * qz;
+  float v11 = 1.f - 2.f * (qyy + qzz), v12 = 2.f * (qxy - qwz), v13 = 2.f * (qxz + qwy);
+  float v21 = 2.f * (qxy + qwz), v22 = 1.f - 2.f * (qxx + qzz), v23 = 2.f * (qyz - qwx);
+  float v31 = 2.f * (qxz - qwy), v32 = 2.f * (qyz + qwx), v33 = 1.f - 2.f * (qxx + qyy);
+  float b11 = A.a00 * v11 + A.a01 * v21 + A.a02 * v31, b12 = A.a00 * v12 + A.a01 * v22 + A.a02 * v32, b13 = A.a00 * v13 + A.a01 * v23 + A.a02 * v33;
+  float b21 = A.a10 * v11 + A.a11 * v21 + A.a12 * v31, b22 = A.a10 * v12 + A.a11 * v22 + A.a12 * v32, b23 = A.a10 * v13 + A.a11 * v23 + A.a12 * v33;
+  float b31 = A.a20 * v11 + A.a21 * v21 + A.a22 * v31, b32 = A.a20 * v12 + A.a21 * v22 + A.a22 * v32, b33 = A.a20 * v13 + A.a21 * v23 + A.a22 * v33;
+  {
+    float r1 = b11 * b11 + b21 * b21 + b31 * b31, r2 = b12 * b12 + b22 * b22 + b32 * b32, r3 = b13 * b13 + b23 * b23 + b33 * b33;
+    bool c = r1 < r2;
+    cnswap32(c, b11, b12); cnswap32(c, v11, v12); cnswap32(c, b21, b22); cnswap32(c, v21, v22); cnswap32(c, b31, b32); cnswap32(c, v31, v32);
+    cswap32(c, r1, r2);
+    c = r1 < r3;
+    cnswap32(c, b11, b13); cnswap32(c, v11, v13); cnswap32(c, b21, b23); cnswap32(c, v21, v23); cnswap32(c, b31, b33); cnswap32(c, v31, v33);
+    cswap32(c, r1, r3);
+    c = r2 < r3;
+    cnswap32(c, b12, b13); cnswap32(c, v12, v13); cnswap32(c, b22, b23); cnswap32(c, v22, v23); cnswap32(c, b32, b33); cnswap32(c, v32, v33);
+  }
+  float ch1, sh1, ch2, sh2, ch3, sh3, ca, cb;
+  qr_givens32(b11, b21, ch1, sh1);
+  ca = 1.f - 2.f * sh1 * sh1; cb = 2.f * ch1 * sh1;
+  float r11 = ca * b11 + cb * b21, r12 = ca * b12 + cb * b22, r13 = ca * b13 + cb * b23;
+  float r21 = -cb * b11 + ca * b21, r22 = -cb * b12 + ca * b22, r23 = -cb * b13 + ca * b23;
+  float r31 = b31, r32 = b32, r33 = b33;
+  (void)r21;
+  qr_givens32(r11, r31, ch2, sh2);
+  ca = 1.f - 2.f * sh2 * sh2; cb = 2.f * ch2 * sh2;
+  b11 = ca * r11 + cb * r31;
+  b22 = r22; b23 = r23;
+  b32 = -cb * r12 + ca * r32; b33 = -cb * r13 + ca * r33;
+  qr_givens32(b22, b32, ch3, sh3);
+  ca = 1.f - 2.f * sh3 * sh3; cb = 2.f * ch3 * sh3;
+  r22 = ca * b22 + cb * b32;
+  r33 = -cb * b23 + ca * b33;
+  float sh12 = sh1 * sh1, sh22 = sh2 * sh2, sh32 = sh3 * sh3;
+  U.a00 = (-1.f + 2.f * sh12) * (-1.f + 2.f * sh22);
+  U.a01 = 4.f * ch2 * ch3 * (-1.f + 2.f * sh12) * sh2 * sh3 + 2.f * ch1 * sh1 * (-1.f + 2.f * sh32);
+  U.a02 = 4.f * ch1 * ch3 * sh1 * sh3 - 2.f * ch2 * (-1.f + 2.f * sh12) * sh2 * (-1.f + 2.f * sh32);
+  U.a10 = 2.f * ch1 * sh1 * (1.f - 2.f * sh22);
+  U.a11 = -8.f * ch1 * ch2 * ch3 * sh1 * sh2 * sh3 + (-1.f + 2.f * sh12) * (-1.f + 2.f * sh32);
+  U.a12 = -2.f * ch3 * sh3 + 4.f * sh1 * (ch3 * sh1 * sh3 + ch1 * ch2 * sh2 * (-1.f + 2.f * sh32));
+  U.a20 = 2.f * ch2 * sh2;
+  U.a21 = 2.f * ch3 * (1.f - 2.f * sh22) * sh3;
+  U.a22 = (-1.f + 2.f * sh22) * (-1.f + 2.f * sh32);
+  Vo.a00 = v11; Vo.a01 = v12; Vo.a02 = v13; Vo.a10 = v21; Vo.a11 = v22; Vo.a12 = v23; Vo.a20 = v31; Vo.a21 = v32; Vo.a22 = v33;
+  sig.x = b11; sig.y = r22; sig.z = r33;
 }
 
 // ---------------------------------------------------------------------------------------------- constitutive model

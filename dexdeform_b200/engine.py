@@ -1,0 +1,152 @@
+"""``FusedSim`` -- thin Python handle on the fused engine (ABI-2).  No arithmetic happens here: every method is one
+C-ABI call.  Arrays may be numpy arrays (host) or torch CUDA tensors (device); both are passed as raw pointers."""
+import ctypes
+
+import numpy as np
+
+from .engine_abi import dd_sim_config
+from .types import lib as _default_lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], "float32 C-contiguous arrays only"
+        return a.ctypes.data
+    # torch tensor
+    assert a.dtype.is_floating_point and a.element_size() == 4 and a.is_contiguous()
+    return a.data_ptr()
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class FusedSim:
+    def __init__(self, n_envs, n_particles, n_bodies, grid_dim, dx, dt, max_steps, ground_friction=0.0, ground_height=3.0,
+                 gravity=(0.0, -30.0, 0.0), svd_mode=1, use_graphs=True, library=None, stream=None):
+        self.lib = library if library is not None else _default_lib
+        self.E, self.N, self.nb = int(n_envs), int(n_particles), int(n_bodies)
+        self.grid_dim = tuple(int(g) for g in grid_dim)
+        self.max_steps = int(max_steps)
+        self.dx, self.dt = float(dx), float(dt)
+        self.stream = stream  # raw cudaStream_t (int) or None for the legacy default stream
+        cfg = dd_sim_config(self.E, self.N, self.nb, *self.grid_dim, self.max_steps, self.dx, self.dt, float(ground_friction),
+                            float(ground_height), (ctypes.c_float * 3)(*[float(g) for g in gravity]), int(svd_mode), int(bool(use_graphs)))
+        handle = ctypes.c_void_p()
+        self._h = None
+        self._check(self.lib.dd_sim_create(ctypes.byref(cfg), ctypes.byref(handle)))
+        self._h = handle
+
+    @classmethod
+    def from_scene(cls, scene, n_envs=1, max_steps=None, **kw):
+        sim = cls(n_envs, scene["n"], scene["nb"], scene["grid_dim"], scene["dx"], scene["dt"],
+                  max_steps if max_steps is not None else scene["steps"], scene["ground_friction"], scene["ground_height"],
+                  scene["gravity"].reshape(3), **kw)
+        E = n_envs
+        tile = lambda a: np.ascontiguousarray(np.broadcast_to(a[None], (E,) + a.shape), dtype=np.float32)
+        sim.set_material(tile(scene["mass"]), tile(scene["vol"]), tile(scene["mu_lam_yield"]))
+        if scene["nb"]:
+            sim.set_bodies(scene["tfsr"], scene["args"])
+            cnt = min(len(scene["pos"]), sim.max_steps + 1)
+            pos = np.ascontiguousarray(np.broadcast_to(scene["pos"][:cnt, None], (cnt, E) + scene["pos"].shape[1:]), dtype=np.float32)
+            rot = np.ascontiguousarray(np.broadcast_to(scene["rot"][:cnt, None], (cnt, E) + scene["rot"].shape[1:]), dtype=np.float32)
+            sim.set_poses(0, pos, rot)
+        sim.set_state(0, tile(scene["x"]), tile(scene["v"]), tile(scene["F"]), tile(scene["C"]))
+        return sim
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.dd_last_error().decode())
+
+    def close(self):
+        if self._h is not None:
+            self.lib.dd_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup
+    def set_material(self, mass, vol, mu_lam_yield):
+        self._check(self.lib.dd_sim_set_material(self._h, _ptr(mass), _ptr(vol), _ptr(mu_lam_yield), self.stream))
+        self.sync()
+
+    def set_bodies(self, tfsr, args):
+        tfsr, args = np.ascontiguousarray(tfsr, np.float32), np.ascontiguousarray(args, np.float32)
+        self._check(self.lib.dd_sim_set_bodies(self._h, _ptr(tfsr), _ptr(args)))
+
+    def set_state(self, f, x, v, F, C):
+        self._check(self.lib.dd_sim_set_state(self._h, f, _ptr(x), _ptr(v), _ptr(F), _ptr(C), self.stream))
+        self.sync()  # host arrays may be released by the caller
+
+    def set_poses(self, f0, pos, rot):
+        """pos (count, E, nb, 3), rot (count, E, nb, 4 wxyz) for slots f0 .. f0+count-1."""
+        count = pos.shape[0]
+        chunk = max(1, (self.E * self.N * 24) // (7 * self.E * max(self.nb, 1)))
+        for c0 in range(0, count, chunk):
+            c1 = min(count, c0 + chunk)
+            p, r = pos[c0:c1], rot[c0:c1]
+            if isinstance(p, np.ndarray):
+                p, r = np.ascontiguousarray(p, np.float32), np.ascontiguousarray(r, np.float32)
+            self._check(self.lib.dd_sim_set_poses(self._h, f0 + c0, c1 - c0, _ptr(p), _ptr(r), self.stream))
+            if isinstance(p, np.ndarray):
+                self.sync()
+
+    # ---- simulation
+    def forward(self, f0, n):
+        self._check(self.lib.dd_sim_forward(self._h, f0, n, self.stream))
+
+    def backward(self, f0, n):
+        self._check(self.lib.dd_sim_backward(self._h, f0, n, self.stream))
+
+    def zero_grad(self, f):
+        self._check(self.lib.dd_sim_zero_grad(self._h, f, self.stream))
+
+    def add_state_grad(self, f, gx=None, gv=None, gF=None, gC=None):
+        self._check(self.lib.dd_sim_add_state_grad(self._h, f, _ptr(gx), _ptr(gv), _ptr(gF), _ptr(gC), self.stream))
+        self.sync()
+
+    def sync(self):
+        self._check(self.lib.dd_sim_sync(self._h, self.stream))
+
+    def launch_count(self):
+        return int(self.lib.dd_sim_launch_count(self._h))
+
+    # ---- readback (numpy, original particle order)
+    def get_state(self, f, names=("x", "v", "F", "C")):
+        shp = dict(x=3, v=3, F=9, C=9)
+        out = {k: np.empty((self.E, self.N, shp[k]), np.float32) for k in names}
+        self._check(self.lib.dd_sim_get_state(self._h, f, _ptr(out.get("x")), _ptr(out.get("v")), _ptr(out.get("F")), _ptr(out.get("C")), self.stream))
+        return out
+
+    def get_state_grad(self, f, names=("x", "v", "F", "C")):
+        shp = dict(x=3, v=3, F=9, C=9)
+        out = {k: np.empty((self.E, self.N, shp[k]), np.float32) for k in names}
+        self._check(self.lib.dd_sim_get_state_grad(self._h, f, _ptr(out.get("x")), _ptr(out.get("v")), _ptr(out.get("F")), _ptr(out.get("C")), self.stream))
+        return out
+
+    def get_pose_grads(self, f0, count):
+        gp = np.empty((count, self.E, self.nb, 3), np.float32)
+        gr = np.empty((count, self.E, self.nb, 4), np.float32)
+        if self.nb:
+            self._check(self.lib.dd_sim_get_pose_grads(self._h, f0, count, _ptr(gp), _ptr(gr), self.stream))
+        return gp, gr
+
+    def add_pose_grads(self, f, gpos=None, grot=None):
+        self._check(self.lib.dd_sim_add_pose_grads(self._h, f, _ptr(gpos), _ptr(grot), self.stream))
+        self.sync()
+
+    def compute_dist(self, f):
+        d = np.empty((self.E, self.N, self.nb), np.float32)
+        if self.nb:
+            self._check(self.lib.dd_sim_compute_dist(self._h, f, _ptr(d), self.stream))
+        return d
+
+    def compute_dist_grad(self, f, dist_grad):
+        self._check(self.lib.dd_sim_compute_dist_grad(self._h, f, _ptr(np.ascontiguousarray(dist_grad, np.float32)), self.stream))
+        self.sync()

@@ -110,6 +110,52 @@ void particle_sdf(void *volume, void *particle_x, void *particle_color, void *bb
 dd_texture_resources create_volume(float *data, int x, int y, int z);
 void destroy_volume(dd_texture_resources tex);
 
+
+/* ------------------------------------------------------------------------------------------------ ABI-2
+ * Fused, batched engine.  One dd_sim owns E independent environments of N particles each (same grid, same primitive
+ * shapes, per-environment poses), a ring of per-substep state checkpoints in HBM (slot f = state after f substeps;
+ * what mpm/simulator.py:206 keeps as states[f]) and two ping-pong gradient slots.  Every function returns 0 on
+ * success and non-zero on failure with a message in dd_last_error().  Array arguments may be host or device pointers
+ * (cudaMemcpyDefault); particle arrays are in the caller's ORIGINAL particle order with the reference's AoS layouts,
+ * shaped (E, N, 3|9); pose arrays are (count, E, n_bodies, 3|4 wxyz).  Work is enqueued on `stream`.
+ *
+ * Replaces, for E environments at once: MPMSimulator.substep / substep_grad (mpm/simulator.py:561-585), set_pose
+ * (:553-559), State.set_state/get_state (:118-134), get_dists (:294-321) and the gradient plumbing of
+ * GradModel.set_obs_grad / diff_forward.backward (mpm/torch_wrapper.py:79-141). */
+typedef struct dd_sim dd_sim;
+typedef struct {
+  int n_envs;          /* E */
+  int n_particles;     /* N per environment; E*N must be a multiple of 4 */
+  int n_bodies;        /* primitives per environment, <= 64 */
+  int grid_x, grid_y, grid_z;
+  int max_steps;       /* checkpoint slots - 1 */
+  float dx, dt;
+  float ground_friction, ground_height;   /* mpm/simulator.py:490-494 */
+  float gravity[3];    /* as uploaded by the reference, i.e. cfg.gravity * 30 (mpm/simulator.py:385) */
+  int svd_mode;        /* 0: reference-order fp64 Jacobi SVD, 1: fp32 in-register SVD (production) */
+  int use_graphs;      /* capture forward/backward ranges into CUDA graphs, cached per (f0, n) */
+} dd_sim_config;
+
+const char *dd_last_error(void);
+int dd_sim_create(const dd_sim_config *cfg, dd_sim **out);
+void dd_sim_destroy(dd_sim *sim);
+long long dd_sim_launch_count(dd_sim *sim);   /* kernels launched (incl. graph replays) since creation */
+int dd_sim_set_material(dd_sim *sim, const float *mass, const float *vol, const float *mu_lam_yield, cudaStream_t stream);
+int dd_sim_set_bodies(dd_sim *sim, const float *tfsr, const float *args);   /* (nb,4) each; simulator.py:388-404 */
+int dd_sim_set_state(dd_sim *sim, int f, const float *x, const float *v, const float *F, const float *C, cudaStream_t stream);
+int dd_sim_get_state(dd_sim *sim, int f, float *x, float *v, float *F, float *C, cudaStream_t stream);   /* any may be NULL; synchronises */
+int dd_sim_set_poses(dd_sim *sim, int f0, int count, const float *pos, const float *rot, cudaStream_t stream);
+int dd_sim_forward(dd_sim *sim, int f0, int n_substeps, cudaStream_t stream);    /* slots f0 -> f0+n */
+int dd_sim_zero_grad(dd_sim *sim, int f, cudaStream_t stream);                   /* start a backward pass at state f */
+int dd_sim_add_state_grad(dd_sim *sim, int f, const float *gx, const float *gv, const float *gF, const float *gC, cudaStream_t stream);
+int dd_sim_get_state_grad(dd_sim *sim, int f, float *gx, float *gv, float *gF, float *gC, cudaStream_t stream);
+int dd_sim_backward(dd_sim *sim, int f0, int n_substeps, cudaStream_t stream);   /* substeps f0+n-1 ... f0 */
+int dd_sim_get_pose_grads(dd_sim *sim, int f0, int count, float *gpos, float *grot, cudaStream_t stream);
+int dd_sim_add_pose_grads(dd_sim *sim, int f, const float *gpos, const float *grot, cudaStream_t stream);
+int dd_sim_compute_dist(dd_sim *sim, int f, float *dist, cudaStream_t stream);   /* (E, N, nb) */
+int dd_sim_compute_dist_grad(dd_sim *sim, int f, const float *dist_grad, cudaStream_t stream);
+int dd_sim_sync(dd_sim *sim, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

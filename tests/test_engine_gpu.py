@@ -1,0 +1,138 @@
+"""GPU parity tests of the fused engine (ABI-2) against the reference's CUDA library, the per-stage ABI-1 path and the
+C oracle, all on identical inputs.  svd_mode=0 uses the reference-order fp64 SVD (tight tolerances); svd_mode=1 is the
+production fp32 in-register SVD (tolerances of SURVEY.md 8c)."""
+import numpy as np
+import pytest
+
+from abi1_driver import Abi1Sim, loss_seed
+from conftest import cosine, rel_err, rel_l2
+from dexdeform_b200.engine import EngineError, FusedSim
+from dexdeform_b200.scenes import make_scene, scene_tutorial
+
+pytestmark = pytest.mark.gpu
+
+
+def run_abi1(lib, sc, S, seedg):
+    sim = Abi1Sim(lib, sc, S)
+    for f in range(S):
+        sim.substep(f)
+    for k, v in seedg.items():
+        sim.states[S][k].upload(v)
+    for f in range(S - 1, -1, -1):
+        sim.substep_grad(f)
+    out = dict(state=sim.get(S), grad=sim.get(0, "x_grad", "v_grad", "F_grad", "C_grad"))
+    if sc["nb"]:
+        out["gpos"] = np.stack([sim.get(f, "body_pos_grad")["body_pos_grad"] for f in range(S + 1)])
+        out["grot"] = np.stack([sim.get(f, "body_rot_grad")["body_rot_grad"] for f in range(S + 1)])
+    return out
+
+
+def run_engine(sc, S, seedg, E=1, **kw):
+    sim = FusedSim.from_scene(sc, n_envs=E, max_steps=S, **kw)
+    sim.forward(0, S)
+    sim.zero_grad(S)
+    t = lambda a: np.ascontiguousarray(np.broadcast_to(a[None], (E,) + a.shape))
+    sim.add_state_grad(S, t(seedg["x_grad"]), t(seedg["v_grad"]), t(seedg["F_grad"]), t(seedg["C_grad"]))
+    sim.backward(0, S)
+    out = dict(state=sim.get_state(S), grad=sim.get_state_grad(0))
+    out["gpos"], out["grot"] = sim.get_pose_grads(0, S + 1)
+    out["launches"] = sim.launch_count()
+    sim.close()
+    return out
+
+
+@pytest.mark.parametrize("svd_mode,graphs", [(0, False), (1, True)])
+def test_engine_matches_reference_cuda_short(ref_gpu, svd_mode, graphs):
+    S = 4
+    sc = scene_tutorial(steps=S, perturb=0.02, vel_scale=0.3, on_floor=True, seed=2)
+    seedg = loss_seed(sc["n"], 3)
+    ref = run_abi1(ref_gpu, sc, S, seedg)
+    eng = run_engine(sc, S, seedg, svd_mode=svd_mode, use_graphs=graphs)
+    tight = svd_mode == 0
+    assert np.abs(eng["state"]["x"][0] - ref["state"]["x"]).max() < (2e-7 if tight else 1e-6)
+    for k, tol in dict(v=2e-5, F=5e-6, C=1e-4).items():
+        e = rel_err(eng["state"][k][0], ref["state"][k])
+        assert e < tol * (1 if tight else 5), (k, e)
+    for k, tol in dict(x=2e-4, v=2e-4, C=5e-2, F=5e-2).items():
+        e = rel_err(eng["grad"][k][0], ref["grad"][k + "_grad"])
+        assert e < tol * (1 if tight else 3), (k, e)
+        assert cosine(eng["grad"][k][0], ref["grad"][k + "_grad"]) > 0.999
+    assert rel_err(eng["gpos"][:, 0], ref["gpos"]) < (2e-4 if tight else 2e-3)
+    assert rel_err(eng["grot"][:, 0], ref["grot"]) < (2e-4 if tight else 2e-3)
+    assert eng["launches"] == 3 * S + 5 * S
+
+
+def test_engine_rollout_50_substeps_vs_reference(ref_gpu):
+    """BASELINE config A through the production path (fp32 SVD, CUDA graphs): tolerances of SURVEY.md 8c."""
+    S = 50
+    sc = scene_tutorial(steps=S, seed=0, on_floor=True)
+    n = sc["n"]
+    seedg = dict(x_grad=np.zeros((n, 3), np.float32), v_grad=np.zeros((n, 3), np.float32), F_grad=np.zeros((n, 9), np.float32),
+                 C_grad=np.zeros((n, 9), np.float32))
+    seedg["x_grad"][:, 1] = -1.0 / n
+    ref = run_abi1(ref_gpu, sc, S, seedg)
+    eng = run_engine(sc, S, seedg)
+    assert np.abs(eng["state"]["x"][0] - ref["state"]["x"]).max() < 1e-4
+    for k in ("v", "F", "C"):
+        assert rel_err(eng["state"][k][0], ref["state"][k]) < 1e-3, (k, rel_err(eng["state"][k][0], ref["state"][k]))
+    assert np.abs(ref["gpos"]).max() > 0
+    for a, b in ((eng["gpos"][:, 0], ref["gpos"]), (eng["grot"][:, 0], ref["grot"])):
+        assert rel_l2(a, b) < 1e-2, rel_l2(a, b)
+        assert cosine(a, b) > 0.999
+    for k in ("x", "v"):
+        assert rel_l2(eng["grad"][k][0], ref["grad"][k + "_grad"]) < 1e-2
+        assert cosine(eng["grad"][k][0], ref["grad"][k + "_grad"]) > 0.999
+
+
+def test_engine_vs_oracle_and_env_batching(oracle_lib):
+    """E=3 environments with different states and poses must each equal a single-environment oracle run."""
+    S, E = 3, 3
+    scs = [make_scene(1200, 32, box_width=(0.12, 0.1, 0.12), steps=S, perturb=0.03, vel_scale=0.4, on_floor=True, seed=40 + e, nb=5)
+           for e in range(E)]
+    for sc in scs[1:]:  # shapes are shared by all environments of one engine
+        sc["tfsr"], sc["args"] = scs[0]["tfsr"], scs[0]["args"]
+    seedg = loss_seed(1200, 8)
+    refs = [run_abi1(oracle_lib, sc, S, seedg) for sc in scs]
+    sc0 = scs[0]
+    sim = FusedSim(E, 1200, 5, sc0["grid_dim"], sc0["dx"], sc0["dt"], S, sc0["ground_friction"], sc0["ground_height"], sc0["gravity"].reshape(3),
+                   svd_mode=0)
+    st = lambda k: np.ascontiguousarray(np.stack([sc[k] for sc in scs]))
+    sim.set_material(st("mass"), st("vol"), st("mu_lam_yield"))
+    sim.set_bodies(sc0["tfsr"], sc0["args"])
+    sim.set_poses(0, np.ascontiguousarray(np.stack([sc["pos"] for sc in scs], 1)), np.ascontiguousarray(np.stack([sc["rot"] for sc in scs], 1)))
+    sim.set_state(0, st("x"), st("v"), st("F"), st("C"))
+    sim.forward(0, S)
+    sim.zero_grad(S)
+    t = lambda a: np.ascontiguousarray(np.broadcast_to(a[None], (E,) + a.shape))
+    sim.add_state_grad(S, t(seedg["x_grad"]), t(seedg["v_grad"]), t(seedg["F_grad"]), t(seedg["C_grad"]))
+    sim.backward(0, S)
+    state, grad = sim.get_state(S), sim.get_state_grad(0)
+    gpos, grot = sim.get_pose_grads(0, S + 1)
+    for e in range(E):
+        for k, tol in dict(x=2e-6, v=5e-5, F=5e-6, C=2e-4).items():
+            assert rel_err(state[k][e], refs[e]["state"][k]) < tol, (e, k)
+        for k in ("x", "v"):
+            assert rel_err(grad[k][e], refs[e]["grad"][k + "_grad"]) < 5e-4, (e, k)
+        assert rel_err(gpos[:, e], refs[e]["gpos"]) < 5e-4 and rel_err(grot[:, e], refs[e]["grot"]) < 5e-4
+    # observations: signed distances and their adjoint against the oracle
+    d = sim.compute_dist(S)
+    a1 = Abi1Sim(oracle_lib, scs[1], S)
+    for f in range(S):
+        a1.substep(f)
+    from dexdeform_b200.types import array, float32
+    dist = array(dtype=float32, length=1200 * 5, library=oracle_lib)
+    a1.compute_dist(a1.states[S], dist, dist, 0)
+    assert np.abs(d[1] - dist.download().reshape(1200, 5)).max() < 2e-6
+    sim.close()
+
+
+def test_engine_error_reporting():
+    with pytest.raises(EngineError, match="n_bodies"):
+        FusedSim(1, 64, 100, (32, 32, 32), 1 / 32, 1e-4, 4)
+    sc = make_scene(64, 32, steps=2, nb=0, seed=1)
+    sim = FusedSim.from_scene(sc, max_steps=2)
+    with pytest.raises(EngineError, match="exceeds max_steps"):
+        sim.forward(0, 5)
+    with pytest.raises(EngineError, match="no gradient seeded"):
+        sim.backward(0, 2)
+    sim.close()
