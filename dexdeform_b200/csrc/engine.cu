@@ -10,8 +10,12 @@
 //   * S substeps (or their reverse) are captured into one CUDA graph; poses for all substeps are device resident
 #include "mpm_math.cuh"
 #include "../../include/dexdeform_mpm.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <tuple>
@@ -319,11 +323,9 @@ DD_DEV float warp_sum(float v) {
 }
 
 // grid_op_v2_grad (integrator.cu:779-1057) without the stored per-body velocities
-__global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restrict__ grid, const float4 *__restrict__ ggrid_v,
-                                                  float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos, float4 *grot, float4 *gnpos,
-                                                  float4 *gnrot) {
-  int node = blockIdx.x * kT + threadIdx.x;
-  bool inr = node < kp.E * kp.G;
+DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, int cy, int cz, const float4 *__restrict__ grid,
+                           const float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, const BodyTables &bt, float4 *gpos, float4 *grot,
+                           float4 *gnpos, float4 *gnrot) {
   float4 mm = inr ? grid[node] : make_float4(0.f, 0.f, 0.f, 0.f);
   bool live = inr && mm.w > 1e-12;
   // a whole warp of empty nodes leaves early (the common case)
@@ -335,9 +337,7 @@ __global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restric
   V3 gv = vzero(), mv = vzero(), gx = vzero(), v0 = vzero();
   unsigned long long mask = 0ull;
   if (live) {
-    env = node / kp.G;
-    int cell = node - env * kp.G;
-    gx_ = cell / kp.gz / kp.gy; gy_ = (cell / kp.gz) % kp.gy; gz_ = cell % kp.gz;
+    env = env_; gx_ = cx; gy_ = cy; gz_ = cz;
     mv = v3(mm.x, mm.y, mm.z);
     v0 = mv * (1.f / mm.w) + kp.dt * v3(kp.g0, kp.g1, kp.g2);
     gx = v3((float)gx_, (float)gy_, (float)gz_) * kp.dx;
@@ -457,8 +457,8 @@ __global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restric
     float r[14] = {g_np.x, g_np.y, g_np.z, g_nq.w, g_nq.x, g_nq.y, g_nq.z, g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z};
 #pragma unroll
     for (int i = 0; i < 14; ++i) r[i] = warp_sum(r[i]);
+    int wenv = __shfl_sync(0xffffffffu, env_, 0);  // a warp never straddles two environments
     if ((threadIdx.x & 31) == 0) {
-      int wenv = (blockIdx.x * kT + (threadIdx.x & ~31)) / kp.G;
       int pb = wenv * kp.nb + b;
       atomicAdd(&gnpos[pb].x, r[0]); atomicAdd(&gnpos[pb].y, r[1]); atomicAdd(&gnpos[pb].z, r[2]);
       atomicAdd(&gnrot[pb].x, r[3]); atomicAdd(&gnrot[pb].y, r[4]); atomicAdd(&gnrot[pb].z, r[5]); atomicAdd(&gnrot[pb].w, r[6]);
@@ -474,6 +474,14 @@ __global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restric
       ggrid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+}
+__global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restrict__ grid, const float4 *__restrict__ ggrid_v,
+                                                  float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos, float4 *grot, float4 *gnpos,
+                                                  float4 *gnrot) {
+  int node = blockIdx.x * kT + threadIdx.x;
+  bool inr = node < kp.E * kp.G;
+  int env = inr ? node / kp.G : 0, cell = node - env * kp.G;
+  grid_grad_body(kp, node, inr, env, cell / kp.gz / kp.gy, (cell / kp.gz) % kp.gy, cell % kp.gz, grid, ggrid_v, ggrid, bt, gpos, grot, gnpos, gnrot);
 }
 
 // p2g_grad + compute_svd_grad (integrator.cu:396-627, 110-186) fused; writes the complete gradient of state t
@@ -555,6 +563,283 @@ __global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict_
   store_F(gout, kp.EN, p, g_F);
 }
 
+// ================================================================================================ tiled kernels
+// Particles are stored brick by brick (4x4x4 cells), a brick's particles cell-sorted and split into chunks.  One warp
+// owns one chunk and a private 8x8x8-node shared-memory tile around the brick (1 node of slack on every side for drift
+// since the last sort).  Inside a chunk lane l walks the sorted ranks [l*R, (l+1)*R), so the 32 particles of a round
+// sit in 32 different cells and their read-modify-writes on the tile never collide; the storage order is the
+// round-major transpose of that assignment, which keeps every global load coalesced.  Collisions that do occur
+// (dense cells, drift) are detected with match.any and serialised.  The tile is flushed with one vector reduction per
+// touched node instead of one per (particle, node).
+constexpr int kTileN = 512;          // 8^3 nodes
+constexpr int kTileWarps = 4;        // chunks per thread block
+DD_DEV int round_off(int j, int L, int q) { return j * (L - 1) + min(j, q); }
+struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, L, q; };
+DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
+  ChunkGeom c;
+  int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
+  c.env = ch.x / NB;
+  int b = ch.x - c.env * NB;
+  c.ox = (b / (nby * nbz)) * 4 - 1; c.oy = ((b / nbz) % nby) * 4 - 1; c.oz = (b % nbz) * 4 - 1;
+  c.start = ch.y; c.cnt = ch.z;
+  c.R = (c.cnt + 31) >> 5;
+  c.L = (c.cnt + c.R - 1) / c.R;
+  c.q = c.cnt - c.R * (c.L - 1);
+  return c;
+}
+// a particle whose stencil leaves the 3x3x3-brick neighbourhood of its home brick has out-run the active region
+DD_DEV void check_drift(int tx, int ty, int tz, int *overflow) {
+  if (tx < -3 || tx > 9 || ty < -3 || ty > 9 || tz < -3 || tz > 9) atomicOr(overflow, 1);
+}
+
+template <int SVD, bool WRITE_F>
+__global__ void __launch_bounds__(32 * kTileWarps, 4) k_p2g_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+                                                              float *__restrict__ nxt, const float4 *__restrict__ mat0,
+                                                              const float *__restrict__ yield, float4 *__restrict__ grid, int *overflow) {
+  extern __shared__ float4 dd_smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ci = blockIdx.x * kTileWarps + warp;
+  if (ci >= nchunks) return;
+  float4 *tile = dd_smem + warp * kTileN;
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  float4 *g = grid + (size_t)cg.env * kp.G;
+  for (int j = 0; j < cg.R; ++j) {
+    bool act = lane < cg.L - (j >= cg.q ? 1 : 0);
+    int p = cg.start + round_off(j, cg.L, cg.q) + lane;
+    Stencil st;
+    V3 mv = vzero(), c0 = vzero(), c1 = vzero(), c2 = vzero();
+    float m = 0.f;
+    int tx = 0, ty = 0, tz = 0;
+    if (act) {
+      XVC s = load_xvc(cur, kp.EN, p);
+      M3 F = load_F(cur, kp.EN, p);
+      float4 m0 = __ldg(mat0 + p);
+      Constit c;
+      constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c);
+      if (WRITE_F) store_F(nxt, kp.EN, p, c.nF);
+      st = make_stencil_safe(s.x, kp);
+      m = m0.x;
+      mv = m * s.v;
+      c0 = v3(c.affine.a00, c.affine.a10, c.affine.a20); c1 = v3(c.affine.a01, c.affine.a11, c.affine.a21); c2 = v3(c.affine.a02, c.affine.a12, c.affine.a22);
+      tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
+    }
+    bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
+    unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    int rank = __popc(peers & ((1u << lane) - 1u));
+    int maxr = __reduce_max_sync(0xffffffffu, rank);
+    for (int r = 0; r <= maxr; ++r) {
+      bool mine = in_tile && rank == r;
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) {
+        float wi = pick(st.w0, st.w1, st.w2, i, 0);
+        V3 ai = mv + c0 * (((float)i - st.fx.x) * kp.dx);
+#pragma unroll 1
+        for (int jj = 0; jj < 3; ++jj) {
+          float wij = wi * pick(st.w0, st.w1, st.w2, jj, 1);
+          V3 aij = ai + c1 * (((float)jj - st.fx.y) * kp.dx);
+          int row = (tx + i) << 6 | (ty + jj) << 3 | tz;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            float w = wij * pick(st.w0, st.w1, st.w2, k, 2);
+            V3 a = (aij + c2 * (((float)k - st.fx.z) * kp.dx)) * w;
+            if (mine) {
+              float4 t = tile[row + k];
+              t.x += a.x; t.y += a.y; t.z += a.z; t.w += m * w;
+              tile[row + k] = t;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (act && !in_tile) {  // drifted more than one cell since the last sort: straight to the grid
+      check_drift(tx, ty, tz, overflow);
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i)
+#pragma unroll 1
+        for (int jj = 0; jj < 3; ++jj)
+#pragma unroll 1
+          for (int k = 0; k < 3; ++k) {
+            float w = pick(st.w0, st.w1, st.w2, i, 0) * pick(st.w0, st.w1, st.w2, jj, 1) * pick(st.w0, st.w1, st.w2, k, 2);
+            V3 a = (mv + c0 * (((float)i - st.fx.x) * kp.dx) + c1 * (((float)jj - st.fx.y) * kp.dx) + c2 * (((float)k - st.fx.z) * kp.dx)) * w;
+            red_add_v4(g + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, a.x, a.y, a.z, m * w);
+          }
+    }
+  }
+  __syncwarp();
+  for (int n = lane; n < kTileN; n += 32) {
+    float4 t = tile[n];
+    int nx = cg.ox + (n >> 6), ny = cg.oy + ((n >> 3) & 7), nz = cg.oz + (n & 7);
+    if ((t.w != 0.f || t.x != 0.f || t.y != 0.f || t.z != 0.f) && (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
+      red_add_v4(g + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, t.w);
+  }
+}
+
+// g2p_grad on tiles: grid velocities are gathered from a tile copy, their adjoint is scattered into a second tile
+__global__ void __launch_bounds__(32 * kTileWarps, 3) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+                                                                   const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
+                                                                   const float *__restrict__ gin, float *__restrict__ gout,
+                                                                   float4 *__restrict__ ggrid_v, int *overflow) {
+  extern __shared__ float4 dd_smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ci = blockIdx.x * kTileWarps + warp;
+  if (ci >= nchunks) return;
+  float4 *tv = dd_smem + warp * (2 * kTileN), *tg = tv + kTileN;
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  size_t goff = (size_t)cg.env * kp.G;
+  for (int n = lane; n < kTileN; n += 32) {
+    int nx = cg.ox + (n >> 6), ny = cg.oy + ((n >> 3) & 7), nz = cg.oz + (n & 7);
+    bool ok = (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz;
+    tv[n] = ok ? __ldg(grid_v + goff + (nx * kp.gy + ny) * kp.gz + nz) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tg[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+  float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
+  for (int j = 0; j < cg.R; ++j) {
+    bool act = lane < cg.L - (j >= cg.q ? 1 : 0);
+    int p = cg.start + round_off(j, cg.L, cg.q) + lane;
+    Stencil st;
+    XVC g;
+    V3 gx = vzero(), gnv = vzero(), d0 = vzero(), d1 = vzero(), d2 = vzero();
+    int tx = 0, ty = 0, tz = 0;
+    if (act) {
+      float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
+      V3 x = v3(a.x, a.y, a.z);
+      float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
+      g = load_xvc(gin, kp.EN, p);
+      gx = g.x; gnv = g.v;
+      V3 nx = x + v3(n0.w, n1.x, n1.y) * kp.dt;
+      if (nx.x > hi.x || nx.x < lo) gx.x = 0;
+      if (nx.y > hi.y || nx.y < lo) gx.y = 0;
+      if (nx.z > hi.z || nx.z < lo) gx.z = 0;
+      gnv += gx * kp.dt;
+      st = make_stencil_safe(x, kp);
+      stencil_dw(st, kp.inv_dx, d0, d1, d2);
+      tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
+    }
+    bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
+    unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    int rank = __popc(peers & ((1u << lane) - 1u));
+    int maxr = __reduce_max_sync(0xffffffffu, rank);
+    for (int r = 0; r <= maxr; ++r) {
+      bool mine = in_tile && rank == r;
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll 1
+        for (int jj = 0; jj < 3; ++jj) {
+          int row = (tx + i) << 6 | (ty + jj) << 3 | tz;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (mine) {
+              float wx = pick(st.w0, st.w1, st.w2, i, 0), wy = pick(st.w0, st.w1, st.w2, jj, 1), wz = pick(st.w0, st.w1, st.w2, k, 2);
+              float w = wx * wy * wz;
+              V3 dpos = v3((float)i, (float)jj, (float)k) - st.fx;
+              float4 t = tv[row + k];
+              V3 v = v3(t.x, t.y, t.z);
+              float xx = w * s4;
+              V3 cd = mul(g.C, dpos);
+              V3 ggv = w * gnv + cd * xx;
+              float4 o = tg[row + k];
+              o.x += ggv.x; o.y += ggv.y; o.z += ggv.z;
+              tg[row + k] = o;
+              gx += (-kp.inv_dx * xx) * mul_t(g.C, v);
+              float gw = dot(gnv, v) + s4 * dot(v, cd);
+              gx += v3(pick(d0, d1, d2, i, 0) * wy * wz, wx * pick(d0, d1, d2, jj, 1) * wz, wx * wy * pick(d0, d1, d2, k, 2)) * gw;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (act && !in_tile) {
+      check_drift(tx, ty, tz, overflow);
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i)
+#pragma unroll 1
+        for (int jj = 0; jj < 3; ++jj)
+#pragma unroll 1
+          for (int k = 0; k < 3; ++k) {
+            float wx = pick(st.w0, st.w1, st.w2, i, 0), wy = pick(st.w0, st.w1, st.w2, jj, 1), wz = pick(st.w0, st.w1, st.w2, k, 2);
+            float w = wx * wy * wz;
+            V3 dpos = v3((float)i, (float)jj, (float)k) - st.fx;
+            size_t node = goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k;
+            float4 t = __ldg(grid_v + node);
+            V3 v = v3(t.x, t.y, t.z);
+            float xx = w * s4;
+            V3 cd = mul(g.C, dpos);
+            V3 ggv = w * gnv + cd * xx;
+            red_add_v4(ggrid_v + node, ggv.x, ggv.y, ggv.z, 0.f);
+            gx += (-kp.inv_dx * xx) * mul_t(g.C, v);
+            float gw = dot(gnv, v) + s4 * dot(v, cd);
+            gx += v3(pick(d0, d1, d2, i, 0) * wy * wz, wx * pick(d0, d1, d2, jj, 1) * wz, wx * wy * pick(d0, d1, d2, k, 2)) * gw;
+          }
+    }
+    if (act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
+  }
+  __syncwarp();
+  for (int n = lane; n < kTileN; n += 32) {
+    float4 t = tg[n];
+    int nx = cg.ox + (n >> 6), ny = cg.oy + ((n >> 3) & 7), nz = cg.oz + (n & 7);
+    if ((t.x != 0.f || t.y != 0.f || t.z != 0.f) && (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
+      red_add_v4(ggrid_v + goff + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, 0.f);
+  }
+}
+
+// ---- grid kernels restricted to the active bricks (3x3x3-brick neighbourhood of every occupied brick) -----------------
+DD_DEV int brick_node(int brick, int local, const KP &kp, int &env, int &gx_, int &gy_, int &gz_) {
+  int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
+  env = brick / NB;
+  int b = brick - env * NB;
+  gx_ = (b / (nby * nbz)) * 4 + (local >> 4); gy_ = ((b / nbz) % nby) * 4 + ((local >> 2) & 3); gz_ = (b % nbz) * 4 + (local & 3);
+  return env * kp.G + (gx_ * kp.gy + gy_) * kp.gz + gz_;
+}
+__global__ void __launch_bounds__(kT) k_zero_bricks(KP kp, int nactive, const int *__restrict__ active, float4 *a, float4 *b) {
+  int t = blockIdx.x * kT + threadIdx.x;
+  if (t >= nactive * 64) return;
+  int env, x, y, z;
+  int node = brick_node(active[t >> 6], t & 63, kp, env, x, y, z);
+  a[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (b) b[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__global__ void __launch_bounds__(kT) k_grid_b(KP kp, int nactive, const int *__restrict__ active, const float4 *__restrict__ grid,
+                                               float4 *__restrict__ grid_v, BodyTables bt) {
+  int t = blockIdx.x * kT + threadIdx.x;
+  if (t >= nactive * 64) return;
+  int env, gx_, gy_, gz_;
+  int node = brick_node(active[t >> 6], t & 63, kp, env, gx_, gy_, gz_);
+  float4 mm = grid[node];
+  if (!(mm.w > 1e-12)) {
+    grid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  V3 v = v3(mm.x, mm.y, mm.z) * (1.f / mm.w) + kp.dt * v3(kp.g0, kp.g1, kp.g2);
+  V3 gx = v3((float)gx_, (float)gy_, (float)gz_) * kp.dx;
+  for (int b = 0; b < kp.nb; ++b) {
+    int pb = env * kp.nb + b;
+    Hit h;
+    Q4 bq = q4f(bt.rot[pb]), tfsr = q4f(bt.tfsr[b]), sargs = q4f(bt.args[b]);
+    if (contact_geom(gx, v3f(bt.pos[pb]), bq, tfsr, sargs, bt.cull[b], h))
+      v = contact_apply(gx, v, bq, v3f(bt.npos[pb]), q4f(bt.nrot[pb]), tfsr, sargs, kp.dt, h);
+  }
+  v = apply_bc(v, gx_, gy_, gz_, kp);
+  grid_v[node] = make_float4(v.x, v.y, v.z, 0.f);
+}
+
+__global__ void __launch_bounds__(kT) k_grid_grad_b(KP kp, int nactive, const int *__restrict__ active, const float4 *__restrict__ grid,
+                                                    const float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos,
+                                                    float4 *grot, float4 *gnpos, float4 *gnrot) {
+  int t = blockIdx.x * kT + threadIdx.x;
+  bool inr = t < nactive * 64;
+  int env = 0, x = 0, y = 0, z = 0, node = 0;
+  if (inr) node = brick_node(active[t >> 6], t & 63, kp, env, x, y, z);
+  grid_grad_body(kp, node, inr, env, x, y, z, grid, ggrid_v, ggrid, bt, gpos, grot, gnpos, gnrot);
+}
+
 // ---- layout conversion (original AoS order <-> sorted planes) --------------------------------------------------------
 __global__ void k_pack(int EN, const int *__restrict__ perm, const float *__restrict__ x, const float *__restrict__ v, const float *__restrict__ F,
                        const float *__restrict__ C, float *slot) {
@@ -597,6 +882,59 @@ __global__ void k_pack_mat(int EN, const int *__restrict__ perm, const float *__
   mat0[i] = make_float4(mass[s], vol[s], mly[3 * s], mly[3 * s + 1]);
   yield[i] = mly[3 * s + 2];
 }
+// sort key of a particle: environment-major, then 4x4x4-cell brick (x-major like the grid), then cell inside the brick
+__global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__restrict__ keys, int *__restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kp.EN) return;
+  V3 x = ld_v3(x_aos, i);
+  int cx = clampi((int)floorf(x.x * kp.inv_dx - 0.5f), 0, kp.gx - 1), cy = clampi((int)floorf(x.y * kp.inv_dx - 0.5f), 0, kp.gy - 1),
+      cz = clampi((int)floorf(x.z * kp.inv_dx - 0.5f), 0, kp.gz - 1);
+  int nby = (kp.gy + 3) >> 2, nbz = (kp.gz + 3) >> 2;
+  unsigned brick = ((cx >> 2) * nby + (cy >> 2)) * nbz + (cz >> 2);
+  unsigned cell = ((cx & 3) << 4) | ((cy & 3) << 2) | (cz & 3);
+  keys[i] = (unsigned)(i / kp.N) * (unsigned)kp.G + (brick << 6 | cell);
+  idx[i] = i;
+}
+
+__global__ void k_mark_heads(int EN, const unsigned *__restrict__ keys, char *__restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= EN) return;
+  flags[i] = (i == 0) || (keys[i] >> 6) != (keys[i - 1] >> 6);
+}
+// one thread per occupied brick: split its particle range into chunks and mark its 3x3x3 neighbourhood active
+__global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_pos, const unsigned *__restrict__ keys, int chunk_max,
+                              int4 *__restrict__ chunks, int *__restrict__ counters, char *__restrict__ active_flag) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nbricks) return;
+  int start = head_pos[k], end = k + 1 < nbricks ? head_pos[k + 1] : kp.EN, cnt = end - start;
+  int brick = (int)(keys[start] >> 6);
+  int nch = (cnt + chunk_max - 1) / chunk_max;
+  int c0 = atomicAdd(&counters[0], nch);
+  for (int c = 0; c < nch; ++c) {
+    int s = start + (int)((long long)cnt * c / nch), t = start + (int)((long long)cnt * (c + 1) / nch);
+    chunks[c0 + c] = make_int4(brick, s, t - s, 0);
+  }
+  int nbx = kp.gx >> 2, nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = nbx * nby * nbz;
+  int env = brick / NB, b = brick - env * NB;
+  int bx = b / (nby * nbz), by = (b / nbz) % nby, bz = b % nbz;
+  for (int dx = -1; dx <= 1; ++dx)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dz = -1; dz <= 1; ++dz) {
+        int x = bx + dx, y = by + dy, z = bz + dz;
+        if ((unsigned)x < (unsigned)nbx && (unsigned)y < (unsigned)nby && (unsigned)z < (unsigned)nbz) active_flag[env * NB + (x * nby + y) * nbz + z] = 1;
+      }
+}
+// round-major transpose of every chunk (see the tiled kernels): one warp per chunk
+__global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks, const int *__restrict__ perm_in, int *__restrict__ perm_out) {
+  int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (ci >= nchunks) return;
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  for (int r = lane; r < cg.cnt; r += 32) {
+    int l = r / cg.R, j = r - l * cg.R;
+    perm_out[cg.start + round_off(j, cg.L, cg.q) + l] = perm_in[cg.start + r];
+  }
+}
+
 __global__ void k_pad4(int n, const float *__restrict__ src, int w, float4 *dst) {  // (n, w<=4) floats -> float4
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -685,13 +1023,33 @@ struct dd_sim {
   float4 *pos = nullptr, *rot = nullptr, *gpos = nullptr, *grot = nullptr;  // slots * E * nb
   float4 *tfsr = nullptr, *args = nullptr;
   float *cull = nullptr;
-  int *perm = nullptr;
+  int *perm = nullptr;       // sorted index -> original particle index
+  unsigned *keys = nullptr, *keys_alt = nullptr;
+  int *idx_alt = nullptr;
+  void *cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  // tiled mode: chunk list, active bricks, per-substep grid checkpoints
+  int4 *chunks = nullptr;
+  int chunk_cap = 0, nchunks = 0, chunk_max = 512;
+  int *head_pos = nullptr;
+  char *head_flags = nullptr, *active_flag = nullptr;
+  int *active = nullptr;
+  int nactive = 0, NBtot = 0;
+  int *counters = nullptr;   // [0] chunks, [1] active bricks, [2] occupied bricks, [3] overflow flag
+  void *sel_tmp = nullptr;
+  size_t sel_bytes = 0;
+  float4 *gridck = nullptr, *gridvck = nullptr;  // (slots-1) * E * G each when grid checkpoints are on
+  bool grid_ckpt = false;
+  float *mat_aos = nullptr;  // (mass | vol | mu_lam_yield) in original order, re-packed after every sort
+  bool have_material = false;
   float *stage = nullptr;    // 24 * EN floats (x|v|F|C in original AoS order) or E*N*nb for dist
   size_t stage_floats = 0;
   std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;
   long long launches = 0;    // kernels launched (or replayed through graphs) since creation
 
   float *slot(int f) const { return ckpt + (size_t)f * slot_floats; }
+  float4 *G(int f) const { return grid_ckpt ? gridck + (size_t)f * kp.E * kp.G : grid; }
+  float4 *GV(int f) const { return grid_ckpt ? gridvck + (size_t)f * kp.E * kp.G : grid_v; }
   BodyTables tables(int f) const {
     BodyTables bt;
     size_t o = (size_t)f * kp.E * kp.nb, o1 = (size_t)(f + 1 < slots ? f + 1 : f) * kp.E * kp.nb;
@@ -703,29 +1061,66 @@ struct dd_sim {
 
 namespace {
 
+int fwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? 4 : 3; }
+int bwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? (s->grid_ckpt ? 4 : 7) : 5; }
+
 template <int SVD>
 void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st) {
   const KP &kp = s->kp;
-  cudaMemsetAsync(s->grid, 0, sizeof(float4) * (size_t)kp.E * kp.G, st);
-  k_p2g<SVD, true><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
-  k_grid<<<nblk((long long)kp.E * kp.G), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
-  k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v);
-  s->launches += 3;
+  if (s->cfg.tile_mode) {
+    int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
+    k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), nullptr);
+    k_p2g_tile<SVD, true><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->counters + 3);
+    k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f));
+    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->GV(f));
+  } else {
+    cudaMemsetAsync(s->grid, 0, sizeof(float4) * (size_t)kp.E * kp.G, st);
+    k_p2g<SVD, true><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
+    k_grid<<<nblk((long long)kp.E * kp.G), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
+    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v);
+  }
+  s->launches += fwd_launches(s);
 }
 template <int SVD>
 void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st) {
   const KP &kp = s->kp;
   float *gin = s->grad[(f + 1) & 1], *gout = s->grad[f & 1];
   size_t eg = (size_t)kp.E * kp.G, ep = (size_t)kp.E * kp.nb;
-  cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st);
-  cudaMemsetAsync(s->ggrid_v, 0, sizeof(float4) * eg, st);
-  k_p2g<SVD, false><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
-  k_grid<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
-  k_g2p_grad<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v, gin, gout, s->ggrid_v);
-  k_grid_grad<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->ggrid_v, s->ggrid, s->tables(f), s->gpos + (size_t)f * ep, s->grot + (size_t)f * ep,
-                                                   s->gpos + (size_t)(f + 1) * ep, s->grot + (size_t)(f + 1) * ep);
-  k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->mat0, s->yield, s->ggrid, gin, gout);
-  s->launches += 5;
+  float4 *gp = s->gpos + (size_t)f * ep, *gr = s->grot + (size_t)f * ep, *gnp = s->gpos + (size_t)(f + 1) * ep, *gnr = s->grot + (size_t)(f + 1) * ep;
+  if (s->cfg.tile_mode) {
+    int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
+    if (s->grid_ckpt) {
+      k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->ggrid_v, nullptr);
+    } else {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
+      k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->ggrid_v);
+      k_p2g_tile<SVD, false><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->counters + 3);
+      k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f));
+    }
+    k_g2p_grad_tile<<<ncb, 32 * kTileWarps, 2 * kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->counters + 3);
+    k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr);
+    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->mat0, s->yield, s->ggrid, gin, gout);
+  } else {
+    cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st);
+    cudaMemsetAsync(s->ggrid_v, 0, sizeof(float4) * eg, st);
+    k_p2g<SVD, false><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
+    k_grid<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
+    k_g2p_grad<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v, gin, gout, s->ggrid_v);
+    k_grid_grad<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr);
+    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->mat0, s->yield, s->ggrid, gin, gout);
+  }
+  s->launches += bwd_launches(s);
+}
+
+int check_overflow(dd_sim *s) {
+  if (!s->cfg.tile_mode) return 0;
+  int flag = 0;
+  DD_CUDA(cudaMemcpy(&flag, s->counters + 3, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(s->counters + 3, 0, sizeof(int));
+    return fail("a particle moved more than two cells away from the brick it was sorted into; results since the last dd_sim_set_state are invalid -- "
+                "re-sort more often (call dd_sim_set_state at environment-step boundaries)");
+  }
+  return 0;
 }
 
 // run `body` either directly or as a cached CUDA graph keyed by (kind, f0, n)
@@ -817,6 +1212,41 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
   DD_ALLOC(s->args, sizeof(float4) * 64);
   DD_ALLOC(s->cull, sizeof(float) * 64);
   DD_ALLOC(s->perm, sizeof(int) * ENp);
+  DD_ALLOC(s->keys, sizeof(unsigned) * ENp);
+  DD_ALLOC(s->keys_alt, sizeof(unsigned) * ENp);
+  DD_ALLOC(s->idx_alt, sizeof(int) * ENp);
+  DD_ALLOC(s->mat_aos, sizeof(float) * 5 * ENp);
+  cub::DeviceRadixSort::SortPairs(nullptr, s->cub_bytes, s->keys, s->keys_alt, s->idx_alt, s->perm, kp.EN);
+  DD_ALLOC(s->cub_tmp, s->cub_bytes + 16);
+  if (cfg->tile_mode) {
+    if (!cfg->sort_particles) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode requires sort_particles"); }
+    if ((kp.gx | kp.gy | kp.gz) & 3) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode needs grid dimensions that are multiples of 4"); }
+    s->NBtot = kp.E * (kp.gx >> 2) * (kp.gy >> 2) * (kp.gz >> 2);
+    cudaFuncSetAttribute(k_g2p_grad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTileWarps * kTileN * sizeof(float4)));
+    s->chunk_max = cfg->chunk_max > 0 ? cfg->chunk_max : std::min(512, std::max(64, kp.EN / (148 * 8)));
+    int occ_cap = std::min(kp.EN, s->NBtot);
+    s->chunk_cap = kp.EN / s->chunk_max + occ_cap + 1;
+    DD_ALLOC(s->chunks, sizeof(int4) * s->chunk_cap);
+    DD_ALLOC(s->head_pos, sizeof(int) * (occ_cap + 1));
+    DD_ALLOC(s->head_flags, ENp);
+    DD_ALLOC(s->active_flag, s->NBtot);
+    DD_ALLOC(s->active, sizeof(int) * s->NBtot);
+    DD_ALLOC(s->counters, sizeof(int) * 8);
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceSelect::Flagged(nullptr, b1, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, s->counters, kp.EN);
+    cub::DeviceSelect::Flagged(nullptr, b2, cub::CountingInputIterator<int>(0), s->active_flag, s->active, s->counters, s->NBtot);
+    s->sel_bytes = std::max(b1, b2);
+    DD_ALLOC(s->sel_tmp, s->sel_bytes + 16);
+    // per-substep grid checkpoints (no scatter / grid-update replay in the backward pass) if they fit
+    size_t need = sizeof(float4) * eg * 2 * (size_t)cfg->max_steps, fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    bool want = cfg->grid_ckpt != 0;
+    if (want && need < (size_t)(0.6 * (double)fr)) {
+      s->grid_ckpt = true;
+      DD_ALLOC(s->gridck, sizeof(float4) * eg * (size_t)cfg->max_steps);
+      DD_ALLOC(s->gridvck, sizeof(float4) * eg * (size_t)cfg->max_steps);
+    }
+  }
   s->stage_floats = (size_t)kp.EN * (24 > kp.nb ? 24 : kp.nb);
   DD_ALLOC(s->stage, sizeof(float) * s->stage_floats);
 #undef DD_ALLOC
@@ -831,7 +1261,8 @@ void dd_sim_destroy(dd_sim *s) {
   if (!s) return;
   for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
   void *ptrs[] = {s->ckpt, s->grad[0], s->grad[1], s->mat0, s->yield, s->grid, s->grid_v, s->ggrid_v, s->ggrid, s->pos, s->rot, s->gpos, s->grot,
-                  s->tfsr, s->args, s->cull, s->perm, s->stage};
+                  s->tfsr, s->args, s->cull, s->perm, s->stage, s->keys, s->keys_alt, s->idx_alt, s->cub_tmp, s->mat_aos,
+                  s->chunks, s->head_pos, s->head_flags, s->active_flag, s->active, s->counters, s->sel_tmp, s->gridck, s->gridvck};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -842,7 +1273,8 @@ long long dd_sim_launch_count(dd_sim *s) { return s ? s->launches : 0; }
 int dd_sim_set_material(dd_sim *s, const float *mass, const float *vol, const float *mu_lam_yield, cudaStream_t st) {
   if (!s || !mass || !vol || !mu_lam_yield) return fail("dd_sim_set_material: null argument");
   int EN = s->kp.EN;
-  float *a = s->stage, *b = a + EN, *c = b + EN;
+  float *a = s->mat_aos, *b = a + EN, *c = b + EN;
+  s->have_material = true;
   DD_CUDA(cudaMemcpyAsync(a, mass, sizeof(float) * EN, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemcpyAsync(b, vol, sizeof(float) * EN, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemcpyAsync(c, mu_lam_yield, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
@@ -881,6 +1313,46 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
   DD_CUDA(cudaMemcpyAsync(sv, v, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemcpyAsync(sF, F, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemcpyAsync(sC, C, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  if (s->cfg.sort_particles) {
+    // cell-sorted particle order: environment, 4^3-cell brick, cell.  perm maps sorted -> original index.
+    k_sort_keys<<<nblk(EN), kT, 0, st>>>(s->kp, sx, s->keys, s->idx_alt);
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)s->kp.E * s->kp.G) ++bits;
+    DD_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_tmp, s->cub_bytes, s->keys, s->keys_alt, s->idx_alt, s->perm, EN, 0, bits, st));
+    if (s->cfg.tile_mode) {
+      const KP &kp = s->kp;
+      int host[4] = {0, 0, 0, 0};
+      k_mark_heads<<<nblk(EN), kT, 0, st>>>(EN, s->keys_alt, s->head_flags);
+      DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, s->counters + 2, EN, st));
+      DD_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(int) * 2, st));
+      DD_CUDA(cudaMemsetAsync(s->active_flag, 0, s->NBtot, st));
+      DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+      DD_CUDA(cudaStreamSynchronize(st));
+      int nbricks = host[2];
+      k_make_chunks<<<nblk(nbricks), kT, 0, st>>>(kp, nbricks, s->head_pos, s->keys_alt, s->chunk_max, s->chunks, s->counters, s->active_flag);
+      DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->active_flag, s->active, s->counters + 1, s->NBtot, st));
+      DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+      DD_CUDA(cudaStreamSynchronize(st));
+      s->nchunks = host[0];
+      s->nactive = host[1];
+      if (s->nchunks > s->chunk_cap) return fail("dd_sim_set_state: chunk list overflow");
+      k_interleave<<<nblk((long long)s->nchunks * 32), kT, 0, st>>>(kp, s->nchunks, s->chunks, s->perm, s->idx_alt);
+      std::swap(s->perm, s->idx_alt);
+      // the active region changed: drop stale graphs (they captured the old launch geometry) and stale grid contents
+      for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
+      s->graphs.clear();
+      size_t eg = (size_t)kp.E * kp.G;
+      DD_CUDA(cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st));
+      DD_CUDA(cudaMemsetAsync(s->grid_v, 0, sizeof(float4) * eg, st));
+      DD_CUDA(cudaMemsetAsync(s->ggrid_v, 0, sizeof(float4) * eg, st));
+      DD_CUDA(cudaMemsetAsync(s->ggrid, 0, sizeof(float4) * eg, st));
+    }
+    if (s->have_material) {
+      float *a = s->mat_aos;
+      k_pack_mat<<<nblk(EN), kT, 0, st>>>(EN, s->perm, a, a + EN, a + 2 * (size_t)EN, s->mat0, s->yield);
+    }
+    for (int k = 0; k < 2; ++k) s->grad_holds[k] = -1;  // gradient slots refer to the previous ordering
+  }
   k_pack<<<nblk(EN), kT, 0, st>>>(EN, s->perm, sx, sv, sF, sC, s->slot(f));
   DD_CUDA(cudaGetLastError());
   return 0;
@@ -932,7 +1404,7 @@ int dd_sim_forward(dd_sim *s, int f0, int n, cudaStream_t st) {
       if (s->cfg.svd_mode == 0) enqueue_forward_substep<0>(s, f, q); else enqueue_forward_substep<1>(s, f, q);
     }
   };
-  return run_graphed(s, 0, f0, n, st, 3LL * n, body);
+  return run_graphed(s, 0, f0, n, st, (long long)fwd_launches(s) * n, body);
 }
 
 int dd_sim_zero_grad(dd_sim *s, int f, cudaStream_t st) {
@@ -985,7 +1457,7 @@ int dd_sim_backward(dd_sim *s, int f0, int n, cudaStream_t st) {
       if (s->cfg.svd_mode == 0) enqueue_backward_substep<0>(s, f, q); else enqueue_backward_substep<1>(s, f, q);
     }
   };
-  int rc = run_graphed(s, 1, f0, n, st, 5LL * n, body);
+  int rc = run_graphed(s, 1, f0, n, st, (long long)bwd_launches(s) * n, body);
   if (rc) return rc;
   s->grad_holds[f0 & 1] = f0;
   s->grad_holds[(f0 + 1) & 1] = n >= 1 ? f0 + 1 : s->grad_holds[(f0 + 1) & 1];
@@ -1053,7 +1525,7 @@ int dd_sim_compute_dist_grad(dd_sim *s, int f, const float *dist_grad, cudaStrea
 int dd_sim_sync(dd_sim *s, cudaStream_t st) {
   if (!s) return fail("dd_sim_sync: null simulator");
   DD_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return check_overflow(s);
 }
 
 }  // extern "C"

@@ -25,7 +25,7 @@ class EngineError(RuntimeError):
 
 class FusedSim:
     def __init__(self, n_envs, n_particles, n_bodies, grid_dim, dx, dt, max_steps, ground_friction=0.0, ground_height=3.0,
-                 gravity=(0.0, -30.0, 0.0), svd_mode=1, use_graphs=True, library=None, stream=None):
+                 gravity=(0.0, -30.0, 0.0), svd_mode=1, use_graphs=True, sort_particles=True, tile_mode=True, grid_ckpt=True, chunk_max=0, library=None, stream=None):
         self.lib = library if library is not None else _default_lib
         self.E, self.N, self.nb = int(n_envs), int(n_particles), int(n_bodies)
         self.grid_dim = tuple(int(g) for g in grid_dim)
@@ -33,7 +33,7 @@ class FusedSim:
         self.dx, self.dt = float(dx), float(dt)
         self.stream = stream  # raw cudaStream_t (int) or None for the legacy default stream
         cfg = dd_sim_config(self.E, self.N, self.nb, *self.grid_dim, self.max_steps, self.dx, self.dt, float(ground_friction),
-                            float(ground_height), (ctypes.c_float * 3)(*[float(g) for g in gravity]), int(svd_mode), int(bool(use_graphs)))
+                            float(ground_height), (ctypes.c_float * 3)(*[float(g) for g in gravity]), int(svd_mode), int(bool(use_graphs)), int(bool(sort_particles)), int(bool(tile_mode)), int(bool(grid_ckpt)), int(chunk_max))
         handle = ctypes.c_void_p()
         self._h = None
         self._check(self.lib.dd_sim_create(ctypes.byref(cfg), ctypes.byref(handle)))

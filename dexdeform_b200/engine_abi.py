@@ -9,7 +9,7 @@ S = c_void_p  # cudaStream_t
 class dd_sim_config(ctypes.Structure):
     _fields_ = [("n_envs", c_int), ("n_particles", c_int), ("n_bodies", c_int), ("grid_x", c_int), ("grid_y", c_int),
                 ("grid_z", c_int), ("max_steps", c_int), ("dx", c_float), ("dt", c_float), ("ground_friction", c_float),
-                ("ground_height", c_float), ("gravity", c_float * 3), ("svd_mode", c_int), ("use_graphs", c_int)]
+                ("ground_height", c_float), ("gravity", c_float * 3), ("svd_mode", c_int), ("use_graphs", c_int), ("sort_particles", c_int), ("tile_mode", c_int), ("grid_ckpt", c_int), ("chunk_max", c_int)]
 
 
 ABI2 = {

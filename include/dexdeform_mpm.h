@@ -134,6 +134,10 @@ typedef struct {
   float gravity[3];    /* as uploaded by the reference, i.e. cfg.gravity * 30 (mpm/simulator.py:385) */
   int svd_mode;        /* 0: reference-order fp64 Jacobi SVD, 1: fp32 in-register SVD (production) */
   int use_graphs;      /* capture forward/backward ranges into CUDA graphs, cached per (f0, n) */
+  int sort_particles;  /* dd_sim_set_state re-orders particles by (env, 4^3-cell brick, cell); results are returned in the caller's order */
+  int tile_mode;       /* 1: warp-private shared-memory tiles for the scatters + grid kernels on active bricks only; 0: global reductions on the dense grid */
+  int grid_ckpt;       /* 1: keep every substep's grid in HBM when it fits, so the adjoint does not replay scatter + grid update */
+  int chunk_max;       /* particles per warp-chunk in tile mode (0 = choose from the problem size) */
 } dd_sim_config;
 
 const char *dd_last_error(void);

@@ -27,6 +27,31 @@ def run_abi1(lib, sc, S, seedg):
     return out
 
 
+def permuted(sc, seedg, seed=0):
+    """The same scene with particles listed in another order (mathematically identical problem)."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(sc["n"])
+    sc2 = dict(sc)
+    for k in ("x", "v", "F", "C", "mass", "vol", "mu_lam_yield"):
+        sc2[k] = np.ascontiguousarray(sc[k][perm])
+    return sc2, {k: np.ascontiguousarray(v[perm]) for k, v in seedg.items()}, np.argsort(perm)
+
+
+def reference_spread(lib, sc, S, seedg, ref):
+    """The reference's own sensitivity to summation order: re-run it on the permuted scene and compare.  Float atomics
+    make the reference irreproducible at this level, so no implementation can be asked to match it tighter."""
+    sc2, seed2, inv = permuted(sc, seedg)
+    other = run_abi1(lib, sc2, S, seed2)
+    spread = {}
+    for grp in ("state", "grad"):
+        for k, v in ref[grp].items():
+            spread[k] = rel_err(other[grp][k][inv], v)
+    for k in ("gpos", "grot"):
+        if k in ref:
+            spread[k] = rel_err(other[k], ref[k])
+    return spread
+
+
 def run_engine(sc, S, seedg, E=1, **kw):
     sim = FusedSim.from_scene(sc, n_envs=E, max_steps=S, **kw)
     sim.forward(0, S)
@@ -41,25 +66,27 @@ def run_engine(sc, S, seedg, E=1, **kw):
     return out
 
 
-@pytest.mark.parametrize("svd_mode,graphs", [(0, False), (1, True)])
-def test_engine_matches_reference_cuda_short(ref_gpu, svd_mode, graphs):
+@pytest.mark.parametrize("svd_mode,graphs,tile", [(0, False, False), (0, False, True), (1, True, True), (1, True, False)])
+def test_engine_matches_reference_cuda_short(ref_gpu, svd_mode, graphs, tile):
     S = 4
     sc = scene_tutorial(steps=S, perturb=0.02, vel_scale=0.3, on_floor=True, seed=2)
     seedg = loss_seed(sc["n"], 3)
     ref = run_abi1(ref_gpu, sc, S, seedg)
-    eng = run_engine(sc, S, seedg, svd_mode=svd_mode, use_graphs=graphs)
+    spread = reference_spread(ref_gpu, sc, S, seedg, ref)
+    eng = run_engine(sc, S, seedg, svd_mode=svd_mode, use_graphs=graphs, tile_mode=tile)
     tight = svd_mode == 0
+    tol_of = lambda key, base: max(base * (1 if tight else 5), 5 * spread[key])
     assert np.abs(eng["state"]["x"][0] - ref["state"]["x"]).max() < (2e-7 if tight else 1e-6)
     for k, tol in dict(v=2e-5, F=5e-6, C=1e-4).items():
         e = rel_err(eng["state"][k][0], ref["state"][k])
-        assert e < tol * (1 if tight else 5), (k, e)
-    for k, tol in dict(x=2e-4, v=2e-4, C=5e-2, F=5e-2).items():
+        assert e < tol_of(k, tol), (k, e, spread[k])
+    for k, tol in dict(x=2e-4, v=2e-4, C=1e-2, F=1e-2).items():
         e = rel_err(eng["grad"][k][0], ref["grad"][k + "_grad"])
-        assert e < tol * (1 if tight else 3), (k, e)
+        assert e < tol_of(k + "_grad", tol), (k, e, spread[k + "_grad"])
         assert cosine(eng["grad"][k][0], ref["grad"][k + "_grad"]) > 0.999
-    assert rel_err(eng["gpos"][:, 0], ref["gpos"]) < (2e-4 if tight else 2e-3)
-    assert rel_err(eng["grot"][:, 0], ref["grot"]) < (2e-4 if tight else 2e-3)
-    assert eng["launches"] == 3 * S + 5 * S
+    assert rel_err(eng["gpos"][:, 0], ref["gpos"]) < tol_of("gpos", 2e-4)
+    assert rel_err(eng["grot"][:, 0], ref["grot"]) < tol_of("grot", 2e-4)
+    assert eng["launches"] == (4 * S + 4 * S if tile else 3 * S + 5 * S)
 
 
 def test_engine_rollout_50_substeps_vs_reference(ref_gpu):
@@ -113,7 +140,9 @@ def test_engine_vs_oracle_and_env_batching(oracle_lib):
             assert rel_err(state[k][e], refs[e]["state"][k]) < tol, (e, k)
         for k in ("x", "v"):
             assert rel_err(grad[k][e], refs[e]["grad"][k + "_grad"]) < 5e-4, (e, k)
-        assert rel_err(gpos[:, e], refs[e]["gpos"]) < 5e-4 and rel_err(grot[:, e], refs[e]["grot"]) < 5e-4
+        # an environment may have (almost) no contact at all: tolerance relative to max(|ref|, 1)
+        for a, b in ((gpos[:, e], refs[e]["gpos"]), (grot[:, e], refs[e]["grot"])):
+            assert np.abs(a - b).max() < 5e-4 * max(np.abs(b).max(), 1.0), (e, np.abs(a - b).max(), np.abs(b).max())
     # observations: signed distances and their adjoint against the oracle
     d = sim.compute_dist(S)
     a1 = Abi1Sim(oracle_lib, scs[1], S)
@@ -136,3 +165,43 @@ def test_engine_error_reporting():
     with pytest.raises(EngineError, match="no gradient seeded"):
         sim.backward(0, 2)
     sim.close()
+
+
+def test_tiled_path_equals_dense_path_with_drift_and_dense_cells():
+    """The shared-memory tile path (conflict serialisation, drift fallback to the grid) against the plain global-reduction
+    path on a scene built to stress it: 40 particles per cell (many same-cell lanes per round) moving 1.5 cells per substep
+    (so after the first substep most particles have left the tile they were sorted into)."""
+    S = 2
+    sc = make_scene(4000, 32, box_center=(0.5, 0.4, 0.5), box_width=(0.14, 0.14, 0.14), steps=S, perturb=0.02, nb=4, seed=13, ground_friction=0.3)
+    sc["v"][:] = np.array([900.0, -600.0, 400.0], np.float32) * (1.0 + 0.01 * np.random.default_rng(0).normal(size=(4000, 3)).astype(np.float32))
+    seedg = loss_seed(4000, 5)
+    outs = {}
+    for tile in (False, True):
+        outs[tile] = run_engine(sc, S, seedg, svd_mode=0, tile_mode=tile, use_graphs=False, grid_ckpt=tile)
+    a, b = outs[False], outs[True]
+    for k in ("x", "v", "F", "C"):
+        assert rel_err(b["state"][k], a["state"][k]) < 2e-5, (k, rel_err(b["state"][k], a["state"][k]))
+    for k in ("x", "v"):
+        assert rel_err(b["grad"][k], a["grad"][k]) < 2e-4, (k, rel_err(b["grad"][k], a["grad"][k]))
+    assert np.abs(b["gpos"] - a["gpos"]).max() < 2e-4 * max(np.abs(a["gpos"]).max(), 1.0)
+
+
+def test_tiled_path_reports_runaway_particles():
+    sc = make_scene(512, 32, box_center=(0.3, 0.5, 0.5), box_width=(0.05, 0.05, 0.05), steps=3, nb=0, seed=3, ground_friction=0.0)
+    sc["v"][:] = np.array([3000.0, 0.0, 0.0], np.float32)  # 4.8 cells per substep
+    sim = FusedSim.from_scene(sc, max_steps=3, tile_mode=True)
+    sim.forward(0, 3)
+    with pytest.raises(EngineError, match="re-sort more often"):
+        sim.sync()
+    sim.close()
+
+
+def test_recompute_mode_matches_checkpoint_mode():
+    S = 3
+    sc = make_scene(3000, 32, box_width=(0.14, 0.1, 0.14), steps=S, perturb=0.02, vel_scale=0.5, on_floor=True, seed=21, nb=6)
+    seedg = loss_seed(3000, 2)
+    a = run_engine(sc, S, seedg, grid_ckpt=True)
+    b = run_engine(sc, S, seedg, grid_ckpt=False)
+    for k in ("x", "v", "F", "C"):
+        assert rel_err(b["grad"][k], a["grad"][k]) < 1e-5, k
+    assert a["launches"] == 8 * S and b["launches"] == 11 * S

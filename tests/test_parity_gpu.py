@@ -29,8 +29,13 @@ def test_kernel_by_kernel_vs_reference_cuda(product_lib, ref_gpu):
     a, b = ref.get_temp(*names), new.get_temp(*names)
     for k in ("sig", "F"):
         assert rel_err(b[k], a[k]) < 1e-6, k
-    for k in ("U", "V"):  # same double-precision algorithm; only FMA contraction may differ
-        assert rel_err(b[k], a[k]) < 1e-5, k
+    # U and V individually are ill-conditioned where two singular values are close (a 1e-7 perturbation rotates them
+    # by 1e-7 / (s_i - s_j)); the quantities the path consumes are R = U V^T and U diag(s) V^T
+    for X in (a, b):
+        X["R"] = np.einsum("nij,nkj->nik", X["U"].reshape(-1, 3, 3), X["V"].reshape(-1, 3, 3))
+        X["rec"] = np.einsum("nij,nj,nkj->nik", X["U"].reshape(-1, 3, 3), X["sig"], X["V"].reshape(-1, 3, 3))
+    assert rel_err(b["R"], a["R"]) < 2e-6 and rel_err(b["rec"], a["rec"]) < 2e-6
+    assert np.median(np.abs(b["U"] - a["U"])) < 1e-6
     for k in ("grid_m", "grid_v_in", "grid_v_out", "grid_body_v_in"):
         assert rel_err(b[k], a[k]) < 2e-5, (k, rel_err(b[k], a[k]))
     sa, sb = ref.get(1), new.get(1)

@@ -16,12 +16,14 @@ grid = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 E = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 svd = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+tile = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+ckpt = int(sys.argv[7]) if len(sys.argv) > 7 else 1
 w = 0.4 if n >= 500000 else 0.09 * (n / 10000) ** (1 / 3)
 sc = make_scene(n, grid, box_center=(0.5, 0.3, 0.5), box_width=(w, w, w), steps=S, seed=0, hand_scale=6.0 if n >= 500000 else 1.5)
 torch.cuda.init()
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
-    sim = FusedSim.from_scene(sc, n_envs=E, max_steps=S, svd_mode=svd, stream=stream.cuda_stream)
+    sim = FusedSim.from_scene(sc, n_envs=E, max_steps=S, svd_mode=svd, tile_mode=tile, grid_ckpt=ckpt, stream=stream.cuda_stream)
     gx = np.zeros((E, n, 3), np.float32); gx[..., 1] = -1.0 / n
 
     def fwd():
@@ -54,6 +56,6 @@ with torch.cuda.stream(stream):
     tot = res["fwd"] + res["bwd"]
     units = E * n * S
     peak = 6547.5
-    print(f"n={n} grid={grid}^3 S={S} E={E} svd_mode={svd}")
+    print(f"n={n} grid={grid}^3 S={S} E={E} svd_mode={svd} tile={tile} grid_ckpt={ckpt}")
     print(f"  forward  {res['fwd'] / S * 1e3:9.1f} us/substep   backward {res['bwd'] / S * 1e3:9.1f} us/substep")
     print(f"  fwd+bwd  {units / tot / 1e3:9.1f} M particle-substeps/s   {520 * units / tot / 1e6:8.1f} GB/s algorithmic = {520 * units / tot / 1e6 / peak * 100:.1f}% of {peak} GB/s")
