@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <string>
 #include <tuple>
@@ -34,7 +35,7 @@ int fail(const std::string &msg) { g_last_error = msg; return 1; }
   } while (0)
 
 constexpr int kT = 256;
-constexpr int kPlaneFloats = 25;  // 16 (x,v,C + pad) + 9 (F)
+constexpr int kPlaneFloats = 29;  // 16 (x,v,C + pad) + 9 (F) + 4 (SVD warm-start quaternion)
 
 struct KP {            // kernel parameters shared by all kernels
   int E, N, EN, nb, G, gx, gy, gz;
@@ -45,6 +46,7 @@ struct KP {            // kernel parameters shared by all kernels
 // ---- particle planes ----------------------------------------------------------------------------------------
 // slot layout (floats): [0,4EN) P0=(x.x,x.y,x.z,v.x)  [4EN,8EN) P1=(v.y,v.z,C00,C01)  [8EN,12EN) P2=(C02,C10,C11,C12)
 //                       [12EN,16EN) P3=(C20,C21,C22,0) [16EN,20EN) F0=(F00..F10) [20EN,24EN) F1=(F11..F21) [24EN,25EN) F2=F22
+//                       [25EN,29EN) Q=(qx,qy,qz,qw): quaternion of V of the SVD that produced this slot's F (warm start / replay)
 struct XVC { V3 x, v; M3 C; };
 DD_DEV const float4 *plane4(const float *slot, int EN, int k) { return reinterpret_cast<const float4 *>(slot + (size_t)4 * k * EN); }
 DD_DEV float4 *plane4(float *slot, int EN, int k) { return reinterpret_cast<float4 *>(slot + (size_t)4 * k * EN); }
@@ -78,6 +80,21 @@ DD_DEV void store_F(float *slot, int EN, int p, const M3 &F) {
   plane4(slot, EN, 5)[p] = make_float4(F.a11, F.a12, F.a20, F.a21);
   slot[(size_t)24 * EN + p] = F.a22;
 }
+DD_DEV float4 load_q(const float *slot, int EN, int p) { return ldg_stream(reinterpret_cast<const float4 *>(slot + (size_t)25 * EN) + p); }
+DD_DEV void store_q(float *slot, int EN, int p, float4 q) { reinterpret_cast<float4 *>(slot + (size_t)25 * EN)[p] = q; }
+// shared-memory access that the compiler may neither reorder nor merge (the tile updates of one warp rely on program order)
+DD_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+DD_DEV float4 lds_v4(unsigned a) {
+  float4 r;
+  asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
+  return r;
+}
+DD_DEV void sts_v4_if(unsigned a, float4 v, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4}; }" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) : "memory");
+}
+// tile slot of node (tx,ty,tz) in an 8^3 tile; the low bits are swizzled so that lanes in neighbouring cells do not pile up
+// on the same bank group
+DD_DEV int tile_slot(int tx, int ty, int tz) { return tx << 6 | ty << 3 | (tz ^ (((ty & 1) << 2 | (ty & 2) >> 1) ^ ((tx & 1) << 1) ^ ((tx & 2) << 1))); }
 DD_DEV void red_add_v4(float4 *addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -100,10 +117,11 @@ struct Constit {
   Plastic pl;
   float J, scale;
 };
+// q: warm-start quaternion in, converged quaternion out (svd_mode 1); max_sweeps = 0 replays a stored factorisation
 template <int SVD>
-DD_DEV void constitutive(const XVC &s, const M3 &F, float4 m0, float yield, const KP &kp, Constit &c) {
+DD_DEV void constitutive(const XVC &s, const M3 &F, float4 m0, float yield, const KP &kp, Constit &c, float4 &q, int max_sweeps) {
   c.Ft = mul(mdiag(1.f) + s.C * kp.dt, F);
-  if (SVD == 0) svd3_f64(c.Ft, c.U, c.sigma, c.Vm); else svd3_f32(c.Ft, c.U, c.sigma, c.Vm);
+  if (SVD == 0) svd3_f64(c.Ft, c.U, c.sigma, c.Vm); else svd3_warm(c.Ft, q.x, q.y, q.z, q.w, c.U, c.sigma, c.Vm, max_sweeps);
   c.J = von_mises(c.Ft, c.U, c.sigma, c.Vm, yield, m0.z, c.nF, c.pl);
   c.r = mul_nt(c.U, c.Vm);
   c.scale = -kp.dt * m0.y * 4.f * kp.inv_dx * kp.inv_dx;
@@ -121,8 +139,9 @@ __global__ void __launch_bounds__(kT) k_p2g(KP kp, const float *__restrict__ cur
   M3 F = load_F(cur, kp.EN, p);
   float4 m0 = __ldg(mat0 + p);
   Constit c;
-  constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c);
-  if (WRITE_F) store_F(nxt, kp.EN, p, c.nF);
+  float4 q = load_q(cur, kp.EN, p);
+  constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c, q, 6);
+  if (WRITE_F) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); }
   Stencil st = make_stencil_safe(s.x, kp);
   float m = m0.x;
   V3 mv = m * s.v;
@@ -231,35 +250,37 @@ __global__ void __launch_bounds__(kT) k_grid(KP kp, const float4 *__restrict__ g
   grid_v[node] = make_float4(v.x, v.y, v.z, 0.f);
 }
 
-// g2p (integrator.cu:1059-1109)
+// g2p (integrator.cu:1059-1109).  v' = sum w v_n ; C' = 4/dx * sum (w v_n) (x) (offset - fx)
 __global__ void __launch_bounds__(kT) k_g2p(KP kp, const float *__restrict__ cur, float *__restrict__ nxt, const float4 *__restrict__ grid_v) {
   int p = blockIdx.x * kT + threadIdx.x;
   if (p >= kp.EN) return;
   float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
   V3 x = v3(a.x, a.y, a.z);
   Stencil st = make_stencil_safe(x, kp);
-  const float4 *g = grid_v + (size_t)(p / kp.N) * kp.G;
+  const float4 *g = grid_v + (size_t)(p / kp.N) * kp.G + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
+  float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
   V3 nv = vzero();
   M3 nC = mzero();
-  float s4 = kp.inv_dx * 4.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    float wi = pick(st.w0, st.w1, st.w2, i, 0);
+    float di = (float)i - st.fx.x;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      float wij = wi * pick(st.w0, st.w1, st.w2, j, 1);
-      int row = ((st.bx + i) * kp.gy + st.by + j) * kp.gz + st.bz;
+      float wij = wx[i] * wy[j], dj = (float)j - st.fx.y;
+      const float4 *row = g + (i * kp.gy + j) * kp.gz;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        float w = wij * pick(st.w0, st.w1, st.w2, k, 2);
-        V3 dpos = v3((float)i, (float)j, (float)k) - st.fx;
-        float4 t = __ldg(g + row + k);
-        V3 v = v3(t.x, t.y, t.z);
-        nv += v * w;
-        nC += outer(v, dpos) * (w * s4);
+        float w = wij * wz[k], dk = (float)k - st.fx.z;
+        float4 t = __ldg(row + k);
+        V3 u = v3(t.x * w, t.y * w, t.z * w);
+        nv += u;
+        nC.a00 = fmaf(u.x, di, nC.a00); nC.a01 = fmaf(u.x, dj, nC.a01); nC.a02 = fmaf(u.x, dk, nC.a02);
+        nC.a10 = fmaf(u.y, di, nC.a10); nC.a11 = fmaf(u.y, dj, nC.a11); nC.a12 = fmaf(u.y, dk, nC.a12);
+        nC.a20 = fmaf(u.z, di, nC.a20); nC.a21 = fmaf(u.z, dj, nC.a21); nC.a22 = fmaf(u.z, dk, nC.a22);
       }
     }
   }
+  nC = nC * (kp.inv_dx * 4.f);
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx;
   V3 t = x + nv * kp.dt;
@@ -484,9 +505,13 @@ __global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restric
   grid_grad_body(kp, node, inr, env, cell / kp.gz / kp.gy, (cell / kp.gz) % kp.gy, cell % kp.gz, grid, ggrid_v, ggrid, bt, gpos, grot, gnpos, gnrot);
 }
 
-// p2g_grad + compute_svd_grad (integrator.cu:396-627, 110-186) fused; writes the complete gradient of state t
+// p2g_grad + compute_svd_grad (integrator.cu:396-627, 110-186) fused; writes the complete gradient of state t.
+// The gather over the 27 nodes is regrouped so that every node costs ~30 FP instructions:
+//   T  = sum N (g_mv (x) dpos)          -> dL/dstress = scale T, dL/dC += m T
+//   Sv = sum N g_mv                     -> dL/dv = m Sv, and the -N A^T g_mv term of dL/dx is -A^T Sv
+//   dL/dx += sum gradN (m g_m + g_mv . (m v + A dpos))
 template <int SVD>
-__global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict__ cur, const float4 *__restrict__ mat0,
+__global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict__ cur, const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                                                  const float *__restrict__ yield, const float4 *__restrict__ ggrid,
                                                  const float *__restrict__ gin, float *__restrict__ gout) {
   int p = blockIdx.x * kT + threadIdx.x;
@@ -496,38 +521,50 @@ __global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict_
   float4 m0 = __ldg(mat0 + p);
   float yl = __ldg(yield + p);
   Constit c;
-  constitutive<SVD>(s, F, m0, yl, kp, c);
+  float4 q = load_q(nxt, kp.EN, p);  // the forward pass left the converged quaternion of this very SVD in the next slot
+  constitutive<SVD>(s, F, m0, yl, kp, c, q, 0);
   float mu = m0.z, lam = m0.w, m_p = m0.x;
   Stencil st = make_stencil_safe(s.x, kp);
   V3 d0, d1, d2;
   stencil_dw(st, kp.inv_dx, d0, d1, d2);
-  const float4 *gg = ggrid + (size_t)(p / kp.N) * kp.G;
-  M3 g_stress = mzero(), g_C = mzero();
-  V3 g_x = vzero(), g_v = vzero();
+  float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
+  float ex[3] = {d0.x, d1.x, d2.x}, ey[3] = {d0.y, d1.y, d2.y}, ez[3] = {d0.z, d1.z, d2.z};
+  V3 c0 = v3(c.affine.a00, c.affine.a10, c.affine.a20) * kp.dx, c1 = v3(c.affine.a01, c.affine.a11, c.affine.a21) * kp.dx,
+     c2 = v3(c.affine.a02, c.affine.a12, c.affine.a22) * kp.dx;
+  V3 base = m_p * s.v - (c0 * st.fx.x + c1 * st.fx.y + c2 * st.fx.z);
+  const float4 *gg = ggrid + (size_t)(p / kp.N) * kp.G + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
+  M3 T = mzero();
+  V3 Sv = vzero(), g_x = vzero();
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
+    float pi = ((float)i - st.fx.x) * kp.dx;
+    V3 vi = base + c0 * (float)i;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      int row = ((st.bx + i) * kp.gy + st.by + j) * kp.gz + st.bz;
+      float wij = wx[i] * wy[j], a1 = ex[i] * wy[j], a2 = wx[i] * ey[j], pj = ((float)j - st.fx.y) * kp.dx;
+      V3 vij = vi + c1 * (float)j;
+      const float4 *row = gg + (i * kp.gy + j) * kp.gz;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        float wx = pick(st.w0, st.w1, st.w2, i, 0), wy = pick(st.w0, st.w1, st.w2, j, 1), wz = pick(st.w0, st.w1, st.w2, k, 2);
-        float N = wx * wy * wz;
-        V3 dpos = (v3((float)i, (float)j, (float)k) - st.fx) * kp.dx;
-        float4 t = __ldg(gg + row + k);
-        V3 ogv = v3(t.x, t.y, t.z);
-        V3 gN = v3(pick(d0, d1, d2, i, 0) * wy * wz, wx * pick(d0, d1, d2, j, 1) * wz, wx * wy * pick(d0, d1, d2, k, 2));
-        M3 tmp = outer(ogv, dpos);
-        g_stress += (N * c.scale) * tmp;
-        g_C += (N * m_p) * tmp;
-        g_v += (N * m_p) * ogv;
-        g_x += (t.w * m_p) * gN;
-        g_x += (dot(s.v, ogv) * m_p) * gN;
-        g_x += (-N) * mul_t(c.affine, ogv) + dot(mul(c.affine, dpos), ogv) * gN;
+        float pk = ((float)k - st.fx.z) * kp.dx;
+        float4 t = __ldg(row + k);
+        V3 val = vij + c2 * (float)k;
+        float N = wij * wz[k];
+        V3 u = v3(t.x * N, t.y * N, t.z * N);
+        T.a00 = fmaf(u.x, pi, T.a00); T.a01 = fmaf(u.x, pj, T.a01); T.a02 = fmaf(u.x, pk, T.a02);
+        T.a10 = fmaf(u.y, pi, T.a10); T.a11 = fmaf(u.y, pj, T.a11); T.a12 = fmaf(u.y, pk, T.a12);
+        T.a20 = fmaf(u.z, pi, T.a20); T.a21 = fmaf(u.z, pj, T.a21); T.a22 = fmaf(u.z, pk, T.a22);
+        Sv += u;
+        float sc = fmaf(m_p, t.w, t.x * val.x + t.y * val.y + t.z * val.z);
+        float tt = wz[k] * sc, uu = ez[k] * sc;
+        g_x.x = fmaf(a1, tt, g_x.x); g_x.y = fmaf(a2, tt, g_x.y); g_x.z = fmaf(wij, uu, g_x.z);
       }
     }
   }
-  float4 part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by k_g2p_grad
+  g_x -= mul_t(c.affine, Sv);
+  M3 g_stress = c.scale * T, g_C = m_p * T;
+  V3 g_v = m_p * Sv;
+  float4 part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by the g2p adjoint
   g_x += v3(part.x, part.y, part.z);
   M3 gF_next = load_F(gin, kp.EN, p);
   M3 g_r = (-2.f * mu) * mul(g_stress, c.nF);
@@ -594,68 +631,64 @@ DD_DEV void check_drift(int tx, int ty, int tz, int *overflow) {
 
 template <int SVD, bool WRITE_F>
 __global__ void __launch_bounds__(32 * kTileWarps, 4) k_p2g_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
-                                                              float *__restrict__ nxt, const float4 *__restrict__ mat0,
-                                                              const float *__restrict__ yield, float4 *__restrict__ grid, int *overflow) {
+                                                                 float *__restrict__ nxt, const float4 *__restrict__ mat0,
+                                                                 const float *__restrict__ yield, float4 *__restrict__ grid, int *overflow) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int ci = blockIdx.x * kTileWarps + warp;
   if (ci >= nchunks) return;
   float4 *tile = dd_smem + warp * kTileN;
+  unsigned tbase = smem_u32(tile);
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   float4 *g = grid + (size_t)cg.env * kp.G;
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane < cg.L - (j >= cg.q ? 1 : 0);
-    int p = cg.start + round_off(j, cg.L, cg.q) + lane;
-    Stencil st;
-    V3 mv = vzero(), c0 = vzero(), c1 = vzero(), c2 = vzero();
-    float m = 0.f;
-    int tx = 0, ty = 0, tz = 0;
-    if (act) {
-      XVC s = load_xvc(cur, kp.EN, p);
-      M3 F = load_F(cur, kp.EN, p);
-      float4 m0 = __ldg(mat0 + p);
-      Constit c;
-      constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c);
-      if (WRITE_F) store_F(nxt, kp.EN, p, c.nF);
-      st = make_stencil_safe(s.x, kp);
-      m = m0.x;
-      mv = m * s.v;
-      c0 = v3(c.affine.a00, c.affine.a10, c.affine.a20); c1 = v3(c.affine.a01, c.affine.a11, c.affine.a21); c2 = v3(c.affine.a02, c.affine.a12, c.affine.a22);
-      tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
-    }
+    int p = act ? cg.start + round_off(j, cg.L, cg.q) + lane : cg.start;  // idle lanes shadow a valid particle, contribute nothing
+    XVC s = load_xvc(cur, kp.EN, p);
+    M3 F = load_F(cur, kp.EN, p);
+    float4 m0 = __ldg(mat0 + p);
+    float4 q = load_q(cur, kp.EN, p);
+    Constit c;
+    constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c, q, 6);
+    if (WRITE_F && act) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); }
+    Stencil st = make_stencil_safe(s.x, kp);
+    float m = m0.x;
+    V3 c0 = v3(c.affine.a00, c.affine.a10, c.affine.a20) * kp.dx, c1 = v3(c.affine.a01, c.affine.a11, c.affine.a21) * kp.dx,
+       c2 = v3(c.affine.a02, c.affine.a12, c.affine.a22) * kp.dx;
+    V3 base = m * s.v - (c0 * st.fx.x + c1 * st.fx.y + c2 * st.fx.z);  // value at node offset (0,0,0); +c_a per step along axis a
+    float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
+    int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
     int rank = __popc(peers & ((1u << lane) - 1u));
     int maxr = __reduce_max_sync(0xffffffffu, rank);
-    for (int r = 0; r <= maxr; ++r) {
+    if (!in_tile) { tx = ty = tz = 0; }
+    for (int r = 0; r <= maxr; ++r) {  // one pass unless two lanes of this round share a cell
       bool mine = in_tile && rank == r;
-#pragma unroll 1
+#pragma unroll
       for (int i = 0; i < 3; ++i) {
-        float wi = pick(st.w0, st.w1, st.w2, i, 0);
-        V3 ai = mv + c0 * (((float)i - st.fx.x) * kp.dx);
-#pragma unroll 1
+        V3 vi = base + c0 * (float)i;
+#pragma unroll
         for (int jj = 0; jj < 3; ++jj) {
-          float wij = wi * pick(st.w0, st.w1, st.w2, jj, 1);
-          V3 aij = ai + c1 * (((float)jj - st.fx.y) * kp.dx);
-          int row = (tx + i) << 6 | (ty + jj) << 3 | tz;
+          V3 vij = vi + c1 * (float)jj;
+          float wij = wx[i] * wy[jj];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            float w = wij * pick(st.w0, st.w1, st.w2, k, 2);
-            V3 a = (aij + c2 * (((float)k - st.fx.z) * kp.dx)) * w;
-            if (mine) {
-              float4 t = tile[row + k];
-              t.x += a.x; t.y += a.y; t.z += a.z; t.w += m * w;
-              tile[row + k] = t;
-            }
-            __syncwarp();
+            V3 val = vij + c2 * (float)k;
+            float w = wij * wz[k];
+            unsigned a = tbase + 16u * (unsigned)tile_slot(tx + i, ty + jj, tz + k);
+            float4 t = lds_v4(a);
+            t.x = fmaf(val.x, w, t.x); t.y = fmaf(val.y, w, t.y); t.z = fmaf(val.z, w, t.z); t.w = fmaf(m, w, t.w);
+            sts_v4_if(a, t, mine);
           }
         }
       }
     }
     if (act && !in_tile) {  // drifted more than one cell since the last sort: straight to the grid
+      tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
       check_drift(tx, ty, tz, overflow);
 #pragma unroll 1
       for (int i = 0; i < 3; ++i)
@@ -664,99 +697,106 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) k_p2g_tile(KP kp, int nchu
 #pragma unroll 1
           for (int k = 0; k < 3; ++k) {
             float w = pick(st.w0, st.w1, st.w2, i, 0) * pick(st.w0, st.w1, st.w2, jj, 1) * pick(st.w0, st.w1, st.w2, k, 2);
-            V3 a = (mv + c0 * (((float)i - st.fx.x) * kp.dx) + c1 * (((float)jj - st.fx.y) * kp.dx) + c2 * (((float)k - st.fx.z) * kp.dx)) * w;
+            V3 a = (base + c0 * (float)i + c1 * (float)jj + c2 * (float)k) * w;
             red_add_v4(g + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, a.x, a.y, a.z, m * w);
           }
     }
   }
   __syncwarp();
   for (int n = lane; n < kTileN; n += 32) {
-    float4 t = tile[n];
-    int nx = cg.ox + (n >> 6), ny = cg.oy + ((n >> 3) & 7), nz = cg.oz + (n & 7);
+    int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
+    float4 t = tile[tile_slot(txx, tyy, tzz)];
+    int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
     if ((t.w != 0.f || t.x != 0.f || t.y != 0.f || t.z != 0.f) && (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
       red_add_v4(g + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, t.w);
   }
 }
 
-// g2p_grad on tiles: grid velocities are gathered from a tile copy, their adjoint is scattered into a second tile
+// g2p_grad on tiles (integrator.cu:1527-1614): grid velocities are gathered from a tile copy, their adjoint is scattered
+// into a second tile.  With h_n = gv' + (4/dx) gC' (offset_n - fx) (affine in the offset, so evaluated incrementally):
+//   d/d v_n  = w_n h_n ;  dL/dx = -(4/dx^2) gC'^T (sum w_n v_n) + sum gradN_n (v_n . h_n)
 __global__ void __launch_bounds__(32 * kTileWarps, 3) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
-                                                                   const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
-                                                                   const float *__restrict__ gin, float *__restrict__ gout,
-                                                                   float4 *__restrict__ ggrid_v, int *overflow) {
+                                                                      const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
+                                                                      const float *__restrict__ gin, float *__restrict__ gout,
+                                                                      float4 *__restrict__ ggrid_v, int *overflow) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int ci = blockIdx.x * kTileWarps + warp;
   if (ci >= nchunks) return;
   float4 *tv = dd_smem + warp * (2 * kTileN), *tg = tv + kTileN;
+  unsigned vbase = smem_u32(tv), gbase = smem_u32(tg);
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   size_t goff = (size_t)cg.env * kp.G;
   for (int n = lane; n < kTileN; n += 32) {
-    int nx = cg.ox + (n >> 6), ny = cg.oy + ((n >> 3) & 7), nz = cg.oz + (n & 7);
+    int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
+    int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
     bool ok = (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz;
-    tv[n] = ok ? __ldg(grid_v + goff + (nx * kp.gy + ny) * kp.gz + nz) : make_float4(0.f, 0.f, 0.f, 0.f);
-    tg[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int slot = tile_slot(txx, tyy, tzz);
+    tv[slot] = ok ? __ldg(grid_v + goff + (nx * kp.gy + ny) * kp.gz + nz) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tg[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncwarp();
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane < cg.L - (j >= cg.q ? 1 : 0);
-    int p = cg.start + round_off(j, cg.L, cg.q) + lane;
-    Stencil st;
-    XVC g;
-    V3 gx = vzero(), gnv = vzero(), d0 = vzero(), d1 = vzero(), d2 = vzero();
-    int tx = 0, ty = 0, tz = 0;
-    if (act) {
-      float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
-      V3 x = v3(a.x, a.y, a.z);
-      float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
-      g = load_xvc(gin, kp.EN, p);
-      gx = g.x; gnv = g.v;
-      V3 nx = x + v3(n0.w, n1.x, n1.y) * kp.dt;
-      if (nx.x > hi.x || nx.x < lo) gx.x = 0;
-      if (nx.y > hi.y || nx.y < lo) gx.y = 0;
-      if (nx.z > hi.z || nx.z < lo) gx.z = 0;
-      gnv += gx * kp.dt;
-      st = make_stencil_safe(x, kp);
-      stencil_dw(st, kp.inv_dx, d0, d1, d2);
-      tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
-    }
+    int p = act ? cg.start + round_off(j, cg.L, cg.q) + lane : cg.start;
+    float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
+    V3 x = v3(a.x, a.y, a.z);
+    float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
+    XVC g = load_xvc(gin, kp.EN, p);
+    V3 gx = g.x, gnv = g.v;
+    V3 nx = x + v3(n0.w, n1.x, n1.y) * kp.dt;
+    if (nx.x > hi.x || nx.x < lo) gx.x = 0;
+    if (nx.y > hi.y || nx.y < lo) gx.y = 0;
+    if (nx.z > hi.z || nx.z < lo) gx.z = 0;
+    gnv += gx * kp.dt;
+    Stencil st = make_stencil_safe(x, kp);
+    V3 d0, d1, d2;
+    stencil_dw(st, kp.inv_dx, d0, d1, d2);
+    float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
+    float ex[3] = {d0.x, d1.x, d2.x}, ey[3] = {d0.y, d1.y, d2.y}, ez[3] = {d0.z, d1.z, d2.z};
+    V3 H0 = v3(g.C.a00, g.C.a10, g.C.a20) * s4, H1 = v3(g.C.a01, g.C.a11, g.C.a21) * s4, H2 = v3(g.C.a02, g.C.a12, g.C.a22) * s4;
+    V3 h0 = gnv - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
+    int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
     int rank = __popc(peers & ((1u << lane) - 1u));
     int maxr = __reduce_max_sync(0xffffffffu, rank);
+    if (!in_tile) { tx = ty = tz = 0; }
+    V3 Vw = vzero(), gxs = vzero();
     for (int r = 0; r <= maxr; ++r) {
       bool mine = in_tile && rank == r;
-#pragma unroll 1
+      V3 Vw_r = vzero(), gx_r = vzero();
+#pragma unroll
       for (int i = 0; i < 3; ++i) {
-#pragma unroll 1
+        V3 hi_ = h0 + H0 * (float)i;
+#pragma unroll
         for (int jj = 0; jj < 3; ++jj) {
-          int row = (tx + i) << 6 | (ty + jj) << 3 | tz;
+          V3 hij = hi_ + H1 * (float)jj;
+          float wij = wx[i] * wy[jj], a1 = ex[i] * wy[jj], a2 = wx[i] * ey[jj];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            if (mine) {
-              float wx = pick(st.w0, st.w1, st.w2, i, 0), wy = pick(st.w0, st.w1, st.w2, jj, 1), wz = pick(st.w0, st.w1, st.w2, k, 2);
-              float w = wx * wy * wz;
-              V3 dpos = v3((float)i, (float)jj, (float)k) - st.fx;
-              float4 t = tv[row + k];
-              V3 v = v3(t.x, t.y, t.z);
-              float xx = w * s4;
-              V3 cd = mul(g.C, dpos);
-              V3 ggv = w * gnv + cd * xx;
-              float4 o = tg[row + k];
-              o.x += ggv.x; o.y += ggv.y; o.z += ggv.z;
-              tg[row + k] = o;
-              gx += (-kp.inv_dx * xx) * mul_t(g.C, v);
-              float gw = dot(gnv, v) + s4 * dot(v, cd);
-              gx += v3(pick(d0, d1, d2, i, 0) * wy * wz, wx * pick(d0, d1, d2, jj, 1) * wz, wx * wy * pick(d0, d1, d2, k, 2)) * gw;
-            }
-            __syncwarp();
+            V3 h = hij + H2 * (float)k;
+            float w = wij * wz[k];
+            int slot = tile_slot(tx + i, ty + jj, tz + k);
+            float4 t = lds_v4(vbase + 16u * (unsigned)slot);
+            unsigned ga = gbase + 16u * (unsigned)slot;
+            float4 o = lds_v4(ga);
+            o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
+            sts_v4_if(ga, o, mine);
+            Vw_r.x = fmaf(w, t.x, Vw_r.x); Vw_r.y = fmaf(w, t.y, Vw_r.y); Vw_r.z = fmaf(w, t.z, Vw_r.z);
+            float qn = t.x * h.x + t.y * h.y + t.z * h.z;
+            float tt = wz[k] * qn, uu = ez[k] * qn;
+            gx_r.x = fmaf(a1, tt, gx_r.x); gx_r.y = fmaf(a2, tt, gx_r.y); gx_r.z = fmaf(wij, uu, gx_r.z);
           }
         }
       }
+      if (mine) { Vw = Vw_r; gxs = gx_r; }
     }
     if (act && !in_tile) {
+      tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
       check_drift(tx, ty, tz, overflow);
 #pragma unroll 1
       for (int i = 0; i < 3; ++i)
@@ -764,27 +804,25 @@ __global__ void __launch_bounds__(32 * kTileWarps, 3) k_g2p_grad_tile(KP kp, int
         for (int jj = 0; jj < 3; ++jj)
 #pragma unroll 1
           for (int k = 0; k < 3; ++k) {
-            float wx = pick(st.w0, st.w1, st.w2, i, 0), wy = pick(st.w0, st.w1, st.w2, jj, 1), wz = pick(st.w0, st.w1, st.w2, k, 2);
-            float w = wx * wy * wz;
-            V3 dpos = v3((float)i, (float)jj, (float)k) - st.fx;
+            float wxi = pick(st.w0, st.w1, st.w2, i, 0), wyj = pick(st.w0, st.w1, st.w2, jj, 1), wzk = pick(st.w0, st.w1, st.w2, k, 2);
+            float w = wxi * wyj * wzk;
+            V3 h = h0 + H0 * (float)i + H1 * (float)jj + H2 * (float)k;
             size_t node = goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k;
             float4 t = __ldg(grid_v + node);
-            V3 v = v3(t.x, t.y, t.z);
-            float xx = w * s4;
-            V3 cd = mul(g.C, dpos);
-            V3 ggv = w * gnv + cd * xx;
-            red_add_v4(ggrid_v + node, ggv.x, ggv.y, ggv.z, 0.f);
-            gx += (-kp.inv_dx * xx) * mul_t(g.C, v);
-            float gw = dot(gnv, v) + s4 * dot(v, cd);
-            gx += v3(pick(d0, d1, d2, i, 0) * wy * wz, wx * pick(d0, d1, d2, jj, 1) * wz, wx * wy * pick(d0, d1, d2, k, 2)) * gw;
+            red_add_v4(ggrid_v + node, w * h.x, w * h.y, w * h.z, 0.f);
+            Vw += v3(t.x, t.y, t.z) * w;
+            float qn = t.x * h.x + t.y * h.y + t.z * h.z;
+            gxs += v3(pick(d0, d1, d2, i, 0) * wyj * wzk, wxi * pick(d0, d1, d2, jj, 1) * wzk, wxi * wyj * pick(d0, d1, d2, k, 2)) * qn;
           }
     }
+    gx += gxs - (kp.inv_dx * s4) * mul_t(g.C, Vw);
     if (act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
   }
   __syncwarp();
   for (int n = lane; n < kTileN; n += 32) {
-    float4 t = tg[n];
-    int nx = cg.ox + (n >> 6), ny = cg.oy + ((n >> 3) & 7), nz = cg.oz + (n & 7);
+    int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
+    float4 t = tg[tile_slot(txx, tyy, tzz)];
+    int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
     if ((t.x != 0.f || t.y != 0.f || t.z != 0.f) && (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
       red_add_v4(ggrid_v + goff + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, 0.f);
   }
@@ -849,7 +887,10 @@ __global__ void k_pack(int EN, const int *__restrict__ perm, const float *__rest
   if (x && v && C) {
     store_xvc(slot, EN, i, ld_v3(x, s), ld_v3(v, s), ld_m3(C, s));
   }
-  if (F) store_F(slot, EN, i, ld_m3(F, s));
+  if (F) {
+    store_F(slot, EN, i, ld_m3(F, s));
+    store_q(slot, EN, i, make_float4(0.f, 0.f, 0.f, 1.f));  // cold start for the first SVD from this state
+  }
 }
 __global__ void k_unpack(int EN, const int *__restrict__ perm, const float *__restrict__ slot, float *x, float *v, float *F, float *C) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1061,18 +1102,24 @@ struct dd_sim {
 
 namespace {
 
+using Mark = std::function<void(const char *)>;
+inline void mark(const Mark *m, const char *name) { if (m) (*m)(name); }
 int fwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? 4 : 3; }
 int bwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? (s->grid_ckpt ? 4 : 7) : 5; }
 
 template <int SVD>
-void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st) {
+void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk = nullptr) {
   const KP &kp = s->kp;
   if (s->cfg.tile_mode) {
     int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
     k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), nullptr);
+    mark(mk, "zero_bricks");
     k_p2g_tile<SVD, true><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->counters + 3);
+    mark(mk, "p2g_tile (svd+return map+scatter)");
     k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f));
+    mark(mk, "grid_b (grid update + contact)");
     k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->GV(f));
+    mark(mk, "g2p");
   } else {
     cudaMemsetAsync(s->grid, 0, sizeof(float4) * (size_t)kp.E * kp.G, st);
     k_p2g<SVD, true><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
@@ -1082,7 +1129,7 @@ void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st) {
   s->launches += fwd_launches(s);
 }
 template <int SVD>
-void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st) {
+void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk = nullptr) {
   const KP &kp = s->kp;
   float *gin = s->grad[(f + 1) & 1], *gout = s->grad[f & 1];
   size_t eg = (size_t)kp.E * kp.G, ep = (size_t)kp.E * kp.nb;
@@ -1091,14 +1138,18 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st) {
     int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
     if (s->grid_ckpt) {
       k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->ggrid_v, nullptr);
+      mark(mk, "zero_bricks (adjoint)");
     } else {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
       k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->ggrid_v);
       k_p2g_tile<SVD, false><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->counters + 3);
       k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f));
     }
     k_g2p_grad_tile<<<ncb, 32 * kTileWarps, 2 * kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->counters + 3);
+    mark(mk, "g2p_grad_tile");
     k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr);
-    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->mat0, s->yield, s->ggrid, gin, gout);
+    mark(mk, "grid_grad_b");
+    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
+    mark(mk, "p2g_grad (+svd adjoint)");
   } else {
     cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st);
     cudaMemsetAsync(s->ggrid_v, 0, sizeof(float4) * eg, st);
@@ -1106,7 +1157,7 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st) {
     k_grid<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
     k_g2p_grad<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v, gin, gout, s->ggrid_v);
     k_grid_grad<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr);
-    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->mat0, s->yield, s->ggrid, gin, gout);
+    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
   }
   s->launches += bwd_launches(s);
 }
@@ -1519,6 +1570,39 @@ int dd_sim_compute_dist_grad(dd_sim *s, int f, const float *dist_grad, cudaStrea
   k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->tables(f), nullptr, s->stage, s->grad[f & 1], s->gpos + (size_t)f * ep,
                                         s->grot + (size_t)f * ep, 1);
   DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Per-kernel device times of one forward + one backward substep (tile mode), CUDA events on `st`, averaged over reps.
+// names_out receives '\n'-separated kernel labels; returns the number of kernels in *n_out.
+int dd_sim_profile_substep(dd_sim *s, int f, int reps, float *ms_out, char *names_out, int names_cap, int *n_out, cudaStream_t st) {
+  if (check_range(s, f, 1, "dd_sim_profile_substep")) return 1;
+  if (!s->cfg.tile_mode || !s->grid_ckpt) return fail("dd_sim_profile_substep: needs tile_mode with grid checkpoints");
+  if (s->grad_holds[(f + 1) & 1] != f + 1) return fail("dd_sim_profile_substep: seed a gradient for state f+1 first");
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+  std::vector<double> acc;
+  for (int r = 0; r < reps; ++r) {
+    size_t k = 0;
+    auto new_event = [&]() {
+      if (k >= ev.size()) { cudaEvent_t e_; cudaEventCreate(&e_); ev.push_back(e_); }
+      cudaEventRecord(ev[k++], st);
+    };
+    new_event();
+    Mark mk = [&](const char *name) { if (r == 0) names.push_back(name); new_event(); };
+    if (s->cfg.svd_mode == 0) { enqueue_forward_substep<0>(s, f, st, &mk); enqueue_backward_substep<0>(s, f, st, &mk); }
+    else { enqueue_forward_substep<1>(s, f, st, &mk); enqueue_backward_substep<1>(s, f, st, &mk); }
+    DD_CUDA(cudaStreamSynchronize(st));
+    if (r == 0) acc.assign(names.size(), 0.0);
+    for (size_t i = 0; i + 1 < k; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms; }
+  }
+  for (auto e_ : ev) cudaEventDestroy(e_);
+  std::string joined;
+  for (size_t i = 0; i < names.size(); ++i) { ms_out[i] = (float)(acc[i] / reps); joined += names[i]; joined += '\n'; }
+  if ((int)joined.size() + 1 > names_cap) return fail("dd_sim_profile_substep: names buffer too small");
+  std::memcpy(names_out, joined.c_str(), joined.size() + 1);
+  *n_out = (int)names.size();
+  s->grad_holds[f & 1] = f;
   return 0;
 }
 

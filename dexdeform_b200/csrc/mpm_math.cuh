@@ -435,6 +435,89 @@ DD_HD void svd3_f32(const M3 &A, M3 &U, V3 &sig, M3 &Vo) {
   sig.x = b11; sig.y = r22; sig.z = r33;
 }
 
+// (3) svd3_warm: (2) with a warm start.  `q` (x,y,z,w) is the quaternion of V from the previous substep of the same
+//     particle (identity on a cold start); the Jacobi sweeps run on V0^T A^T A V0 and stop as soon as the off-diagonal
+//     mass is at rounding level, so a particle whose F changed little converges in 0-1 sweeps instead of 5.  On return
+//     q holds the converged quaternion.  Calling it again with that q and the same A reproduces U, sig, V bit for bit
+//     with zero sweeps -- which is how the adjoint kernel re-creates the forward factors without re-iterating.
+DD_HD int svd3_warm(const M3 &A, float &qx, float &qy, float &qz, float &qw, M3 &U, V3 &sig, M3 &Vo, int max_sweeps = 6) {
+  float v11, v12, v13, v21, v22, v23, v31, v32, v33;
+  float b11, b12, b13, b21, b22, b23, b31, b32, b33;
+  int sweeps = 0;
+  {
+    float qxx = qx * qx, qyy = qy * qy, qzz = qz * qz, qxz = qx * qz, qxy = qx * qy, qyz = qy * qz, qwx = qw * qx, qwy = qw * qy, qwz = qw * qz;
+    v11 = 1.f - 2.f * (qyy + qzz); v12 = 2.f * (qxy - qwz); v13 = 2.f * (qxz + qwy);
+    v21 = 2.f * (qxy + qwz); v22 = 1.f - 2.f * (qxx + qzz); v23 = 2.f * (qyz - qwx);
+    v31 = 2.f * (qxz - qwy); v32 = 2.f * (qyz + qwx); v33 = 1.f - 2.f * (qxx + qyy);
+  }
+  b11 = A.a00 * v11 + A.a01 * v21 + A.a02 * v31; b12 = A.a00 * v12 + A.a01 * v22 + A.a02 * v32; b13 = A.a00 * v13 + A.a01 * v23 + A.a02 * v33;
+  b21 = A.a10 * v11 + A.a11 * v21 + A.a12 * v31; b22 = A.a10 * v12 + A.a11 * v22 + A.a12 * v32; b23 = A.a10 * v13 + A.a11 * v23 + A.a12 * v33;
+  b31 = A.a20 * v11 + A.a21 * v21 + A.a22 * v31; b32 = A.a20 * v12 + A.a21 * v22 + A.a22 * v32; b33 = A.a20 * v13 + A.a21 * v23 + A.a22 * v33;
+  float s11 = b11 * b11 + b21 * b21 + b31 * b31, s21 = b12 * b11 + b22 * b21 + b32 * b31, s22 = b12 * b12 + b22 * b22 + b32 * b32;
+  float s31 = b13 * b11 + b23 * b21 + b33 * b31, s32 = b13 * b12 + b23 * b22 + b33 * b32, s33 = b13 * b13 + b23 * b23 + b33 * b33;
+  const float tol2 = 1.0e-13f;  // (3.2e-7)^2: off-diagonal mass relative to the trace, at fp32 rounding level
+  bool rotated = false;
+#pragma unroll 1
+  for (; sweeps < max_sweeps; ++sweeps) {
+    float off = s21 * s21 + s31 * s31 + s32 * s32, tr = s11 + s22 + s33;
+    if (off <= tol2 * tr * tr) break;
+    jacobi32(s11, s21, s22, s31, s32, s33, qx, qy, qz, qw);
+    jacobi32(s11, s21, s22, s31, s32, s33, qy, qz, qx, qw);
+    jacobi32(s11, s21, s22, s31, s32, s33, qz, qx, qy, qw);
+    rotated = true;
+  }
+  if (rotated) {
+    float n = DD_RSQRT(qx * qx + qy * qy + qz * qz + qw * qw);
+    qx *= n; qy *= n; qz *= n; qw *= n;
+    float qxx = qx * qx, qyy = qy * qy, qzz = qz * qz, qxz = qx * qz, qxy = qx * qy, qyz = qy * qz, qwx = qw * qx, qwy = qw * qy, qwz = qw * qz;
+    v11 = 1.f - 2.f * (qyy + qzz); v12 = 2.f * (qxy - qwz); v13 = 2.f * (qxz + qwy);
+    v21 = 2.f * (qxy + qwz); v22 = 1.f - 2.f * (qxx + qzz); v23 = 2.f * (qyz - qwx);
+    v31 = 2.f * (qxz - qwy); v32 = 2.f * (qyz + qwx); v33 = 1.f - 2.f * (qxx + qyy);
+    b11 = A.a00 * v11 + A.a01 * v21 + A.a02 * v31; b12 = A.a00 * v12 + A.a01 * v22 + A.a02 * v32; b13 = A.a00 * v13 + A.a01 * v23 + A.a02 * v33;
+    b21 = A.a10 * v11 + A.a11 * v21 + A.a12 * v31; b22 = A.a10 * v12 + A.a11 * v22 + A.a12 * v32; b23 = A.a10 * v13 + A.a11 * v23 + A.a12 * v33;
+    b31 = A.a20 * v11 + A.a21 * v21 + A.a22 * v31; b32 = A.a20 * v12 + A.a21 * v22 + A.a22 * v32; b33 = A.a20 * v13 + A.a21 * v23 + A.a22 * v33;
+  }
+  {
+    float r1 = b11 * b11 + b21 * b21 + b31 * b31, r2 = b12 * b12 + b22 * b22 + b32 * b32, r3 = b13 * b13 + b23 * b23 + b33 * b33;
+    bool c = r1 < r2;
+    cnswap32(c, b11, b12); cnswap32(c, v11, v12); cnswap32(c, b21, b22); cnswap32(c, v21, v22); cnswap32(c, b31, b32); cnswap32(c, v31, v32);
+    cswap32(c, r1, r2);
+    c = r1 < r3;
+    cnswap32(c, b11, b13); cnswap32(c, v11, v13); cnswap32(c, b21, b23); cnswap32(c, v21, v23); cnswap32(c, b31, b33); cnswap32(c, v31, v33);
+    cswap32(c, r1, r3);
+    c = r2 < r3;
+    cnswap32(c, b12, b13); cnswap32(c, v12, v13); cnswap32(c, b22, b23); cnswap32(c, v22, v23); cnswap32(c, b32, b33); cnswap32(c, v32, v33);
+  }
+  float ch1, sh1, ch2, sh2, ch3, sh3, ca, cb;
+  qr_givens32(b11, b21, ch1, sh1);
+  ca = 1.f - 2.f * sh1 * sh1; cb = 2.f * ch1 * sh1;
+  float r11 = ca * b11 + cb * b21, r12 = ca * b12 + cb * b22, r13 = ca * b13 + cb * b23;
+  float r22 = -cb * b12 + ca * b22, r23 = -cb * b13 + ca * b23;
+  float r31 = b31, r32 = b32, r33 = b33;
+  qr_givens32(r11, r31, ch2, sh2);
+  ca = 1.f - 2.f * sh2 * sh2; cb = 2.f * ch2 * sh2;
+  b11 = ca * r11 + cb * r31;
+  b22 = r22; b23 = r23;
+  b32 = -cb * r12 + ca * r32; b33 = -cb * r13 + ca * r33;
+  qr_givens32(b22, b32, ch3, sh3);
+  ca = 1.f - 2.f * sh3 * sh3; cb = 2.f * ch3 * sh3;
+  r22 = ca * b22 + cb * b32;
+  r33 = -cb * b23 + ca * b33;
+  float sh12 = sh1 * sh1, sh22 = sh2 * sh2, sh32 = sh3 * sh3;
+  U.a00 = (-1.f + 2.f * sh12) * (-1.f + 2.f * sh22);
+  U.a01 = 4.f * ch2 * ch3 * (-1.f + 2.f * sh12) * sh2 * sh3 + 2.f * ch1 * sh1 * (-1.f + 2.f * sh32);
+  U.a02 = 4.f * ch1 * ch3 * sh1 * sh3 - 2.f * ch2 * (-1.f + 2.f * sh12) * sh2 * (-1.f + 2.f * sh32);
+  U.a10 = 2.f * ch1 * sh1 * (1.f - 2.f * sh22);
+  U.a11 = -8.f * ch1 * ch2 * ch3 * sh1 * sh2 * sh3 + (-1.f + 2.f * sh12) * (-1.f + 2.f * sh32);
+  U.a12 = -2.f * ch3 * sh3 + 4.f * sh1 * (ch3 * sh1 * sh3 + ch1 * ch2 * sh2 * (-1.f + 2.f * sh32));
+  U.a20 = 2.f * ch2 * sh2;
+  U.a21 = 2.f * ch3 * (1.f - 2.f * sh22) * sh3;
+  U.a22 = (-1.f + 2.f * sh22) * (-1.f + 2.f * sh32);
+  Vo.a00 = v11; Vo.a01 = v12; Vo.a02 = v13; Vo.a10 = v21; Vo.a11 = v22; Vo.a12 = v23; Vo.a20 = v31; Vo.a21 = v32; Vo.a22 = v33;
+  sig.x = b11; sig.y = r22; sig.z = r33;
+  return sweeps;
+}
+
 // ---------------------------------------------------------------------------------------------- constitutive model
 // von-Mises return mapping in log-strain space (integrator.cu:42-67).  Returns J and writes F_new; `plastic`
 // and `ee` (= exp of the projected log strains) are kept for the adjoint.

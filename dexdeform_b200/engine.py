@@ -150,3 +150,12 @@ class FusedSim:
     def compute_dist_grad(self, f, dist_grad):
         self._check(self.lib.dd_sim_compute_dist_grad(self._h, f, _ptr(np.ascontiguousarray(dist_grad, np.float32)), self.stream))
         self.sync()
+
+    def profile_substep(self, f, reps=5):
+        """[(kernel label, ms)] for one forward + backward substep (needs a gradient seeded for state f+1)."""
+        ms = (ctypes.c_float * 32)()
+        names = ctypes.create_string_buffer(2048)
+        n = ctypes.c_int(0)
+        self._check(self.lib.dd_sim_profile_substep(self._h, f, reps, ms, names, 2048, ctypes.byref(n), self.stream))
+        labels = names.value.decode().strip().split("\n")
+        return [(labels[i], float(ms[i])) for i in range(n.value)]

@@ -32,6 +32,7 @@ ABI2 = {
     "dd_sim_compute_dist": (c_int, [P, c_int, P, S]),
     "dd_sim_compute_dist_grad": (c_int, [P, c_int, P, S]),
     "dd_sim_sync": (c_int, [P, S]),
+    "dd_sim_profile_substep": (c_int, [P, c_int, c_int, P, P, c_int, P, S]),
 }
 
 

@@ -159,6 +159,8 @@ int dd_sim_add_pose_grads(dd_sim *sim, int f, const float *gpos, const float *gr
 int dd_sim_compute_dist(dd_sim *sim, int f, float *dist, cudaStream_t stream);   /* (E, N, nb) */
 int dd_sim_compute_dist_grad(dd_sim *sim, int f, const float *dist_grad, cudaStream_t stream);
 int dd_sim_sync(dd_sim *sim, cudaStream_t stream);
+/* measurement aid: device time of every kernel of one forward + backward substep (CUDA events on `stream`) */
+int dd_sim_profile_substep(dd_sim *sim, int f, int reps, float *ms_out, char *names_out, int names_cap, int *n_out, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

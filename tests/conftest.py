@@ -58,3 +58,18 @@ def ref_gpu():
 def product_lib():
     from dexdeform_b200.types import load_library
     return load_library()
+
+
+def assert_close_rows(a, b, tol, name="", frac=2e-3, l2_factor=20.0):
+    """Robust field comparison for quantities that sit behind hard branches (yield surface, contact band, friction cone,
+    position clamp): the reference itself flips such branches from run to run (float-atomic summation order), which
+    changes the affected particles' values discretely.  Required: all but a fraction `frac` of the rows agree to `tol`
+    (L-inf, relative to the field's largest magnitude) and the whole field agrees in relative L2 to `l2_factor * tol`."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    a, b = a.reshape(len(a), -1), b.reshape(len(b), -1)
+    scale = np.abs(b).max() + 1e-30
+    row = np.abs(a - b).max(axis=1) / scale
+    bad = int((row > tol).sum())
+    assert bad <= max(1, int(frac * len(row))), f"{name}: {bad}/{len(row)} rows differ by more than {tol} (worst {row.max():.3e})"
+    l2 = np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+    assert l2 < l2_factor * tol, f"{name}: relative L2 error {l2:.3e}"
