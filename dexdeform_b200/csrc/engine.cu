@@ -1045,6 +1045,39 @@ __global__ void __launch_bounds__(kT) k_dist(KP kp, const int *__restrict__ perm
   }
 }
 
+// particle2mass (integrator.cu:239-310) on the engine layout: density-grid observation of object `id` (-1 = all) and its
+// adjoint into the gradient slot.  `ids` is in ORIGINAL particle order (may be null when id == -1).
+__global__ void __launch_bounds__(kT) k_grid_mass(KP kp, const int *__restrict__ perm, const float *__restrict__ slot, const float4 *__restrict__ mat0,
+                                                  const int *__restrict__ ids, int id, float *grid_m, const float *__restrict__ grid_m_grad,
+                                                  float *gslot, int need_grad) {
+  int p = blockIdx.x * kT + threadIdx.x;
+  if (p >= kp.EN) return;
+  if (id != -1 && ids[perm[p]] != id) return;
+  float4 a = plane4(slot, kp.EN, 0)[p];
+  Stencil st = make_stencil_safe(v3(a.x, a.y, a.z), kp);
+  V3 d0, d1, d2;
+  stencil_dw(st, kp.inv_dx, d0, d1, d2);
+  float m = mat0[p].x;
+  size_t goff = (size_t)(p / kp.N) * kp.G;
+  V3 g = vzero();
+#pragma unroll 1
+  for (int i = 0; i < 3; ++i)
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float wx = pick(st.w0, st.w1, st.w2, i, 0), wy = pick(st.w0, st.w1, st.w2, j, 1), wz = pick(st.w0, st.w1, st.w2, k, 2);
+        size_t node = goff + ((st.bx + i) * kp.gy + st.by + j) * kp.gz + st.bz + k;
+        if (need_grad) g += v3(pick(d0, d1, d2, i, 0) * wy * wz, wx * pick(d0, d1, d2, j, 1) * wz, wx * wy * pick(d0, d1, d2, k, 2)) * (grid_m_grad[node] * m);
+        else atomicAdd(&grid_m[node], m * (wx * wy * wz));
+      }
+  if (need_grad) {
+    float4 *o = plane4(gslot, kp.EN, 0) + p;
+    float4 t = *o;
+    *o = make_float4(t.x + g.x, t.y + g.y, t.z + g.z, t.w);
+  }
+}
+
 inline int nblk(long long n) { return (int)((n + kT - 1) / kT); }
 
 }  // namespace
@@ -1603,6 +1636,39 @@ int dd_sim_profile_substep(dd_sim *s, int f, int reps, float *ms_out, char *name
   std::memcpy(names_out, joined.c_str(), joined.size() + 1);
   *n_out = (int)names.size();
   s->grad_holds[f & 1] = f;
+  return 0;
+}
+
+// density-grid observation (mpm/simulator.py:323-354).  ids: (E*N) object ids in original order or NULL; out: (E, gx, gy, gz)
+int dd_sim_compute_grid_mass(dd_sim *s, int f, const int *ids, int id, float *out, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_compute_grid_mass")) return 1;
+  if (!out) return fail("dd_sim_compute_grid_mass: null output");
+  if (id != -1 && !ids) return fail("dd_sim_compute_grid_mass: object ids required when id != -1");
+  size_t eg = (size_t)s->kp.E * s->kp.G;
+  float *buf = reinterpret_cast<float *>(s->ggrid);  // scratch: E*G floats fit in the float4 adjoint grid
+  int *dids = reinterpret_cast<int *>(s->keys);
+  if (ids) DD_CUDA(cudaMemcpyAsync(dids, ids, sizeof(int) * s->kp.EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemsetAsync(buf, 0, sizeof(float) * eg, st));
+  k_grid_mass<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->mat0, ids ? dids : nullptr, id, buf, nullptr, nullptr, 0);
+  DD_CUDA(cudaGetLastError());
+  DD_CUDA(cudaMemcpyAsync(out, buf, sizeof(float) * eg, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemsetAsync(buf, 0, sizeof(float) * eg, st));  // ggrid must stay zero outside the active bricks
+  DD_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+int dd_sim_compute_grid_mass_grad(dd_sim *s, int f, const int *ids, int id, const float *grid_m_grad, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_compute_grid_mass_grad")) return 1;
+  if (!grid_m_grad) return fail("dd_sim_compute_grid_mass_grad: null argument");
+  if (id != -1 && !ids) return fail("dd_sim_compute_grid_mass_grad: object ids required when id != -1");
+  if (s->grad_holds[f & 1] != f) return fail("dd_sim_compute_grid_mass_grad: gradient slot does not hold state " + std::to_string(f));
+  size_t eg = (size_t)s->kp.E * s->kp.G;
+  float *buf = reinterpret_cast<float *>(s->ggrid);
+  int *dids = reinterpret_cast<int *>(s->keys);
+  if (ids) DD_CUDA(cudaMemcpyAsync(dids, ids, sizeof(int) * s->kp.EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaMemcpyAsync(buf, grid_m_grad, sizeof(float) * eg, cudaMemcpyDefault, st));
+  k_grid_mass<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->mat0, ids ? dids : nullptr, id, nullptr, buf, s->grad[f & 1], 1);
+  DD_CUDA(cudaGetLastError());
+  DD_CUDA(cudaMemsetAsync(buf, 0, sizeof(float) * eg, st));
   return 0;
 }
 

@@ -159,3 +159,15 @@ class FusedSim:
         self._check(self.lib.dd_sim_profile_substep(self._h, f, reps, ms, names, 2048, ctypes.byref(n), self.stream))
         labels = names.value.decode().strip().split("\n")
         return [(labels[i], float(ms[i])) for i in range(n.value)]
+
+    def compute_grid_mass(self, f, ids=None, id=-1):
+        out = np.empty((self.E,) + self.grid_dim, np.float32)
+        ids_p = None if ids is None else np.ascontiguousarray(ids, np.int32).ctypes.data
+        self._check(self.lib.dd_sim_compute_grid_mass(self._h, f, ids_p, int(id), _ptr(out), self.stream))
+        return out
+
+    def compute_grid_mass_grad(self, f, grid_m_grad, ids=None, id=-1):
+        g = np.ascontiguousarray(grid_m_grad, np.float32)
+        ids_a = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        self._check(self.lib.dd_sim_compute_grid_mass_grad(self._h, f, None if ids_a is None else ids_a.ctypes.data, int(id), _ptr(g), self.stream))
+        self.sync()

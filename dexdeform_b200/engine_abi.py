@@ -31,6 +31,8 @@ ABI2 = {
     "dd_sim_add_pose_grads": (c_int, [P, c_int, P, P, S]),
     "dd_sim_compute_dist": (c_int, [P, c_int, P, S]),
     "dd_sim_compute_dist_grad": (c_int, [P, c_int, P, S]),
+    "dd_sim_compute_grid_mass": (c_int, [P, c_int, P, c_int, P, S]),
+    "dd_sim_compute_grid_mass_grad": (c_int, [P, c_int, P, c_int, P, S]),
     "dd_sim_sync": (c_int, [P, S]),
     "dd_sim_profile_substep": (c_int, [P, c_int, c_int, P, P, c_int, P, S]),
 }

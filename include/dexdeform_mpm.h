@@ -158,6 +158,9 @@ int dd_sim_get_pose_grads(dd_sim *sim, int f0, int count, float *gpos, float *gr
 int dd_sim_add_pose_grads(dd_sim *sim, int f, const float *gpos, const float *grot, cudaStream_t stream);
 int dd_sim_compute_dist(dd_sim *sim, int f, float *dist, cudaStream_t stream);   /* (E, N, nb) */
 int dd_sim_compute_dist_grad(dd_sim *sim, int f, const float *dist_grad, cudaStream_t stream);
+/* density-grid observation of object `id` (-1: all particles) and its adjoint; ids (E*N ints, original order) may be NULL for id == -1 */
+int dd_sim_compute_grid_mass(dd_sim *sim, int f, const int *ids, int id, float *out, cudaStream_t stream);
+int dd_sim_compute_grid_mass_grad(dd_sim *sim, int f, const int *ids, int id, const float *grid_m_grad, cudaStream_t stream);
 int dd_sim_sync(dd_sim *sim, cudaStream_t stream);
 /* measurement aid: device time of every kernel of one forward + backward substep (CUDA events on `stream`) */
 int dd_sim_profile_substep(dd_sim *sim, int f, int reps, float *ms_out, char *names_out, int names_cap, int *n_out, cudaStream_t stream);
