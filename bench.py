@@ -139,6 +139,7 @@ def run_ours(args):
         sim.backward(0, S)
         if world > 1:  # NCCL over NVLink: loss and pose (action) gradients only; environments never exchange state
             import torch.distributed as dist
+            sim._check(sim.lib.dd_sim_get_pose_grads_device(sim._h, 0, S + 1, packed.data_ptr() + 4, sim.stream)) if hasattr(sim.lib, "dd_sim_get_pose_grads_device") else None
             dist.all_reduce(packed)
 
     for _ in range(args.warmup):
@@ -239,7 +240,7 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------------- CPU baseline
-def cpu_baseline(workload, budget_substeps=2):
+def cpu_baseline(workload, budget_substeps=24):
     """The reference's own kernels compiled for the host (oracle/_ref, kind "reference") -- else the C oracle (kind "port") --
     on a bounded sample of the same workload: the full scene, `budget_substeps` substeps forward + backward."""
     from abi1_driver import Abi1Sim
