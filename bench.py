@@ -139,7 +139,8 @@ def run_ours(args):
         sim.backward(0, S)
         if world > 1:  # NCCL over NVLink: loss and pose (action) gradients only; environments never exchange state
             import torch.distributed as dist
-            sim._check(sim.lib.dd_sim_get_pose_grads_device(sim._h, 0, S + 1, packed.data_ptr() + 4, sim.stream)) if hasattr(sim.lib, "dd_sim_get_pose_grads_device") else None
+            base = packed.data_ptr() + 4  # [0] is the loss; pose gradients are written device-to-device behind it
+            sim._check(sim.lib.dd_sim_get_pose_grads(sim._h, 0, S + 1, base, base + 4 * 3 * (S + 1) * nb, sim.stream))
             dist.all_reduce(packed)
 
     for _ in range(args.warmup):
