@@ -30,7 +30,7 @@ METRIC = "particle-substeps/sec fwd+bwd"
 UNIT = "particle-substeps/s"
 ALG_BYTES_FWD, ALG_BYTES_BWD = 212, 308  # SURVEY.md 8(d), per particle-substep
 # algorithmic bytes per particle of each kernel (DESIGN.md "kernels"): grid kernels work on the L2-resident grid
-KERNEL_ALG_BYTES = {"p2g_tile": 152, "g2p": 60, "g2p_grad_tile": 60, "p2g_grad": 248}
+KERNEL_ALG_BYTES = {"p2g_tile": 152, "g2p_tile": 60, "g2p_grad_tile": 60, "p2g_grad_tile": 248, "g2p": 60, "p2g_grad": 248}
 
 
 def workload_scene(name, seed=0):

@@ -8,6 +8,7 @@
 //     from a contact bit-mask (contacts are velocity independent) by replaying the few contacting bodies
 //   * p2g_grad + compute_svd_grad are one kernel; gradients of state t are written once (ping-pong grad slots)
 //   * S substeps (or their reverse) are captured into one CUDA graph; poses for all substeps are device resident
+#define DD_FLOAT_LENGTH 1
 #include "mpm_math.cuh"
 #include "../../include/dexdeform_mpm.h"
 #include <cub/device/device_radix_sort.cuh>
@@ -35,6 +36,22 @@ int fail(const std::string &msg) { g_last_error = msg; return 1; }
   } while (0)
 
 constexpr int kT = 256;
+// occupancy knobs (min resident blocks per SM) -- tuned with ncu, see profiles/
+#ifndef DD_LB_P2G_TILE
+#define DD_LB_P2G_TILE 5
+#endif
+#ifndef DD_LB_G2PG_TILE
+#define DD_LB_G2PG_TILE 4
+#endif
+#ifndef DD_LB_G2P_TILE
+#define DD_LB_G2P_TILE 5
+#endif
+#ifndef DD_LB_P2GG_TILE
+#define DD_LB_P2GG_TILE 4
+#endif
+#ifndef DD_LB_P2G_GRAD
+#define DD_LB_P2G_GRAD 2
+#endif
 constexpr int kPlaneFloats = 29;  // 16 (x,v,C + pad) + 9 (F) + 4 (SVD warm-start quaternion)
 
 struct KP {            // kernel parameters shared by all kernels
@@ -197,7 +214,7 @@ DD_DEV V3 contact_apply(V3 gx, V3 v, Q4 bq, V3 npos, Q4 nrot, Q4 tfsr, Q4 sargs,
   h.rel = v - h.bv;
   h.nc = dot(h.rel, h.nrm);
   h.vt_in = h.rel - fminf(h.nc, 0.f) * h.nrm;
-  h.has_fric = h.nc < 0.f && (double)dot(h.vt_in, h.vt_in) > 1e-30;
+  h.has_fric = h.nc < 0.f && dot(h.vt_in, h.vt_in) > 1e-30f;
   h.vtn = length30(h.vt_in);
   h.vt = h.vt_in;
   if (h.has_fric) h.vt = h.vt_in * (1.f / h.vtn) * fmaxf(0.f, h.vtn + h.nc * tfsr.x);
@@ -213,7 +230,7 @@ DD_DEV V3 apply_bc(V3 v, int gx_, int gy_, int gz_, const KP &kp) {  // integrat
         float lin = v.y;
         V3 vit = v3(v.x, 0.f, v.z);
         float lit = sqrtf(dot(vit, vit) + 1e-8f);
-        v = vit * fmaxf((float)(1. + (double)(kp.gf * lin / lit)), 0.f);
+        v = vit * fmaxf(1.f + kp.gf * lin / lit, 0.f);
       } else {
         v = vzero();
       }
@@ -251,9 +268,11 @@ __global__ void __launch_bounds__(kT) k_grid(KP kp, const float4 *__restrict__ g
 }
 
 // g2p (integrator.cu:1059-1109).  v' = sum w v_n ; C' = 4/dx * sum (w v_n) (x) (offset - fx)
-__global__ void __launch_bounds__(kT) k_g2p(KP kp, const float *__restrict__ cur, float *__restrict__ nxt, const float4 *__restrict__ grid_v) {
+__global__ void __launch_bounds__(kT) k_g2p(KP kp, const int *__restrict__ spos, const float *__restrict__ cur, float *__restrict__ nxt,
+                                            const float4 *__restrict__ grid_v) {
   int p = blockIdx.x * kT + threadIdx.x;
   if (p >= kp.EN) return;
+  if (spos) p = __ldg(spos + p);  // neighbouring threads take particles of the same / adjacent cells: the 27-node gathers hit L1
   float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
   V3 x = v3(a.x, a.y, a.z);
   Stencil st = make_stencil_safe(x, kp);
@@ -344,19 +363,28 @@ DD_DEV float warp_sum(float v) {
 }
 
 // grid_op_v2_grad (integrator.cu:779-1057) without the stored per-body velocities
-DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, int cy, int cz, const float4 *__restrict__ grid,
-                           const float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, const BodyTables &bt, float4 *gpos, float4 *grot,
-                           float4 *gnpos, float4 *gnrot) {
+// cand: bodies that can touch this node's brick at all (superset of the contact mask); zero_gv / zero_m: clear the node's
+// entry of ggrid_v / grid after it has been consumed, so the next substep finds zeros without a separate memset pass
+DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, int cy, int cz, float4 *__restrict__ grid,
+                           float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, const BodyTables &bt, float4 *gpos, float4 *grot,
+                           float4 *gnpos, float4 *gnrot, unsigned long long cand, bool zero_gv, bool zero_m) {
   float4 mm = inr ? grid[node] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gvn = inr ? ggrid_v[node] : make_float4(0.f, 0.f, 0.f, 0.f);  // both node loads in flight together (cold HBM in the adjoint sweep)
+  if (inr && zero_m) grid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
   bool live = inr && mm.w > 1e-12;
   // a whole warp of empty nodes leaves early (the common case)
   if (!__any_sync(0xffffffffu, live)) {
-    if (inr) ggrid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inr) {
+      ggrid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zero_gv) ggrid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     return;
   }
   int env = 0, gx_ = 0, gy_ = 0, gz_ = 0;
   V3 gv = vzero(), mv = vzero(), gx = vzero(), v0 = vzero();
   unsigned long long mask = 0ull;
+  constexpr int kStageStack = 6;
+  V3 stage_in[kStageStack];
   if (live) {
     env = env_; gx_ = cx; gy_ = cy; gz_ = cz;
     mv = v3(mm.x, mm.y, mm.z);
@@ -364,17 +392,21 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
     gx = v3((float)gx_, (float)gy_, (float)gz_) * kp.dx;
     // forward replay: contact mask + velocity after all bodies
     V3 v = v0;
-    for (int b = 0; b < kp.nb; ++b) {
-      int pb = env * kp.nb + b;
+    int nc = 0;
+    for (unsigned long long c = cand; c; c &= c - 1ull) {
+      int b = __ffsll((long long)c) - 1, pb = env * kp.nb + b;
       Hit h;
       Q4 bq = q4f(bt.rot[pb]), tfsr = q4f(bt.tfsr[b]), sargs = q4f(bt.args[b]);
       if (contact_geom(gx, v3f(bt.pos[pb]), bq, tfsr, sargs, bt.cull[b], h)) {
         mask |= 1ull << b;
+        if (nc < kStageStack) stage_in[nc] = v;  // input velocity of this contact stage, for the reverse sweep
+        ++nc;
         v = contact_apply(gx, v, bq, v3f(bt.npos[pb]), q4f(bt.nrot[pb]), tfsr, sargs, kp.dt, h);
       }
     }
     V3 vv = v;
-    float4 t = ggrid_v[node];
+    float4 t = gvn;
+    if (zero_gv) ggrid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
     gv = v3(t.x, t.y, t.z);
     // boundary-condition adjoint (integrator.cu:829-893)
     V3 vin = vv;
@@ -388,7 +420,7 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
       lin = vin.y;
       vit = v3(vin.x, 0.f, vin.z);
       lit = sqrtf(dot(vit, vit) + 1e-8f);
-      float flag = (float)(1. + (double)(kp.gf * lin / lit));
+      float flag = 1.f + kp.gf * lin / lit;
       vin = vit * fmaxf(flag, 0.f);
     }
     if (gz_ > kp.gz - bound && vin.z > 0) gv.z = 0;
@@ -396,7 +428,7 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
     if (gy_ > kp.gy - bound && vin.y > 0) gv.y = 0;
     if (hit_ground) {
       gv.y = 0;
-      float flag = (float)(1. + (double)(kp.gf * lin / lit));
+      float flag = 1.f + kp.gf * lin / lit;
       if (flag >= 0.f) {
         V3 g_vit = flag * gv;
         float g_lin = kp.gf / lit * dot(vit, gv);
@@ -422,9 +454,12 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
     g_bq.w = g_bq.x = g_bq.y = g_bq.z = 0.f;
     g_nq = g_bq;
     if (live && (mask >> b & 1ull)) {
-      // input velocity of stage b: replay the contacting bodies before it
+      // input velocity of stage b: kept from the forward replay for the first kStageStack contacts of this node, otherwise
+      // re-derived by replaying the contacting bodies before it
       V3 v = v0;
       unsigned long long lower = mask & ((1ull << b) - 1ull);
+      int ci = __popcll(lower);
+      if (ci < kStageStack) { v = stage_in[ci]; lower = 0ull; }
       while (lower) {
         int c = __ffsll((long long)lower) - 1;
         lower &= lower - 1ull;
@@ -449,7 +484,7 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
         if (bf > 0.f) {
           g_nc += dot(h.vt_in, g_vt) * friction / h.vtn;
           float g_vtn = -h.nc * g_nc / h.vtn;
-          g_vt = g_vt * (float)(1. / (double)h.vtn) * bf + g_vtn * h.vt_in / h.vtn;
+          g_vt = g_vt * (1.f / h.vtn) * bf + g_vtn * h.vt_in / h.vtn;
         } else {
           g_vt = vzero();
         }
@@ -479,6 +514,7 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
 #pragma unroll
     for (int i = 0; i < 14; ++i) r[i] = warp_sum(r[i]);
     int wenv = __shfl_sync(0xffffffffu, env_, 0);  // a warp never straddles two environments
+#ifndef DD_NO_POSE_ATOMICS
     if ((threadIdx.x & 31) == 0) {
       int pb = wenv * kp.nb + b;
       atomicAdd(&gnpos[pb].x, r[0]); atomicAdd(&gnpos[pb].y, r[1]); atomicAdd(&gnpos[pb].z, r[2]);
@@ -486,23 +522,28 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
       atomicAdd(&gpos[pb].x, r[7]); atomicAdd(&gpos[pb].y, r[8]); atomicAdd(&gpos[pb].z, r[9]);
       atomicAdd(&grot[pb].x, r[10]); atomicAdd(&grot[pb].y, r[11]); atomicAdd(&grot[pb].z, r[12]); atomicAdd(&grot[pb].w, r[13]);
     }
+#else
+    if (r[0] == 12345.f) gnpos[0].x = r[1] + r[2] + r[3] + r[4] + r[5] + r[6] + r[7] + r[8] + r[9] + r[10] + r[11] + r[12] + r[13] + (float)wenv;
+#endif
   }
   if (inr) {
     if (live) {
-      V3 o = gv * (float)(1. / (double)mm.w);
+      V3 o = gv * (1.f / mm.w);
       ggrid[node] = make_float4(o.x, o.y, o.z, (-1.f / mm.w / mm.w) * dot(mv, gv));
     } else {
       ggrid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zero_gv) ggrid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 }
-__global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restrict__ grid, const float4 *__restrict__ ggrid_v,
+__global__ void __launch_bounds__(kT) k_grid_grad(KP kp, float4 *__restrict__ grid, float4 *__restrict__ ggrid_v,
                                                   float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos, float4 *grot, float4 *gnpos,
                                                   float4 *gnrot) {
   int node = blockIdx.x * kT + threadIdx.x;
   bool inr = node < kp.E * kp.G;
   int env = inr ? node / kp.G : 0, cell = node - env * kp.G;
-  grid_grad_body(kp, node, inr, env, cell / kp.gz / kp.gy, (cell / kp.gz) % kp.gy, cell % kp.gz, grid, ggrid_v, ggrid, bt, gpos, grot, gnpos, gnrot);
+  grid_grad_body(kp, node, inr, env, cell / kp.gz / kp.gy, (cell / kp.gz) % kp.gy, cell % kp.gz, grid, ggrid_v, ggrid, bt, gpos, grot, gnpos, gnrot,
+                 kp.nb >= 64 ? ~0ull : (1ull << kp.nb) - 1ull, false, false);
 }
 
 // p2g_grad + compute_svd_grad (integrator.cu:396-627, 110-186) fused; writes the complete gradient of state t.
@@ -510,12 +551,32 @@ __global__ void __launch_bounds__(kT) k_grid_grad(KP kp, const float4 *__restric
 //   T  = sum N (g_mv (x) dpos)          -> dL/dstress = scale T, dL/dC += m T
 //   Sv = sum N g_mv                     -> dL/dv = m Sv, and the -N A^T g_mv term of dL/dx is -A^T Sv
 //   dL/dx += sum gradN (m g_m + g_mv . (m v + A dpos))
-template <int SVD>
-__global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict__ cur, const float *__restrict__ nxt, const float4 *__restrict__ mat0,
-                                                 const float *__restrict__ yield, const float4 *__restrict__ ggrid,
-                                                 const float *__restrict__ gin, float *__restrict__ gout) {
-  int p = blockIdx.x * kT + threadIdx.x;
-  if (p >= kp.EN) return;
+constexpr int kTileN = 512;          // 8^3 nodes
+constexpr int kTileWarps = 4;        // chunks per thread block
+DD_DEV int round_off(int j, int L, int q) { return j * (L - 1) + min(j, q); }
+struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, L, q; };
+DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
+  ChunkGeom c;
+  int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
+  c.env = ch.x / NB;
+  int b = ch.x - c.env * NB;
+  c.ox = (b / (nby * nbz)) * 4 - 1; c.oy = ((b / nbz) % nby) * 4 - 1; c.oz = (b % nbz) * 4 - 1;
+  c.start = ch.y; c.cnt = ch.z;
+  c.R = (c.cnt + 31) >> 5;
+  c.L = (c.cnt + c.R - 1) / c.R;
+  c.q = c.cnt - c.R * (c.L - 1);
+  return c;
+}
+// a particle whose stencil leaves the 3x3x3-brick neighbourhood of its home brick has out-run the active region
+DD_DEV void check_drift(int tx, int ty, int tz, int *overflow) {
+  if (tx < -3 || tx > 9 || ty < -3 || ty > 9 || tz < -3 || tz > 9) atomicOr(overflow, 1);
+}
+
+// TILE = true: node adjoints are read from a swizzled shared-memory tile at (tx,ty,tz); otherwise from the dense grid
+template <int SVD, bool TILE>
+DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur, const float *__restrict__ nxt, const float4 *__restrict__ mat0,
+                              const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *tile, int ox, int oy, int oz,
+                              const float *__restrict__ gin, float *__restrict__ gout, int *overflow) {
   XVC s = load_xvc(cur, kp.EN, p);
   M3 F = load_F(cur, kp.EN, p);
   float4 m0 = __ldg(mat0 + p);
@@ -533,6 +594,9 @@ __global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict_
      c2 = v3(c.affine.a02, c.affine.a12, c.affine.a22) * kp.dx;
   V3 base = m_p * s.v - (c0 * st.fx.x + c1 * st.fx.y + c2 * st.fx.z);
   const float4 *gg = ggrid + (size_t)(p / kp.N) * kp.G + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
+  int tx = st.bx - ox, ty = st.by - oy, tz = st.bz - oz;
+  bool in_tile = TILE && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
+  if (TILE && !in_tile) check_drift(tx, ty, tz, overflow);
   M3 T = mzero();
   V3 Sv = vzero(), g_x = vzero();
 #pragma unroll
@@ -547,7 +611,7 @@ __global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict_
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         float pk = ((float)k - st.fx.z) * kp.dx;
-        float4 t = __ldg(row + k);
+        float4 t = in_tile ? tile[tile_slot(tx + i, ty + j, tz + k)] : __ldg(row + k);
         V3 val = vij + c2 * (float)k;
         float N = wij * wz[k];
         V3 u = v3(t.x * N, t.y * N, t.z * N);
@@ -584,7 +648,7 @@ __global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict_
     V3 g_eh = (-pl.dg / pl.ehn) * g_eps;
     float g_ehn = -dot(pl.eh / pl.ehn, g_eps) * (yl / (2 * mu)) / pl.ehn;
     g_eh += (pl.eh / pl.ehn) * g_ehn;
-    float mean_g = (float)((double)(g_eh.x + g_eh.y + g_eh.z) / 3.);
+    float mean_g = (g_eh.x + g_eh.y + g_eh.z) / 3.f;
     g_eps += v3(g_eh.x - mean_g, g_eh.y - mean_g, g_eh.z - mean_g);
     if (c.sigma.x >= 0.05) g_sig.x += g_eps.x / c.sigma.x;
     if (c.sigma.y >= 0.05) g_sig.y += g_eps.y / c.sigma.y;
@@ -599,6 +663,15 @@ __global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict_
   store_xvc(gout, kp.EN, p, g_x, g_v, g_C);
   store_F(gout, kp.EN, p, g_F);
 }
+template <int SVD>
+__global__ void __launch_bounds__(kT, DD_LB_P2G_GRAD) k_p2g_grad(KP kp, const int *__restrict__ spos, const float *__restrict__ cur, const float *__restrict__ nxt,
+                                                 const float4 *__restrict__ mat0, const float *__restrict__ yield, const float4 *__restrict__ ggrid,
+                                                 const float *__restrict__ gin, float *__restrict__ gout) {
+  int p = blockIdx.x * kT + threadIdx.x;
+  if (p >= kp.EN) return;
+  (void)spos;  // measured: strided state loads cost this kernel more than the gather locality gains
+  p2g_grad_particle<SVD, false>(kp, p, cur, nxt, mat0, yield, ggrid, nullptr, 0, 0, 0, gin, gout, nullptr);
+}
 
 // ================================================================================================ tiled kernels
 // Particles are stored brick by brick (4x4x4 cells), a brick's particles cell-sorted and split into chunks.  One warp
@@ -608,29 +681,9 @@ __global__ void __launch_bounds__(kT) k_p2g_grad(KP kp, const float *__restrict_
 // round-major transpose of that assignment, which keeps every global load coalesced.  Collisions that do occur
 // (dense cells, drift) are detected with match.any and serialised.  The tile is flushed with one vector reduction per
 // touched node instead of one per (particle, node).
-constexpr int kTileN = 512;          // 8^3 nodes
-constexpr int kTileWarps = 4;        // chunks per thread block
-DD_DEV int round_off(int j, int L, int q) { return j * (L - 1) + min(j, q); }
-struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, L, q; };
-DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
-  ChunkGeom c;
-  int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
-  c.env = ch.x / NB;
-  int b = ch.x - c.env * NB;
-  c.ox = (b / (nby * nbz)) * 4 - 1; c.oy = ((b / nbz) % nby) * 4 - 1; c.oz = (b % nbz) * 4 - 1;
-  c.start = ch.y; c.cnt = ch.z;
-  c.R = (c.cnt + 31) >> 5;
-  c.L = (c.cnt + c.R - 1) / c.R;
-  c.q = c.cnt - c.R * (c.L - 1);
-  return c;
-}
-// a particle whose stencil leaves the 3x3x3-brick neighbourhood of its home brick has out-run the active region
-DD_DEV void check_drift(int tx, int ty, int tz, int *overflow) {
-  if (tx < -3 || tx > 9 || ty < -3 || ty > 9 || tz < -3 || tz > 9) atomicOr(overflow, 1);
-}
 
 template <int SVD, bool WRITE_F>
-__global__ void __launch_bounds__(32 * kTileWarps, 4) k_p2g_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                  float *__restrict__ nxt, const float4 *__restrict__ mat0,
                                                                  const float *__restrict__ yield, float4 *__restrict__ grid, int *overflow) {
   extern __shared__ float4 dd_smem[];
@@ -715,7 +768,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) k_p2g_tile(KP kp, int nchu
 // g2p_grad on tiles (integrator.cu:1527-1614): grid velocities are gathered from a tile copy, their adjoint is scattered
 // into a second tile.  With h_n = gv' + (4/dx) gC' (offset_n - fx) (affine in the offset, so evaluated incrementally):
 //   d/d v_n  = w_n h_n ;  dL/dx = -(4/dx^2) gC'^T (sum w_n v_n) + sum gradN_n (v_n . h_n)
-__global__ void __launch_bounds__(32 * kTileWarps, 3) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout,
                                                                       float4 *__restrict__ ggrid_v, int *overflow) {
@@ -828,6 +881,87 @@ __global__ void __launch_bounds__(32 * kTileWarps, 3) k_g2p_grad_tile(KP kp, int
   }
 }
 
+// load the 8^3 tile of a dense float4 grid into shared memory (swizzled slots); out-of-grid nodes read as zero
+DD_DEV void load_tile(float4 *tile, const float4 *__restrict__ grid_env, const ChunkGeom &cg, const KP &kp, int lane) {
+  for (int n = lane; n < kTileN; n += 32) {
+    int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
+    int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
+    bool ok = (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz;
+    tile[tile_slot(txx, tyy, tzz)] = ok ? __ldg(grid_env + (nx * kp.gy + ny) * kp.gz + nz) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// p2g_grad on tiles
+template <int SVD>
+__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+                                                                      const float *__restrict__ nxt, const float4 *__restrict__ mat0,
+                                                                      const float *__restrict__ yield, const float4 *__restrict__ ggrid,
+                                                                      const float *__restrict__ gin, float *__restrict__ gout, int *overflow) {
+  extern __shared__ float4 dd_smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ci = blockIdx.x * kTileWarps + warp;
+  if (ci >= nchunks) return;
+  float4 *tile = dd_smem + warp * kTileN;
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  load_tile(tile, ggrid + (size_t)cg.env * kp.G, cg, kp, lane);
+  __syncwarp();
+  for (int j = 0; j < cg.R; ++j) {
+    if (lane >= cg.L - (j >= cg.q ? 1 : 0)) continue;
+    p2g_grad_particle<SVD, true>(kp, cg.start + round_off(j, cg.L, cg.q) + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow);
+  }
+}
+
+// g2p on tiles: the 27 node velocities come from a shared-memory copy of the brick's neighbourhood
+__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+                                                                 float *__restrict__ nxt, const float4 *__restrict__ grid_v, int *overflow) {
+  extern __shared__ float4 dd_smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ci = blockIdx.x * kTileWarps + warp;
+  if (ci >= nchunks) return;
+  float4 *tile = dd_smem + warp * kTileN;
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  const float4 *genv = grid_v + (size_t)cg.env * kp.G;
+  load_tile(tile, genv, cg, kp, lane);
+  __syncwarp();
+  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+  float lo = kp.gh * kp.dx;
+  for (int j = 0; j < cg.R; ++j) {
+    if (lane >= cg.L - (j >= cg.q ? 1 : 0)) continue;
+    int p = cg.start + round_off(j, cg.L, cg.q) + lane;
+    float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
+    V3 x = v3(a.x, a.y, a.z);
+    Stencil st = make_stencil_safe(x, kp);
+    float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
+    int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
+    bool in_tile = (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
+    if (!in_tile) check_drift(tx, ty, tz, overflow);
+    const float4 *g = genv + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
+    V3 nv = vzero();
+    M3 nC = mzero();
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float di = (float)i - st.fx.x;
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj) {
+        float wij = wx[i] * wy[jj], dj = (float)jj - st.fx.y;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float w = wij * wz[k], dk = (float)k - st.fx.z;
+          float4 t = in_tile ? tile[tile_slot(tx + i, ty + jj, tz + k)] : __ldg(g + (i * kp.gy + jj) * kp.gz + k);
+          V3 u = v3(t.x * w, t.y * w, t.z * w);
+          nv += u;
+          nC.a00 = fmaf(u.x, di, nC.a00); nC.a01 = fmaf(u.x, dj, nC.a01); nC.a02 = fmaf(u.x, dk, nC.a02);
+          nC.a10 = fmaf(u.y, di, nC.a10); nC.a11 = fmaf(u.y, dj, nC.a11); nC.a12 = fmaf(u.y, dk, nC.a12);
+          nC.a20 = fmaf(u.z, di, nC.a20); nC.a21 = fmaf(u.z, dj, nC.a21); nC.a22 = fmaf(u.z, dk, nC.a22);
+        }
+      }
+    }
+    nC = nC * (kp.inv_dx * 4.f);
+    V3 t = x + nv * kp.dt;
+    store_xvc(nxt, kp.EN, p, v3(fmaxf(fminf(t.x, hi.x), lo), fmaxf(fminf(t.y, hi.y), lo), fmaxf(fminf(t.z, hi.z), lo)), nv, nC);
+  }
+}
+
 // ---- grid kernels restricted to the active bricks (3x3x3-brick neighbourhood of every occupied brick) -----------------
 DD_DEV int brick_node(int brick, int local, const KP &kp, int &env, int &gx_, int &gy_, int &gz_) {
   int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
@@ -844,38 +978,82 @@ __global__ void __launch_bounds__(kT) k_zero_bricks(KP kp, int nactive, const in
   a[node] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (b) b[node] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
-__global__ void __launch_bounds__(kT) k_grid_b(KP kp, int nactive, const int *__restrict__ active, const float4 *__restrict__ grid,
-                                               float4 *__restrict__ grid_v, BodyTables bt) {
-  int t = blockIdx.x * kT + threadIdx.x;
-  if (t >= nactive * 64) return;
+// Four bricks (64 nodes each) per block.  Each 64-thread group first copies its environment's body poses into shared
+// memory and builds a 64-bit mask of the bodies whose activation sphere reaches the brick's bounding box at all; the
+// per-node loop then only visits those (typically 0-3 of the 19 primitives) in index order.
+struct GridSm {
+  float4 pos[4][64], rot[4][64], npos[4][64], nrot[4][64], tfsr[64], args[64];
+  float cull[64];
+  unsigned long long cand[4];
+};
+DD_DEV unsigned long long stage_bodies(GridSm &sm, const KP &kp, const BodyTables &bt, bool valid, int brick, int grp, int g, BodyTables &view) {
+  if (threadIdx.x < 4) sm.cand[threadIdx.x] = 0ull;
+  if ((int)threadIdx.x < kp.nb) { sm.tfsr[threadIdx.x] = bt.tfsr[threadIdx.x]; sm.args[threadIdx.x] = bt.args[threadIdx.x]; sm.cull[threadIdx.x] = bt.cull[threadIdx.x]; }
+  __syncthreads();
+  int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
+  int env = valid ? brick / NB : 0, bb = valid ? brick - env * NB : 0;
+  if (valid && g < kp.nb) {
+    int pb = env * kp.nb + g;
+    float4 p = bt.pos[pb];
+    sm.pos[grp][g] = p; sm.rot[grp][g] = bt.rot[pb]; sm.npos[grp][g] = bt.npos[pb]; sm.nrot[grp][g] = bt.nrot[pb];
+    // squared distance from the body centre to the brick's node box [lo, lo + 3 dx]
+    float lx = (float)((bb / (nby * nbz)) * 4) * kp.dx, ly = (float)(((bb / nbz) % nby) * 4) * kp.dx, lz = (float)((bb % nbz) * 4) * kp.dx, w = 3.f * kp.dx;
+    float dx_ = fmaxf(fmaxf(lx - p.x, p.x - (lx + w)), 0.f), dy_ = fmaxf(fmaxf(ly - p.y, p.y - (ly + w)), 0.f), dz_ = fmaxf(fmaxf(lz - p.z, p.z - (lz + w)), 0.f);
+    float c = bt.cull[g] * 1.0001f + 1e-6f;
+    if (dx_ * dx_ + dy_ * dy_ + dz_ * dz_ <= c * c) atomicOr(&sm.cand[grp], 1ull << g);
+  }
+  __syncthreads();
+  // body index inside the kernels is env*nb + b: bias the shared-memory pointers so the same expression lands on [b]
+  view.pos = sm.pos[grp] - env * kp.nb; view.rot = sm.rot[grp] - env * kp.nb; view.npos = sm.npos[grp] - env * kp.nb; view.nrot = sm.nrot[grp] - env * kp.nb;
+  view.tfsr = sm.tfsr; view.args = sm.args; view.cull = sm.cull;
+  return sm.cand[grp];
+}
+
+// zero_next: the (distinct) scatter target of the NEXT substep, cleared here so that no separate zeroing pass is needed;
+// zero_self: clear this substep's (m, mv) after use (forward-only mode with a single grid buffer)
+__global__ void __launch_bounds__(kT, 4) k_grid_b(KP kp, int nactive, const int *__restrict__ active, float4 *__restrict__ grid,
+                                               float4 *__restrict__ grid_v, BodyTables bt, float4 *__restrict__ zero_next, int zero_self) {
+  __shared__ GridSm sm;
+  int t = blockIdx.x * kT + threadIdx.x, grp = threadIdx.x >> 6, g = threadIdx.x & 63;
+  bool valid = t < nactive * 64;
+  int brick = valid ? active[t >> 6] : 0;
+  BodyTables view;
+  unsigned long long cand = stage_bodies(sm, kp, bt, valid, brick, grp, g, view);
+  if (!valid) return;
   int env, gx_, gy_, gz_;
-  int node = brick_node(active[t >> 6], t & 63, kp, env, gx_, gy_, gz_);
+  int node = brick_node(brick, g, kp, env, gx_, gy_, gz_);
   float4 mm = grid[node];
+  if (zero_next) zero_next[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (zero_self) grid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!(mm.w > 1e-12)) {
     grid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
   V3 v = v3(mm.x, mm.y, mm.z) * (1.f / mm.w) + kp.dt * v3(kp.g0, kp.g1, kp.g2);
   V3 gx = v3((float)gx_, (float)gy_, (float)gz_) * kp.dx;
-  for (int b = 0; b < kp.nb; ++b) {
-    int pb = env * kp.nb + b;
+  for (unsigned long long c = cand; c; c &= c - 1ull) {
+    int b = __ffsll((long long)c) - 1, pb = env * kp.nb + b;
     Hit h;
-    Q4 bq = q4f(bt.rot[pb]), tfsr = q4f(bt.tfsr[b]), sargs = q4f(bt.args[b]);
-    if (contact_geom(gx, v3f(bt.pos[pb]), bq, tfsr, sargs, bt.cull[b], h))
-      v = contact_apply(gx, v, bq, v3f(bt.npos[pb]), q4f(bt.nrot[pb]), tfsr, sargs, kp.dt, h);
+    Q4 bq = q4f(view.rot[pb]), tfsr = q4f(view.tfsr[b]), sargs = q4f(view.args[b]);
+    if (contact_geom(gx, v3f(view.pos[pb]), bq, tfsr, sargs, view.cull[b], h))
+      v = contact_apply(gx, v, bq, v3f(view.npos[pb]), q4f(view.nrot[pb]), tfsr, sargs, kp.dt, h);
   }
   v = apply_bc(v, gx_, gy_, gz_, kp);
   grid_v[node] = make_float4(v.x, v.y, v.z, 0.f);
 }
 
-__global__ void __launch_bounds__(kT) k_grid_grad_b(KP kp, int nactive, const int *__restrict__ active, const float4 *__restrict__ grid,
-                                                    const float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos,
-                                                    float4 *grot, float4 *gnpos, float4 *gnrot) {
-  int t = blockIdx.x * kT + threadIdx.x;
+__global__ void __launch_bounds__(kT, 4) k_grid_grad_b(KP kp, int nactive, const int *__restrict__ active, float4 *__restrict__ grid,
+                                                    float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos,
+                                                    float4 *grot, float4 *gnpos, float4 *gnrot, int zero_m) {
+  __shared__ GridSm sm;
+  int t = blockIdx.x * kT + threadIdx.x, grp = threadIdx.x >> 6, g = threadIdx.x & 63;
   bool inr = t < nactive * 64;
+  int brick = inr ? active[t >> 6] : 0;
+  BodyTables view;
+  unsigned long long cand = stage_bodies(sm, kp, bt, inr, brick, grp, g, view);
   int env = 0, x = 0, y = 0, z = 0, node = 0;
-  if (inr) node = brick_node(active[t >> 6], t & 63, kp, env, x, y, z);
-  grid_grad_body(kp, node, inr, env, x, y, z, grid, ggrid_v, ggrid, bt, gpos, grot, gnpos, gnrot);
+  if (inr) node = brick_node(brick, g, kp, env, x, y, z);
+  grid_grad_body(kp, node, inr, env, x, y, z, grid, ggrid_v, ggrid, view, gpos, grot, gnpos, gnrot, cand, true, zero_m != 0);
 }
 
 // ---- layout conversion (original AoS order <-> sorted planes) --------------------------------------------------------
@@ -942,18 +1120,23 @@ __global__ void k_mark_heads(int EN, const unsigned *__restrict__ keys, char *__
   if (i >= EN) return;
   flags[i] = (i == 0) || (keys[i] >> 6) != (keys[i - 1] >> 6);
 }
-// one thread per occupied brick: split its particle range into chunks and mark its 3x3x3 neighbourhood active
+// one thread per occupied brick: split its particles into `nsub` chunks and mark its 3x3x3 neighbourhood active.
+// Chunk c takes the cell-sorted ranks r = c (mod nsub) of the brick -- a thinned copy of the whole brick, so that the
+// lanes of a round still sit in different cells -- and owns the storage range after chunks 0..c-1.
 __global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_pos, const unsigned *__restrict__ keys, int chunk_max,
-                              int4 *__restrict__ chunks, int *__restrict__ counters, char *__restrict__ active_flag) {
+                              int4 *__restrict__ chunks, int4 *__restrict__ chunk_src, int *__restrict__ counters, char *__restrict__ active_flag) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nbricks) return;
   int start = head_pos[k], end = k + 1 < nbricks ? head_pos[k + 1] : kp.EN, cnt = end - start;
   int brick = (int)(keys[start] >> 6);
-  int nch = (cnt + chunk_max - 1) / chunk_max;
-  int c0 = atomicAdd(&counters[0], nch);
-  for (int c = 0; c < nch; ++c) {
-    int s = start + (int)((long long)cnt * c / nch), t = start + (int)((long long)cnt * (c + 1) / nch);
-    chunks[c0 + c] = make_int4(brick, s, t - s, 0);
+  int nsub = (cnt + chunk_max - 1) / chunk_max;
+  int c0 = atomicAdd(&counters[0], nsub);
+  int s = start;
+  for (int c = 0; c < nsub; ++c) {
+    int n_c = (cnt - c + nsub - 1) / nsub;
+    chunks[c0 + c] = make_int4(brick, s, n_c, 0);
+    chunk_src[c0 + c] = make_int4(start, cnt, c, nsub);
+    s += n_c;
   }
   int nbx = kp.gx >> 2, nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = nbx * nby * nbz;
   int env = brick / NB, b = brick - env * NB;
@@ -965,14 +1148,18 @@ __global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_p
         if ((unsigned)x < (unsigned)nbx && (unsigned)y < (unsigned)nby && (unsigned)z < (unsigned)nbz) active_flag[env * NB + (x * nby + y) * nbz + z] = 1;
       }
 }
-// round-major transpose of every chunk (see the tiled kernels): one warp per chunk
-__global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks, const int *__restrict__ perm_in, int *__restrict__ perm_out) {
+// storage order: every chunk round-major (see the tiled kernels); one warp per chunk
+__global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src, const int *__restrict__ perm_in,
+                             int *__restrict__ perm_out, int *__restrict__ spos) {
   int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (ci >= nchunks) return;
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  int4 src = chunk_src[ci];  // (brick start, brick count, c, nsub)
   for (int r = lane; r < cg.cnt; r += 32) {
     int l = r / cg.R, j = r - l * cg.R;
-    perm_out[cg.start + round_off(j, cg.L, cg.q) + l] = perm_in[cg.start + r];
+    int pos = cg.start + round_off(j, cg.L, cg.q) + l, from = src.x + src.z + r * src.w;
+    perm_out[pos] = perm_in[from];
+    spos[from] = pos;  // cell-sorted rank -> storage position, for the flat gather kernels
   }
 }
 
@@ -1103,9 +1290,9 @@ struct dd_sim {
   void *cub_tmp = nullptr;
   size_t cub_bytes = 0;
   // tiled mode: chunk list, active bricks, per-substep grid checkpoints
-  int4 *chunks = nullptr;
+  int4 *chunks = nullptr, *chunk_src = nullptr;
   int chunk_cap = 0, nchunks = 0, chunk_max = 512;
-  int *head_pos = nullptr;
+  int *head_pos = nullptr, *spos = nullptr;
   char *head_flags = nullptr, *active_flag = nullptr;
   int *active = nullptr;
   int nactive = 0, NBtot = 0;
@@ -1137,27 +1324,28 @@ namespace {
 
 using Mark = std::function<void(const char *)>;
 inline void mark(const Mark *m, const char *name) { if (m) (*m)(name); }
-int fwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? 4 : 3; }
-int bwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? (s->grid_ckpt ? 4 : 7) : 5; }
+int fwd_launches(const dd_sim *s) { return 3; }
+int bwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? (s->grid_ckpt ? 3 : 5) : 5; }
 
 template <int SVD>
 void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk = nullptr) {
   const KP &kp = s->kp;
   if (s->cfg.tile_mode) {
     int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
-    k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), nullptr);
-    mark(mk, "zero_bricks");
+    // invariant: the scatter target of substep f is already zero on the active bricks (cleared by the previous grid
+    // kernel, or by dd_sim_forward for the first substep of a range)
     k_p2g_tile<SVD, true><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->counters + 3);
     mark(mk, "p2g_tile (svd+return map+scatter)");
-    k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f));
+    float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
+    k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_b (grid update + contact)");
-    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->GV(f));
+    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->GV(f));
     mark(mk, "g2p");
   } else {
     cudaMemsetAsync(s->grid, 0, sizeof(float4) * (size_t)kp.E * kp.G, st);
     k_p2g<SVD, true><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
     k_grid<<<nblk((long long)kp.E * kp.G), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
-    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v);
+    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, nullptr, s->slot(f), s->slot(f + 1), s->grid_v);
   }
   s->launches += fwd_launches(s);
 }
@@ -1169,19 +1357,16 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
   float4 *gp = s->gpos + (size_t)f * ep, *gr = s->grot + (size_t)f * ep, *gnp = s->gpos + (size_t)(f + 1) * ep, *gnr = s->grot + (size_t)(f + 1) * ep;
   if (s->cfg.tile_mode) {
     int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
-    if (s->grid_ckpt) {
-      k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->ggrid_v, nullptr);
-      mark(mk, "zero_bricks (adjoint)");
-    } else {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
-      k_zero_bricks<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->ggrid_v);
+    // invariant: ggrid_v is zero on the active bricks (k_grid_grad_b clears what it consumes)
+    if (!s->grid_ckpt) {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
       k_p2g_tile<SVD, false><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->counters + 3);
-      k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f));
+      k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
     k_g2p_grad_tile<<<ncb, 32 * kTileWarps, 2 * kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->counters + 3);
     mark(mk, "g2p_grad_tile");
-    k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr);
+    k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
-    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
+    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
     mark(mk, "p2g_grad (+svd adjoint)");
   } else {
     cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st);
@@ -1190,7 +1375,7 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
     k_grid<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
     k_g2p_grad<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v, gin, gout, s->ggrid_v);
     k_grid_grad<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr);
-    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
+    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, nullptr, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
   }
   s->launches += bwd_launches(s);
 }
@@ -1307,11 +1492,13 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
     if ((kp.gx | kp.gy | kp.gz) & 3) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode needs grid dimensions that are multiples of 4"); }
     s->NBtot = kp.E * (kp.gx >> 2) * (kp.gy >> 2) * (kp.gz >> 2);
     cudaFuncSetAttribute(k_g2p_grad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTileWarps * kTileN * sizeof(float4)));
-    s->chunk_max = cfg->chunk_max > 0 ? cfg->chunk_max : std::min(512, std::max(64, kp.EN / (148 * 8)));
+    s->chunk_max = cfg->chunk_max > 0 ? cfg->chunk_max : 160;  // ~3 thinned chunks per dense brick: several waves of warps (profiles/)
     int occ_cap = std::min(kp.EN, s->NBtot);
     s->chunk_cap = kp.EN / s->chunk_max + occ_cap + 1;
     DD_ALLOC(s->chunks, sizeof(int4) * s->chunk_cap);
+    DD_ALLOC(s->chunk_src, sizeof(int4) * s->chunk_cap);
     DD_ALLOC(s->head_pos, sizeof(int) * (occ_cap + 1));
+    DD_ALLOC(s->spos, sizeof(int) * ENp);
     DD_ALLOC(s->head_flags, ENp);
     DD_ALLOC(s->active_flag, s->NBtot);
     DD_ALLOC(s->active, sizeof(int) * s->NBtot);
@@ -1346,7 +1533,7 @@ void dd_sim_destroy(dd_sim *s) {
   for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
   void *ptrs[] = {s->ckpt, s->grad[0], s->grad[1], s->mat0, s->yield, s->grid, s->grid_v, s->ggrid_v, s->ggrid, s->pos, s->rot, s->gpos, s->grot,
                   s->tfsr, s->args, s->cull, s->perm, s->stage, s->keys, s->keys_alt, s->idx_alt, s->cub_tmp, s->mat_aos,
-                  s->chunks, s->head_pos, s->head_flags, s->active_flag, s->active, s->counters, s->sel_tmp, s->gridck, s->gridvck};
+                  s->chunks, s->chunk_src, s->head_pos, s->spos, s->head_flags, s->active_flag, s->active, s->counters, s->sel_tmp, s->gridck, s->gridvck};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -1413,14 +1600,14 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
       DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
       DD_CUDA(cudaStreamSynchronize(st));
       int nbricks = host[2];
-      k_make_chunks<<<nblk(nbricks), kT, 0, st>>>(kp, nbricks, s->head_pos, s->keys_alt, s->chunk_max, s->chunks, s->counters, s->active_flag);
+      k_make_chunks<<<nblk(nbricks), kT, 0, st>>>(kp, nbricks, s->head_pos, s->keys_alt, s->chunk_max, s->chunks, s->chunk_src, s->counters, s->active_flag);
       DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->active_flag, s->active, s->counters + 1, s->NBtot, st));
       DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
       DD_CUDA(cudaStreamSynchronize(st));
       s->nchunks = host[0];
       s->nactive = host[1];
       if (s->nchunks > s->chunk_cap) return fail("dd_sim_set_state: chunk list overflow");
-      k_interleave<<<nblk((long long)s->nchunks * 32), kT, 0, st>>>(kp, s->nchunks, s->chunks, s->perm, s->idx_alt);
+      k_interleave<<<nblk((long long)s->nchunks * 32), kT, 0, st>>>(kp, s->nchunks, s->chunks, s->chunk_src, s->perm, s->idx_alt, s->spos);
       std::swap(s->perm, s->idx_alt);
       // the active region changed: drop stale graphs (they captured the old launch geometry) and stale grid contents
       for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
@@ -1484,11 +1671,15 @@ int dd_sim_forward(dd_sim *s, int f0, int n, cudaStream_t st) {
       cudaMemsetAsync(s->gpos + (size_t)(f0 + 1) * ep, 0, sizeof(float4) * ep * n, q);
       cudaMemsetAsync(s->grot + (size_t)(f0 + 1) * ep, 0, sizeof(float4) * ep * n, q);
     }
+    if (s->cfg.tile_mode) {
+      k_zero_bricks<<<nblk((long long)s->nactive * 64), kT, 0, q>>>(s->kp, s->nactive, s->active, s->G(f0), nullptr);
+      s->launches += 1;
+    }
     for (int f = f0; f < f0 + n; ++f) {
       if (s->cfg.svd_mode == 0) enqueue_forward_substep<0>(s, f, q); else enqueue_forward_substep<1>(s, f, q);
     }
   };
-  return run_graphed(s, 0, f0, n, st, (long long)fwd_launches(s) * n, body);
+  return run_graphed(s, 0, f0, n, st, (long long)fwd_launches(s) * n + (s->cfg.tile_mode ? 1 : 0), body);
 }
 
 int dd_sim_zero_grad(dd_sim *s, int f, cudaStream_t st) {
@@ -1621,6 +1812,7 @@ int dd_sim_profile_substep(dd_sim *s, int f, int reps, float *ms_out, char *name
       if (k >= ev.size()) { cudaEvent_t e_; cudaEventCreate(&e_); ev.push_back(e_); }
       cudaEventRecord(ev[k++], st);
     };
+    k_zero_bricks<<<nblk((long long)s->nactive * 64), kT, 0, st>>>(s->kp, s->nactive, s->active, s->G(f), nullptr);  // untimed: scatter target of this substep
     new_event();
     Mark mk = [&](const char *name) { if (r == 0) names.push_back(name); new_event(); };
     if (s->cfg.svd_mode == 0) { enqueue_forward_substep<0>(s, f, st, &mk); enqueue_backward_substep<0>(s, f, st, &mk); }

@@ -124,7 +124,12 @@ DD_DEV void xform_inv_adj(V3 p, Q4 q, V3 pt, V3 g, V3 &gp, Q4 &gq, V3 &gpt) {
 
 // ---------------------------------------------------------------------------------------------- shapes
 // length with the 1e-30 epsilon evaluated in double as in the reference (shape.h:4-9: float + double literal)
+#ifdef DD_FLOAT_LENGTH
+// engine kernels: the 1e-30 epsilon only matters for |a|^2 < 1e-23, where both forms return ~1e-15; no fp64 sqrt
+DD_DEV float length30(V3 a) { return sqrtf(dot(a, a) + 1e-30f); }
+#else
 DD_DEV float length30(V3 a) { return (float)sqrt((double)dot(a, a) + 1e-30); }
+#endif
 DD_DEV V3 normalized(V3 a) { return a / length30(a); }                           // shape.h:12-14
 DD_DEV V3 normalized_adj(V3 vec, V3 g) {                                         // shape.h:16-25
   float doted = (float)((double)dot(vec, vec) + 1e-30);
@@ -550,11 +555,18 @@ DD_DEV float clamp_eps(float a) { return a >= 0.f ? fmaxf(a, 1e-6f) : fminf(a, -
 // Adjoint through (U,sigma,V) = svd(Ft): returns dL/dFt given dL/dU, dL/dsigma, dL/dV (integrator.cu:131-159,
 // without the newF_grad term).
 DD_DEV M3 svd_adj(const M3 &u, V3 sigma, const M3 &v, const M3 &gu, V3 gs, const M3 &gv) {
+#ifdef DD_FLOAT_LENGTH
+  // s_j^2 - s_i^2 = (s_j - s_i)(s_j + s_i): the difference of nearby floats is exact, so this matches the reference's
+  // double-precision squares rounded to float to within one ulp, without fp64 multiplies and divides
+  float d10 = (sigma.y - sigma.x) * (sigma.y + sigma.x), d20 = (sigma.z - sigma.x) * (sigma.z + sigma.x), d21 = (sigma.z - sigma.y) * (sigma.z + sigma.y);
+  M3 K = m3(0.f, 1.f / clamp_eps(d10), 1.f / clamp_eps(d20), 1.f / clamp_eps(-d10), 0.f, 1.f / clamp_eps(d21), 1.f / clamp_eps(-d20), 1.f / clamp_eps(-d21), 0.f);
+#else
   double s0 = sigma.x, s1 = sigma.y, s2 = sigma.z;
   s0 = s0 * s0; s1 = s1 * s1; s2 = s2 * s2;
   M3 K = m3(0.f, (float)(1.0 / clamp_eps((float)(s1 - s0))), (float)(1.0 / clamp_eps((float)(s2 - s0))),
             (float)(1.0 / clamp_eps((float)(s0 - s1))), 0.f, (float)(1.0 / clamp_eps((float)(s2 - s1))),
             (float)(1.0 / clamp_eps((float)(s0 - s2))), (float)(1.0 / clamp_eps((float)(s1 - s2))), 0.f);
+#endif
   M3 ut_gu = mul_tn(u, gu);
   M3 vt_gv = mul_tn(v, gv);
   M3 u_term = mul_nt(mul(u, mul_diag(hadamard(K, ut_gu - transpose(ut_gu)), sigma)), v);

@@ -16,7 +16,7 @@ from ctypes import c_bool, c_float, c_int32, c_size_t, c_ulonglong, c_void_p
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libmaniskill_mpm.so")
+LIB_PATH = os.environ.get("DEXDEFORM_B200_LIB") or os.path.join(PKG_DIR, "libmaniskill_mpm.so")  # env override: A/B-test builds
 
 cuda_stream_t = c_void_p
 texture_t = c_ulonglong

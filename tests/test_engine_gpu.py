@@ -85,7 +85,7 @@ def test_engine_matches_reference_cuda_short(ref_gpu, svd_mode, graphs, tile):
         assert cosine(eng["grad"][k][0], ref["grad"][k + "_grad"]) > 0.999
     assert rel_err(eng["gpos"][:, 0], ref["gpos"]) < tol_of("gpos", 2e-4)
     assert rel_err(eng["grot"][:, 0], ref["grot"]) < tol_of("grot", 2e-4)
-    assert eng["launches"] == (4 * S + 4 * S if tile else 3 * S + 5 * S)
+    assert eng["launches"] == (3 * S + 1 + 3 * S if tile else 3 * S + 5 * S)
 
 
 def test_engine_rollout_50_substeps_vs_reference(ref_gpu):
@@ -203,4 +203,4 @@ def test_recompute_mode_matches_checkpoint_mode():
     b = run_engine(sc, S, seedg, grid_ckpt=False)
     for k in ("x", "v", "F", "C"):
         assert_close_rows(b["grad"][k][0], a["grad"][k][0], 1e-4, k + "_grad")
-    assert a["launches"] == 8 * S and b["launches"] == 11 * S
+    assert a["launches"] == 6 * S + 1 and b["launches"] == 8 * S + 1
