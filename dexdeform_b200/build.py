@@ -6,7 +6,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libmaniskill_mpm.so")
-SOURCES = ["abi1_kernels.cu", "engine.cu"]
+SOURCES = ["abi1_kernels.cu", "engine.cu", "fk.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1434,9 +1434,22 @@ int check_range(dd_sim *s, int f0, int n, const char *what) {
 
 }  // namespace
 
+int dd_set_error(const char *msg) { return fail(msg); }  // shared with fk.cu
+
 extern "C" {
 
 const char *dd_last_error(void) { return g_last_error.c_str(); }
+
+// device pointers of the pose table: float4 (x,y,z,0) / (w,x,y,z) per (slot, env, body)
+int dd_sim_pose_table(dd_sim *s, float **pos, float **rot, int *slots, int *n_envs, int *n_bodies) {
+  if (!s) return fail("dd_sim_pose_table: null simulator");
+  if (pos) *pos = reinterpret_cast<float *>(s->pos);
+  if (rot) *rot = reinterpret_cast<float *>(s->rot);
+  if (slots) *slots = s->slots;
+  if (n_envs) *n_envs = s->kp.E;
+  if (n_bodies) *n_bodies = s->kp.nb;
+  return 0;
+}
 
 int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
   if (!cfg || !out) return fail("dd_sim_create: null argument");

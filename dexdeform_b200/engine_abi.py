@@ -34,6 +34,10 @@ ABI2 = {
     "dd_sim_compute_grid_mass": (c_int, [P, c_int, P, c_int, P, S]),
     "dd_sim_compute_grid_mass_grad": (c_int, [P, c_int, P, c_int, P, S]),
     "dd_sim_sync": (c_int, [P, S]),
+    "dd_sim_pose_table": (c_int, [P, P, P, P, P, P]),
+    "dd_hand_create": (c_int, [c_int, c_int, P, P, P, c_int, P, P, P, c_int, P, P, P, P, P, P, P]),
+    "dd_hand_destroy": (None, [P]),
+    "dd_hand_fk": (c_int, [P, P, c_int, c_int, P, P, P, P, P, c_int, S]),
     "dd_sim_profile_substep": (c_int, [P, c_int, c_int, P, P, c_int, P, S]),
 }
 

@@ -165,6 +165,19 @@ int dd_sim_sync(dd_sim *sim, cudaStream_t stream);
 /* measurement aid: device time of every kernel of one forward + backward substep (CUDA events on `stream`) */
 int dd_sim_profile_substep(dd_sim *sim, int f, int reps, float *ms_out, char *names_out, int names_cap, int *n_out, cudaStream_t stream);
 
+/* device pointers of the engine's pose table: float4 (x,y,z,0) and (w,x,y,z) per (slot, env, body) */
+int dd_sim_pose_table(dd_sim *sim, float **pos, float **rot, int *slots, int *n_envs, int *n_bodies);
+
+/* ---- Shadow-hand kinematics on the device (replaces HandSimulator.JointVel_Fk + hand_forward_kinematics, mpm/hand.py:347-428).
+ * Tables as produced by dexdeform_b200.mujoco_parser.hand_tables; all pointer arguments of dd_hand_fk are DEVICE pointers. */
+typedef struct dd_hand dd_hand;
+int dd_hand_create(int n_hands, int n_ops, const int *op_kind, const int *op_index, const int *op_reset, int n_mats, const float *mats,
+                   const float *joint_pos, const float *joint_axis, int n_geoms, const int *geom_joint, const float *geom_local,
+                   const float *q_lower, const float *q_upper, const int *action_map, const float *action_scale, dd_hand **out);
+void dd_hand_destroy(dd_hand *hand);
+int dd_hand_fk(dd_hand *hand, dd_sim *sim, int f, int n_substeps, const float *base_pose, const float *joint_rot, const float *action,
+               float *next_base, float *next_q, int has_base_action, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,8 @@ TOL_GRID = 2e-5
 
 
 def golden_cases(suffix=""):
-    return sorted(f[: -4 - len(suffix)] for f in os.listdir(GOLDEN_DIR) if f.endswith(suffix + ".npz") and (suffix or not f.endswith("_gpu.npz")))
+    from golden.make_golden import CASES
+    return sorted(c for c in CASES if os.path.isfile(os.path.join(GOLDEN_DIR, c + suffix + ".npz")))
 
 
 def load_golden(name, suffix=""):

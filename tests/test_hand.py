@@ -1,0 +1,182 @@
+"""Hand layer: MJCF tables, rotation helpers, torch FK (CPU) and the device FK kernel (GPU) against the torch FK."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from dexdeform_b200.hand import HandKinematics, rigid_body_motion_hand
+from dexdeform_b200.mujoco_parser import HandTables, default_assets_dir
+from dexdeform_b200.robots import JOINTS, N_ACTUATORS, actuator_of_joint, joint_limits
+from dexdeform_b200.rotations import axis_angle_to_matrix, euler2mat, matrix_to_quaternion, quaternion_to_matrix
+
+FIX = os.path.join(ROOT, "tests", "golden", "shadow_tables.npz")
+HAVE_ASSETS = os.path.isdir(os.path.join(default_assets_dir(), "robots", "shadow"))
+
+
+def tables(tag="rh15"):
+    z = np.load(FIX)
+    return HandTables(**{k.split(".", 1)[1]: (int(z[k]) if k.endswith("n_hands") else z[k]) for k in z.files if k.startswith(tag + ".")})
+
+
+def test_joint_tables():
+    assert len(JOINTS) == 24 and N_ACTUATORS == 20
+    m = actuator_of_joint()
+    assert m[4] == m[5] == 4 and m[23] == 19 and sorted(set(m)) == list(range(20))
+    lim = joint_limits()
+    assert np.allclose(lim[4], [0.0, 3.1416 / 2]) and np.allclose(lim[0], [-0.4887, 0.1396])  # coupled joints get half the range
+
+
+def test_rotation_helpers_roundtrip():
+    g = torch.Generator().manual_seed(0)
+    q = torch.nn.functional.normalize(torch.randn(200, 4, generator=g), dim=-1)
+    R = quaternion_to_matrix(q)
+    assert torch.allclose(R @ R.transpose(-1, -2), torch.eye(3).expand(200, 3, 3), atol=1e-5)
+    q2 = matrix_to_quaternion(R)
+    assert torch.allclose(torch.minimum((q - q2).norm(dim=-1), (q + q2).norm(dim=-1)), torch.zeros(200), atol=2e-6)
+    aa = torch.randn(50, 3, generator=g)
+    Ra = axis_angle_to_matrix(aa)
+    ang = aa.norm(dim=-1)
+    assert torch.allclose((Ra.diagonal(dim1=-2, dim2=-1).sum(-1) - 1) / 2, torch.cos(ang), atol=1e-5)   # trace = 1 + 2 cos
+    assert torch.allclose(torch.einsum("nij,nj->ni", Ra, aa), aa, atol=1e-5)                              # the axis is invariant
+    assert np.allclose(euler2mat(0.3, 0.0, 0.0), [[1, 0, 0], [0, np.cos(0.3), -np.sin(0.3)], [0, np.sin(0.3), np.cos(0.3)]])
+    assert np.allclose(euler2mat(0.0, 0.0, np.pi) @ [1, 0, 0], [-1, 0, 0], atol=1e-12)
+
+
+@pytest.mark.skipif(not HAVE_ASSETS, reason="DexDeform asset files not present")
+def test_parser_reproduces_fixture_tables():
+    from dexdeform_b200.mujoco_parser import hand_tables, load_hand
+    t = hand_tables([load_hand("right_hand", 1.5)])
+    ref = tables("rh15")
+    for k, v in ref.__dict__.items():
+        assert np.array_equal(np.asarray(getattr(t, k)), np.asarray(v)), k
+    m = load_hand("right_hand", 1.5)
+    kinds = [p.kind for p in m.primitives]
+    assert len(kinds) == 19 and kinds.count("box") == 3 and kinds.count("capsule") == 16
+    assert [len(c) for c in m.chains] == [12, 12, 12, 14, 14]
+
+
+def test_torch_fk_geometry_and_gradients():
+    t = tables()
+    kin = HandKinematics(t)
+    base = torch.tensor(t.root_frame, dtype=torch.float32)[None]
+    pos0, rot0 = kin.forward(base, torch.zeros(1, 1, 24))
+    assert pos0.shape == (1, 19, 3) and torch.allclose(rot0.norm(dim=-1), torch.ones(1, 19), atol=1e-5)
+    # wrist capsule sits at the wrist frame origin; bending FFJ3..FFJ0 moves only the first finger's primitives (3, 4, 5)
+    assert torch.allclose(pos0[0, 0], base[0, 0, :3, 3], atol=1e-6)
+    q = torch.zeros(1, 1, 24)
+    q[..., 3] = 0.5
+    pos1, _ = kin.forward(base, q)
+    moved = ((pos1 - pos0).norm(dim=-1) > 1e-6)[0]
+    assert moved.nonzero().flatten().tolist() == [3, 4, 5]
+    # a rigid motion of the wrist moves every primitive rigidly
+    T = torch.eye(4)
+    T[:3, :3] = axis_angle_to_matrix(torch.tensor([0.2, -0.4, 0.3]))
+    T[:3, 3] = torch.tensor([0.1, 0.2, -0.3])
+    pos2, _ = kin.forward((T @ base[0])[None], torch.zeros(1, 1, 24))
+    assert torch.allclose(pos2[0], (T[:3, :3] @ pos0[0].T).T + T[:3, 3], atol=1e-5)
+    # differentiable w.r.t. joints and base
+    q = torch.full((1, 1, 24), 0.1, requires_grad=True)
+    p, r = kin.forward(base, q)
+    (p.sum() + r.sum()).backward()
+    assert torch.isfinite(q.grad).all() and q.grad.abs().sum() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,fixed_base,E", [("rh15", False, 1), ("rh25", True, 3), ("dual15", False, 2)])
+def test_device_fk_matches_torch_fk(tag, fixed_base, E):
+    from dexdeform_b200.engine import FusedSim
+    from dexdeform_b200.hand import DeviceFK, read_poses
+    t = tables(tag)
+    nh, ng = t.n_hands, len(t.geom_joint)
+    S = 40
+    scale = np.array([0.33 * 0.002] * 20 + ([0.0] * 6 if fixed_base else [0.01] * 3 + [0.015] * 3))
+    eng = FusedSim(E, 64, nh * ng, (32, 32, 32), 1 / 32, 1e-4, S)
+    fk = DeviceFK(t, scale)
+    g = torch.Generator().manual_seed(3)
+    kin = HandKinematics(t, "cuda")
+    base = torch.tensor(t.root_frame, dtype=torch.float32, device="cuda")[None].repeat(E, 1, 1, 1)
+    base[..., :3, :3] = axis_angle_to_matrix(torch.randn(E, nh, 3, generator=g).cuda() * 0.7) @ base[..., :3, :3]
+    q0 = (torch.rand(E, nh, 24, generator=g).cuda() * 0.3)
+    act = (torch.rand(E, nh, 26, generator=g).cuda() * 3 - 1.5)       # beyond [-1, 1]: exercises the clamp
+    nb_, nq_ = fk.run(eng, 0, S, base, q0, act, has_base_action=not fixed_base)
+    pos_d, rot_d = read_poses(eng, 1, S)
+    for e in range(E):
+        sc = torch.tensor(scale, dtype=torch.float32, device="cuda")
+        nbase = rigid_body_motion_hand(base[e], act[e, :, -6:] * sc[None, -6:], S) if not fixed_base else base[e][None].expand(S, -1, -1, -1)
+        a = (act[e, :, :20].clamp(-1, 1) * sc[None, :20])[:, kin.action_map]
+        nq = (q0[e][None] + a[None] * (torch.arange(S, device="cuda")[:, None, None] + 1)).clamp(kin.q_lower, kin.q_upper)
+        pos_t, rot_t = kin.forward(nbase, nq)
+        assert torch.allclose(pos_d[:, e], pos_t, atol=2e-6), (pos_d[:, e] - pos_t).abs().max()
+        sign = torch.sign((rot_d[:, e] * rot_t).sum(-1, keepdim=True))
+        assert torch.allclose(rot_d[:, e] * sign, rot_t, atol=5e-6), (rot_d[:, e] * sign - rot_t).abs().max()
+        assert torch.allclose(nb_[e], nbase[-1], atol=2e-6) and torch.allclose(nq_[e], nq[-1], atol=1e-7)
+    eng.close()
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/mpm/shapes.py"), reason="reference checkout not present")
+def test_shapes_reproduce_reference_particles_bit_for_bit():
+    """mpm/shapes.py imports open3d at module level only for its (unused) mesh sampler; with an empty stand-in module the
+    reference's own box / cylinder / sphere samplers run here and must produce the very same particles (seed 0)."""
+    import importlib.util
+    import sys
+    import types
+    from dexdeform_b200.shapes import Shapes
+    sys.modules.setdefault("open3d", types.ModuleType("open3d"))
+    spec = importlib.util.spec_from_file_location("ref_shapes", "/root/reference/mpm/shapes.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cfgs = [
+        [dict(shape="box", width="(0.09, 0.09, 0.09)", init_pos="(0.49, 0.22, 0.45)", n_particles=10000)],               # lift_box.yml
+        [dict(shape="cylinder", h=0.003, r=0.1, init_pos="(0.5, 0.38, 0.6)")],                                             # flip.yml
+        [dict(shape="sphere", radius=0.05, init_pos="(0.5, 0.2, 0.5)", n_particles=3000, E=4000.0, yield_stress=80.0),
+         dict(shape="box", width=0.05, init_pos="(0.3, 0.1, 0.3)", n_particles=500)],
+    ]
+    for cfg in cfgs:
+        a, b = ref.Shapes(cfg).get(), Shapes(cfg).get()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert (a[3] is None and b[3] is None) or np.array_equal(a[3], b[3])
+
+
+@pytest.mark.gpu
+def test_hand_simulator_step_and_gradmodel():
+    """HandSimulator built from the fixture tables (the MJCF files do not exist on the GPU box): lift_box-like scene, two env
+    steps forward-only with device FK, then a differentiable step through GradModel with gradients w.r.t. the action."""
+    from dexdeform_b200.hand import HandSimulator
+    from dexdeform_b200.torch_wrapper import GradModel
+    from dexdeform_b200.hand import HandEnv
+    t = tables("rh15")
+    nb = len(t.prim_type)
+    n = 4000
+    cfg = dict(n_particles=n, E=5e3, nu=0.2, yield_stress=50.0, ground_friction=0.3, quality=1, max_steps=90, gravity=(0.0, -2.0, 0.0), fixed_base=False)
+    sim = HandSimulator(nb, {"tables": t}, cfg=cfg)
+    assert sim.substeps == 40 and abs(sim.dt - 5e-5) < 1e-12 and sim.grid_dim == (64, 64, 64)
+    sim.init_bodies(t.prim_type.astype(np.float32), np.full(nb, 666.0, np.float32), np.full(nb, 0.9, np.float32), np.zeros(nb, np.float32), t.prim_size,
+                    action_scales=[()] * nb)
+    rng = np.random.default_rng(0)
+    x = ((rng.random((n, 3)) * 2 - 1) * 0.045 + np.array([0.49, 0.22, 0.45])).astype(np.float32)
+    root = HandEnv.get_root_matrix((0.5, 0.2, 0.3), (0.0, 0.0, np.pi))[None]
+    state = (x, np.zeros((n, 3), np.float32), np.tile(np.eye(3, dtype=np.float32)[None], (n, 1, 1)), np.zeros((n, 3, 3), np.float32), np.float32(root),
+             np.zeros((1, 24), np.float32))
+    sim.set_state(0, state)
+    st = sim.get_state(0)
+    assert len(st) == 4 + nb + 2 and st[-2].shape == (1, 4, 4) and st[-1].shape == (1, 24)
+    act = np.zeros((1, 26), np.float32)
+    act[0, :20] = 0.5
+    act[0, 21] = -0.5
+    sim.step(act)
+    sim.step(act)
+    x2 = sim.get_x(0)
+    assert np.isfinite(x2).all() and x2[:, 1].mean() < x[:, 1].mean()
+    assert float(sim.joint_rot[0][0, 3]) > 0.0                     # FFJ2 closed by the positive actuator command
+    assert float(sim.base_pose[0][0, 1, 3]) < 0.2                  # wrist translated down
+    # differentiable step
+    model = GradModel(sim, return_grid=())
+    model.zero_grad()
+    a = torch.tensor(act, device="cuda:0", requires_grad=True)
+    obs = model.get_obs(0, "cuda:0")
+    obs = model.forward(0, a, *obs)
+    loss = obs[0][:, 1].mean() + 0.1 * obs[0][:, 6:].mean()
+    loss.backward()
+    assert torch.isfinite(a.grad).all() and a.grad.abs().sum() > 0
