@@ -7,6 +7,7 @@
 // torch kernels per env step followed by a device->host->device copy per substep (mpm/simulator.py:553-559).
 #include "mpm_math.cuh"
 #include "../../include/dexdeform_mpm.h"
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -42,20 +43,23 @@ DD_DEV M3 quat_to_mat(float r, float i, float j, float k) {
   return m3(1 - s * (j * j + k * k), s * (i * j - k * r), s * (i * k + j * r), s * (i * j + k * r), 1 - s * (i * i + k * k), s * (j * k - i * r),
             s * (i * k - j * r), s * (j * k + i * r), 1 - s * (i * i + j * j));
 }
-// pytorch3d.transforms.matrix_to_quaternion: four candidates, the one with the largest |component| wins
-DD_DEV void mat_to_quat(const M3 &m, float q[4]) {
-  float a[4] = {1.f + m.a00 + m.a11 + m.a22, 1.f + m.a00 - m.a11 - m.a22, 1.f - m.a00 + m.a11 - m.a22, 1.f - m.a00 - m.a11 + m.a22};
+// pytorch3d.transforms.matrix_to_quaternion: four candidates, the one with the largest |component| wins.  Written with
+// scalars only: local arrays here shared stack slots with the caller's joint-angle array (ptxas 12.9) and corrupted it.
+DD_DEV float4 mat_to_quat(const M3 &m) {
+  float t0 = 1.f + m.a00 + m.a11 + m.a22, t1 = 1.f + m.a00 - m.a11 - m.a22, t2 = 1.f - m.a00 + m.a11 - m.a22, t3 = 1.f - m.a00 - m.a11 + m.a22;
+  float a0 = t0 > 0.f ? sqrtf(t0) : 0.f, a1 = t1 > 0.f ? sqrtf(t1) : 0.f, a2 = t2 > 0.f ? sqrtf(t2) : 0.f, a3 = t3 > 0.f ? sqrtf(t3) : 0.f;
   int best = 0;
-  float qa[4];
-  for (int c = 0; c < 4; ++c) qa[c] = a[c] > 0.f ? sqrtf(a[c]) : 0.f;
-  for (int c = 1; c < 4; ++c)
-    if (qa[c] > qa[best]) best = c;
-  float d = 2.f * fmaxf(qa[best], 0.1f);
-  if (best == 0) { q[0] = qa[0] * qa[0]; q[1] = m.a21 - m.a12; q[2] = m.a02 - m.a20; q[3] = m.a10 - m.a01; }
-  else if (best == 1) { q[0] = m.a21 - m.a12; q[1] = qa[1] * qa[1]; q[2] = m.a10 + m.a01; q[3] = m.a02 + m.a20; }
-  else if (best == 2) { q[0] = m.a02 - m.a20; q[1] = m.a10 + m.a01; q[2] = qa[2] * qa[2]; q[3] = m.a12 + m.a21; }
-  else { q[0] = m.a10 - m.a01; q[1] = m.a20 + m.a02; q[2] = m.a21 + m.a12; q[3] = qa[3] * qa[3]; }
-  for (int c = 0; c < 4; ++c) q[c] /= d;
+  float ab = a0;
+  if (a1 > ab) { best = 1; ab = a1; }
+  if (a2 > ab) { best = 2; ab = a2; }
+  if (a3 > ab) { best = 3; ab = a3; }
+  float inv = 1.f / (2.f * fmaxf(ab, 0.1f));
+  float4 q;
+  if (best == 0) q = make_float4(a0 * a0, m.a21 - m.a12, m.a02 - m.a20, m.a10 - m.a01);
+  else if (best == 1) q = make_float4(m.a21 - m.a12, a1 * a1, m.a10 + m.a01, m.a02 + m.a20);
+  else if (best == 2) q = make_float4(m.a02 - m.a20, m.a10 + m.a01, a2 * a2, m.a12 + m.a21);
+  else q = make_float4(m.a10 - m.a01, m.a20 + m.a02, m.a21 + m.a12, a3 * a3);
+  return make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
 }
 // pytorch3d axis_angle_to_matrix (via the quaternion, with its small-angle series)
 DD_DEV M3 axis_angle_to_mat(V3 aa) {
@@ -77,8 +81,8 @@ __global__ void k_hand_fk(dd_hand H, int S, int E, int nb, const float *__restri
     float ramp = (float)(t + 1) / (float)S;
     V3 tr = v3(act[20] * H.scale[20], act[21] * H.scale[21], act[22] * H.scale[22]) * ramp;
     V3 rv = v3(act[23] * H.scale[23], act[24] * H.scale[24], act[25] * H.scale[25]) * ramp;
-    float q0[4];
-    mat_to_quat(base.R, q0);
+    float4 qb = mat_to_quat(base.R);
+    float q0[4] = {qb.x, qb.y, qb.z, qb.w};
     float w = sqrtf(dot(rv, rv) + 1e-16f), sw = sinf(0.5f * w) / fminf(fmaxf(w, 1e-7f), 1e9f);
     float d0 = cosf(0.5f * w), d1 = rv.x * sw, d2 = rv.y * sw, d3 = rv.z * sw;
     float o0 = q0[0] * d0 - q0[1] * d1 - q0[2] * d2 - q0[3] * d3, o1 = q0[0] * d1 + q0[1] * d0 - q0[2] * d3 + q0[3] * d2;
@@ -101,7 +105,13 @@ __global__ void k_hand_fk(dd_hand H, int S, int E, int nb, const float *__restri
   // ---- chains (hand.py:366-376) and primitives (hand.py:377-381)
   Fr cur = base;
   size_t out0 = ((size_t)t * E + e) * nb + (size_t)h * H.n_geoms;
+#ifdef DD_FK_DEBUG
+  if (tid == 0) printf("base R %f %f %f | %f %f %f | %f %f %f p %f %f %f q0 %f q1 %f nops %d nmats %d ngeoms %d\n", base.R.a00, base.R.a01, base.R.a02, base.R.a10, base.R.a11, base.R.a12, base.R.a20, base.R.a21, base.R.a22, base.p.x, base.p.y, base.p.z, q[0], q[1], H.n_ops, H.n_mats, H.n_geoms);
+#endif
   for (int k = 0; k < H.n_ops; ++k) {
+#ifdef DD_FK_DEBUG
+    if (tid == 0 && k < 6) printf("op %d kind %d idx %d reset %d g0 %d g1 %d cur.p %f %f %f R00 %f R11 %f\n", k, H.op_kind[k], H.op_index[k], H.op_reset[k], H.op_g0[k], H.op_g1[k], cur.p.x, cur.p.y, cur.p.z, cur.R.a00, cur.R.a11);
+#endif
     if (H.op_reset[k]) cur = base;
     if (H.op_kind[k] == 0) {
       cur = fmul(cur, load_fr(H.mats + ((size_t)h * H.n_mats + H.op_index[k]) * 16));
@@ -111,14 +121,15 @@ __global__ void k_hand_fk(dd_hand H, int S, int E, int nb, const float *__restri
       const float *ax = H.joint_axis + ((size_t)h * 24 + j) * 3, *jp = H.joint_pos + ((size_t)h * 24 + j) * 3;
       T.R = axis_angle_to_mat(v3(ax[0] * q[j], ax[1] * q[j], ax[2] * q[j]));
       T.p = v3(jp[0], jp[1], jp[2]);
+#ifdef DD_FK_DEBUG
+      if (tid == 0 && k < 4) printf("  joint %d q %f ax %f %f %f jp %f %f %f T.R %f %f %f / %f %f %f\n", j, q[j], ax[0], ax[1], ax[2], jp[0], jp[1], jp[2], T.R.a00, T.R.a01, T.R.a02, T.R.a10, T.R.a11, T.R.a12);
+#endif
       cur = fmul(cur, T);
       for (int gi = H.op_g0[k]; gi < H.op_g1[k]; ++gi) {  // primitives carried by this joint (first visit only)
         int g = H.geom_order[gi];
         Fr G = fmul(cur, load_fr(H.geom_local + ((size_t)h * H.n_geoms + g) * 16));
-        float qq[4];
-        mat_to_quat(G.R, qq);
         pos_out[out0 + g] = make_float4(G.p.x, G.p.y, G.p.z, 0.f);
-        rot_out[out0 + g] = make_float4(qq[0], qq[1], qq[2], qq[3]);
+        rot_out[out0 + g] = mat_to_quat(G.R);
       }
     }
   }
