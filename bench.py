@@ -67,7 +67,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.samples:
@@ -157,6 +157,10 @@ def run_ours(args):
     e1.record(stream)
     barrier_sync(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
+    t_load = time.perf_counter()
+    while len(sampler.samples) < 6 and time.perf_counter() - t_load < 4.0:  # short timed region: keep the same load up (untimed) for more clock samples
+        step()
+    torch.cuda.synchronize()
     sampler.stop_flag = True
     launches = sim.launch_count() - launches0
     units = float(world) * n * S * args.steps
@@ -335,7 +339,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="D", choices=["D", "A", "B"])
