@@ -631,18 +631,23 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   float4 part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by the g2p adjoint
   g_x += v3(part.x, part.y, part.z);
   M3 gF_next = load_F(gin, kp.EN, p);
-  M3 g_r = (-2.f * mu) * mul(g_stress, c.nF);
-  M3 g_U = mul(g_r, c.Vm);
-  M3 g_V = mul_tn(g_r, c.U);
-  M3 g_nF = gF_next + (2.f * mu) * (mul_tn(g_stress, c.nF - c.r) + mul(g_stress, c.nF));
+  // Adjoint of stress -> (F_new, R = U V^T, J) and of the return map, then through the SVD (integrator.cu:541-620, 131-159),
+  // regrouped: with W = U^T g_R V and Y = U^T g_Fnew V every U/V gradient the reference materialises is
+  //   U^T gU = W + Y E,   V^T gV = W^T + Y^T E      (E = diag(exp eps), plastic branch only)
+  // and the three SVD-adjoint terms share one U ( . ) V^T sandwich.
+  M3 gsF = mul(g_stress, c.nF);
+  M3 g_nF = gF_next + (2.f * mu) * (mul_tn(g_stress, c.nF - c.r) + gsF);
+  M3 W = mul_tn(c.U, mul((-2.f * mu) * gsF, c.Vm));
   float g_J = ((2 * c.J - 1) * lam) * trace(g_stress);
   V3 g_sig = vzero();
   M3 G = mzero();  // dL/dF~ accumulated directly
+  M3 A = W, B = transpose(W);  // U^T gU and V^T gV
   if (c.pl.plastic) {
     const Plastic &pl = c.pl;
-    g_U += mul_diag(mul(g_nF, c.Vm), pl.ee);
-    g_V += mul_diag(mul_tn(g_nF, c.U), pl.ee);
-    V3 Fpart = diag(mul(mul_tn(c.U, g_nF), c.Vm));
+    M3 Y = mul_tn(c.U, mul(g_nF, c.Vm));
+    A += mul_diag(Y, pl.ee);
+    B += mul_diag(transpose(Y), pl.ee);
+    V3 Fpart = diag(Y);
     V3 Jpart = v3(g_J * pl.ee.y * pl.ee.z, g_J * pl.ee.x * pl.ee.z, g_J * pl.ee.x * pl.ee.y);
     V3 g_eps = pl.ee * (Jpart + Fpart);
     V3 g_eh = (-pl.dg / pl.ehn) * g_eps;
@@ -657,7 +662,14 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
     g_sig += v3(g_J * c.sigma.y * c.sigma.z, g_J * c.sigma.x * c.sigma.z, g_J * c.sigma.x * c.sigma.y);
     G = g_nF;
   }
-  G += svd_adj(c.U, c.sigma, c.Vm, g_U, g_sig, g_V);
+  {
+    V3 sg = c.sigma;
+    float d10 = (sg.y - sg.x) * (sg.y + sg.x), d20 = (sg.z - sg.x) * (sg.z + sg.x), d21 = (sg.z - sg.y) * (sg.z + sg.y);
+    M3 K = m3(0.f, 1.f / clamp_eps(d10), 1.f / clamp_eps(d20), 1.f / clamp_eps(-d10), 0.f, 1.f / clamp_eps(d21), 1.f / clamp_eps(-d20), 1.f / clamp_eps(-d21), 0.f);
+    // inner = (K o (A - A^T)) Sigma + Sigma (K o (B - B^T)) + diag(g_sigma)
+    M3 inner = mul_diag(hadamard(K, A - transpose(A)), sg) + diag_mul(sg, hadamard(K, B - transpose(B))) + mdiag(g_sig);
+    G += mul_nt(mul(c.U, inner), c.Vm);
+  }
   g_C += kp.dt * mul_nt(G, F);
   M3 g_F = mul_tn(mdiag(1.f) + kp.dt * s.C, G);
   store_xvc(gout, kp.EN, p, g_x, g_v, g_C);
