@@ -554,22 +554,44 @@ __global__ void __launch_bounds__(kT) k_grid_grad(KP kp, float4 *__restrict__ gr
 constexpr int kTileN = 512;          // 8^3 nodes
 constexpr int kTileWarps = 4;        // chunks per thread block
 DD_DEV int round_off(int j, int L, int q) { return j * (L - 1) + min(j, q); }
-struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, L, q; };
+struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, L, q, bx, by, bz; };
 DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
   ChunkGeom c;
   int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
   c.env = ch.x / NB;
   int b = ch.x - c.env * NB;
-  c.ox = (b / (nby * nbz)) * 4 - 1; c.oy = ((b / nbz) % nby) * 4 - 1; c.oz = (b % nbz) * 4 - 1;
+  c.bx = b / (nby * nbz); c.by = (b / nbz) % nby; c.bz = b % nbz;
+  c.ox = c.bx * 4 - 1; c.oy = c.by * 4 - 1; c.oz = c.bz * 4 - 1;
   c.start = ch.y; c.cnt = ch.z;
   c.R = (c.cnt + 31) >> 5;
   c.L = (c.cnt + c.R - 1) / c.R;
   c.q = c.cnt - c.R * (c.L - 1);
   return c;
 }
-// a particle whose stencil leaves the 3x3x3-brick neighbourhood of its home brick has out-run the active region
-DD_DEV void check_drift(int tx, int ty, int tz, int *overflow) {
-  if (tx < -3 || tx > 9 || ty < -3 || ty > 9 || tz < -3 || tz > 9) atomicOr(overflow, 1);
+// Which of the 27 bricks around the chunk's home brick are active (bit (dx+1)*9 + (dy+1)*3 + (dz+1)); whole warp calls.
+DD_DEV unsigned chunk_active_mask(const char *__restrict__ active_flag, const ChunkGeom &cg, const KP &kp, int lane) {
+  int nbx = kp.gx >> 2, nby = kp.gy >> 2, nbz = kp.gz >> 2;
+  bool on = false;
+  if (lane < 27) {
+    int x = cg.bx + lane / 9 - 1, y = cg.by + (lane / 3) % 3 - 1, z = cg.bz + lane % 3 - 1;
+    if ((unsigned)x < (unsigned)nbx && (unsigned)y < (unsigned)nby && (unsigned)z < (unsigned)nbz)
+      on = active_flag[(size_t)cg.env * nbx * nby * nbz + (x * nby + y) * nbz + z] != 0;
+  }
+  return __ballot_sync(0xffffffffu, on);
+}
+// The active region is exactly the set of bricks some particle's stencil (+1 node of slack) touched at the last sort.  A
+// particle whose stencil now reaches a brick outside it has out-run the region: its mass would land on nodes no grid
+// kernel processes, so the step is flagged invalid (reported at the next sync).  (tx,ty,tz) = stencil base in tile coordinates.
+DD_DEV void check_active(unsigned amask, int tx, int ty, int tz, int *overflow) {
+  int ax = (tx + 3) >> 2, bx = (tx + 5) >> 2, ay = (ty + 3) >> 2, by = (ty + 5) >> 2, az = (tz + 3) >> 2, bz = (tz + 5) >> 2;
+  bool ok = ax >= 0 && bx <= 2 && ay >= 0 && by <= 2 && az >= 0 && bz <= 2;
+  if (ok) {
+    unsigned need = 0u;
+    need |= 1u << (ax * 9 + ay * 3 + az); need |= 1u << (ax * 9 + ay * 3 + bz); need |= 1u << (ax * 9 + by * 3 + az); need |= 1u << (ax * 9 + by * 3 + bz);
+    need |= 1u << (bx * 9 + ay * 3 + az); need |= 1u << (bx * 9 + ay * 3 + bz); need |= 1u << (bx * 9 + by * 3 + az); need |= 1u << (bx * 9 + by * 3 + bz);
+    ok = (need & ~amask) == 0u;
+  }
+  if (!ok) atomicOr(overflow, 1);
 }
 
 // TILE = true: node adjoints are read from a swizzled shared-memory tile at (tx,ty,tz); otherwise from the dense grid
@@ -596,7 +618,6 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   const float4 *gg = ggrid + (size_t)(p / kp.N) * kp.G + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
   int tx = st.bx - ox, ty = st.by - oy, tz = st.bz - oz;
   bool in_tile = TILE && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
-  if (TILE && !in_tile) check_drift(tx, ty, tz, overflow);
   M3 T = mzero();
   V3 Sv = vzero(), g_x = vzero();
 #pragma unroll
@@ -697,7 +718,7 @@ __global__ void __launch_bounds__(kT, DD_LB_P2G_GRAD) k_p2g_grad(KP kp, const in
 template <int SVD, bool WRITE_F>
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                  float *__restrict__ nxt, const float4 *__restrict__ mat0,
-                                                                 const float *__restrict__ yield, float4 *__restrict__ grid, int *overflow) {
+                                                                 const float *__restrict__ yield, float4 *__restrict__ grid, const char *__restrict__ active_flag, int *overflow) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int ci = blockIdx.x * kTileWarps + warp;
@@ -705,6 +726,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
   float4 *tile = dd_smem + warp * kTileN;
   unsigned tbase = smem_u32(tile);
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   float4 *g = grid + (size_t)cg.env * kp.G;
@@ -725,6 +747,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     V3 base = m * s.v - (c0 * st.fx.x + c1 * st.fx.y + c2 * st.fx.z);  // value at node offset (0,0,0); +c_a per step along axis a
     float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
     int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
+    if (act) check_active(amask, tx, ty, tz, overflow);
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -754,7 +777,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     }
     if (act && !in_tile) {  // drifted more than one cell since the last sort: straight to the grid
       tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
-      check_drift(tx, ty, tz, overflow);
 #pragma unroll 1
       for (int i = 0; i < 3; ++i)
 #pragma unroll 1
@@ -783,7 +805,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout,
-                                                                      float4 *__restrict__ ggrid_v, int *overflow) {
+                                                                      float4 *__restrict__ ggrid_v, const char *__restrict__ active_flag, int *overflow) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int ci = blockIdx.x * kTileWarps + warp;
@@ -791,6 +813,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
   float4 *tv = dd_smem + warp * (2 * kTileN), *tg = tv + kTileN;
   unsigned vbase = smem_u32(tv), gbase = smem_u32(tg);
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   size_t goff = (size_t)cg.env * kp.G;
   for (int n = lane; n < kTileN; n += 32) {
     int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
@@ -824,6 +847,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     V3 H0 = v3(g.C.a00, g.C.a10, g.C.a20) * s4, H1 = v3(g.C.a01, g.C.a11, g.C.a21) * s4, H2 = v3(g.C.a02, g.C.a12, g.C.a22) * s4;
     V3 h0 = gnv - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
     int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
+    if (act) check_active(amask, tx, ty, tz, overflow);
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -862,7 +886,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     }
     if (act && !in_tile) {
       tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
-      check_drift(tx, ty, tz, overflow);
 #pragma unroll 1
       for (int i = 0; i < 3; ++i)
 #pragma unroll 1
@@ -946,7 +969,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
     float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
     int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
     bool in_tile = (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
-    if (!in_tile) check_drift(tx, ty, tz, overflow);
     const float4 *g = genv + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
     V3 nv = vzero();
     M3 nC = mzero();
@@ -1114,7 +1136,7 @@ __global__ void k_pack_mat(int EN, const int *__restrict__ perm, const float *__
   yield[i] = mly[3 * s + 2];
 }
 // sort key of a particle: environment-major, then 4x4x4-cell brick (x-major like the grid), then cell inside the brick
-__global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__restrict__ keys, int *__restrict__ idx) {
+__global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__restrict__ keys, int *__restrict__ idx, char *__restrict__ active_flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kp.EN) return;
   V3 x = ld_v3(x_aos, i);
@@ -1125,6 +1147,15 @@ __global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__
   unsigned cell = ((cx & 3) << 4) | ((cy & 3) << 2) | (cz & 3);
   keys[i] = (unsigned)(i / kp.N) * (unsigned)kp.G + (brick << 6 | cell);
   idx[i] = i;
+  if (active_flag) {  // active region = bricks reached by the stencil [base, base+2] padded by one node on each side
+    int nbx = kp.gx >> 2, NB = nbx * nby * nbz, env = i / kp.N;
+    int b0x = clampi(cx, 0, kp.gx - 3), b0y = clampi(cy, 0, kp.gy - 3), b0z = clampi(cz, 0, kp.gz - 3);
+    int lx = max(b0x - 1, 0) >> 2, hx = min((b0x + 3) >> 2, nbx - 1), ly = max(b0y - 1, 0) >> 2, hy = min((b0y + 3) >> 2, nby - 1),
+        lz = max(b0z - 1, 0) >> 2, hz = min((b0z + 3) >> 2, nbz - 1);
+    for (int x_ = lx; x_ <= hx; ++x_)
+      for (int y_ = ly; y_ <= hy; ++y_)
+        for (int z_ = lz; z_ <= hz; ++z_) active_flag[(size_t)env * NB + (x_ * nby + y_) * nbz + z_] = 1;
+  }
 }
 
 __global__ void k_mark_heads(int EN, const unsigned *__restrict__ keys, char *__restrict__ flags) {
@@ -1132,11 +1163,11 @@ __global__ void k_mark_heads(int EN, const unsigned *__restrict__ keys, char *__
   if (i >= EN) return;
   flags[i] = (i == 0) || (keys[i] >> 6) != (keys[i - 1] >> 6);
 }
-// one thread per occupied brick: split its particles into `nsub` chunks and mark its 3x3x3 neighbourhood active.
+// one thread per occupied brick: split its particles into `nsub` chunks.
 // Chunk c takes the cell-sorted ranks r = c (mod nsub) of the brick -- a thinned copy of the whole brick, so that the
 // lanes of a round still sit in different cells -- and owns the storage range after chunks 0..c-1.
 __global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_pos, const unsigned *__restrict__ keys, int chunk_max,
-                              int4 *__restrict__ chunks, int4 *__restrict__ chunk_src, int *__restrict__ counters, char *__restrict__ active_flag) {
+                              int4 *__restrict__ chunks, int4 *__restrict__ chunk_src, int *__restrict__ counters) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nbricks) return;
   int start = head_pos[k], end = k + 1 < nbricks ? head_pos[k + 1] : kp.EN, cnt = end - start;
@@ -1150,15 +1181,6 @@ __global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_p
     chunk_src[c0 + c] = make_int4(start, cnt, c, nsub);
     s += n_c;
   }
-  int nbx = kp.gx >> 2, nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = nbx * nby * nbz;
-  int env = brick / NB, b = brick - env * NB;
-  int bx = b / (nby * nbz), by = (b / nbz) % nby, bz = b % nbz;
-  for (int dx = -1; dx <= 1; ++dx)
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dz = -1; dz <= 1; ++dz) {
-        int x = bx + dx, y = by + dy, z = bz + dz;
-        if ((unsigned)x < (unsigned)nbx && (unsigned)y < (unsigned)nby && (unsigned)z < (unsigned)nbz) active_flag[env * NB + (x * nby + y) * nbz + z] = 1;
-      }
 }
 // storage order: every chunk round-major (see the tiled kernels); one warp per chunk
 __global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src, const int *__restrict__ perm_in,
@@ -1346,7 +1368,7 @@ void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk =
     int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
     // invariant: the scatter target of substep f is already zero on the active bricks (cleared by the previous grid
     // kernel, or by dd_sim_forward for the first substep of a range)
-    k_p2g_tile<SVD, true><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->counters + 3);
+    k_p2g_tile<SVD, true><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->active_flag, s->counters + 3);
     mark(mk, "p2g_tile (svd+return map+scatter)");
     float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
     k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
@@ -1371,10 +1393,10 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
     int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
     // invariant: ggrid_v is zero on the active bricks (k_grid_grad_b clears what it consumes)
     if (!s->grid_ckpt) {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
-      k_p2g_tile<SVD, false><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->counters + 3);
+      k_p2g_tile<SVD, false><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->active_flag, s->counters + 3);
       k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
-    k_g2p_grad_tile<<<ncb, 32 * kTileWarps, 2 * kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->counters + 3);
+    k_g2p_grad_tile<<<ncb, 32 * kTileWarps, 2 * kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3);
     mark(mk, "g2p_grad_tile");
     k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
@@ -1611,7 +1633,8 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
   DD_CUDA(cudaMemcpyAsync(sC, C, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
   if (s->cfg.sort_particles) {
     // cell-sorted particle order: environment, 4^3-cell brick, cell.  perm maps sorted -> original index.
-    k_sort_keys<<<nblk(EN), kT, 0, st>>>(s->kp, sx, s->keys, s->idx_alt);
+    if (s->cfg.tile_mode) DD_CUDA(cudaMemsetAsync(s->active_flag, 0, s->NBtot, st));
+    k_sort_keys<<<nblk(EN), kT, 0, st>>>(s->kp, sx, s->keys, s->idx_alt, s->cfg.tile_mode ? s->active_flag : nullptr);
     int bits = 1;
     while (bits < 32 && (1ull << bits) < (unsigned long long)s->kp.E * s->kp.G) ++bits;
     DD_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_tmp, s->cub_bytes, s->keys, s->keys_alt, s->idx_alt, s->perm, EN, 0, bits, st));
@@ -1621,11 +1644,10 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
       k_mark_heads<<<nblk(EN), kT, 0, st>>>(EN, s->keys_alt, s->head_flags);
       DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, s->counters + 2, EN, st));
       DD_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(int) * 2, st));
-      DD_CUDA(cudaMemsetAsync(s->active_flag, 0, s->NBtot, st));
       DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
       DD_CUDA(cudaStreamSynchronize(st));
       int nbricks = host[2];
-      k_make_chunks<<<nblk(nbricks), kT, 0, st>>>(kp, nbricks, s->head_pos, s->keys_alt, s->chunk_max, s->chunks, s->chunk_src, s->counters, s->active_flag);
+      k_make_chunks<<<nblk(nbricks), kT, 0, st>>>(kp, nbricks, s->head_pos, s->keys_alt, s->chunk_max, s->chunks, s->chunk_src, s->counters);
       DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->active_flag, s->active, s->counters + 1, s->NBtot, st));
       DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
       DD_CUDA(cudaStreamSynchronize(st));

@@ -168,11 +168,12 @@ def test_engine_error_reporting():
 
 def test_tiled_path_equals_dense_path_with_drift_and_dense_cells():
     """The shared-memory tile path (conflict serialisation, drift fallback to the grid) against the plain global-reduction
-    path on a scene built to stress it: 40 particles per cell (many same-cell lanes per round) moving 1.5 cells per substep
-    (so after the first substep most particles have left the tile they were sorted into)."""
+    path on a scene built to stress it: 40 particles per cell (many same-cell lanes per round) moving fast enough that
+    most of them change cell (and many leave the tile interior) within the two substeps."""
     S = 2
     sc = make_scene(4000, 32, box_center=(0.5, 0.4, 0.5), box_width=(0.14, 0.14, 0.14), steps=S, perturb=0.02, nb=4, seed=13, ground_friction=0.3)
-    sc["v"][:] = np.array([900.0, -600.0, 400.0], np.float32) * (1.0 + 0.01 * np.random.default_rng(0).normal(size=(4000, 3)).astype(np.float32))
+    # ~0.7 cells per substep: after two substeps most particles sit in another cell than the one they were sorted into
+    sc["v"][:] = np.array([450.0, -300.0, 200.0], np.float32) * (1.0 + 0.01 * np.random.default_rng(0).normal(size=(4000, 3)).astype(np.float32))
     seedg = loss_seed(4000, 5)
     outs = {}
     for tile in (False, True):
@@ -187,7 +188,7 @@ def test_tiled_path_equals_dense_path_with_drift_and_dense_cells():
 
 def test_tiled_path_reports_runaway_particles():
     sc = make_scene(512, 32, box_center=(0.3, 0.5, 0.5), box_width=(0.05, 0.05, 0.05), steps=3, nb=0, seed=3, ground_friction=0.0)
-    sc["v"][:] = np.array([3000.0, 0.0, 0.0], np.float32)  # 4.8 cells per substep
+    sc["v"][:] = np.array([3000.0, 0.0, 0.0], np.float32)  # 4.8 cells per substep: leaves the active region at once
     sim = FusedSim.from_scene(sc, max_steps=3, tile_mode=True)
     sim.forward(0, 3)
     with pytest.raises(EngineError, match="re-sort more often"):
