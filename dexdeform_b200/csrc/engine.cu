@@ -16,6 +16,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include <functional>
 #include <map>
@@ -99,19 +100,29 @@ DD_DEV void store_F(float *slot, int EN, int p, const M3 &F) {
 }
 DD_DEV float4 load_q(const float *slot, int EN, int p) { return ldg_stream(reinterpret_cast<const float4 *>(slot + (size_t)25 * EN) + p); }
 DD_DEV void store_q(float *slot, int EN, int p, float4 q) { reinterpret_cast<float4 *>(slot + (size_t)25 * EN)[p] = q; }
-// shared-memory access that the compiler may neither reorder nor merge (the tile updates of one warp rely on program order)
+// shared-memory access that the compiler may neither reorder nor merge (the tile updates of one warp rely on program order).
+// Volatile asm statements keep their mutual order; plain accesses to the tiles (fill, flush) are fenced by __syncwarp().
+#ifdef DD_TILE_MEMCLOBBER
+#define DD_TILE_CLOBBER : "memory"
+#else
+#define DD_TILE_CLOBBER
+#endif
 DD_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 DD_DEV float4 lds_v4(unsigned a) {
   float4 r;
-  asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
+  asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) DD_TILE_CLOBBER);
   return r;
 }
 DD_DEV void sts_v4_if(unsigned a, float4 v, bool pred) {
-  asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4}; }" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) : "memory");
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4}; }" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) DD_TILE_CLOBBER);
 }
-// tile slot of node (tx,ty,tz) in an 8^3 tile; the low bits are swizzled so that lanes in neighbouring cells do not pile up
-// on the same bank group
-DD_DEV int tile_slot(int tx, int ty, int tz) { return tx << 6 | ty << 3 | (tz ^ (((ty & 1) << 2 | (ty & 2) >> 1) ^ ((tx & 1) << 1) ^ ((tx & 2) << 1))); }
+// Tile slot of node (tx,ty,tz) in an 8^3 tile.  A 128-bit shared-memory access is served one quarter-warp (8 lanes) at a
+// time and is conflict-free when those 8 lanes hit 8 different 16-byte bank groups; the group of a node is the low three
+// bits of its slot, (tz + 4 ty + 2 tx) mod 8.  The map is ADDITIVE, so moving every lane by the same stencil offset
+// (i,j,k) rotates all groups by the same amount: lanes whose home cells lie in different groups stay conflict-free for
+// all 27 nodes.  The particle order (k_sort_keys / k_interleave) puts group g's particles into lanes g, g+8, g+16, g+24.
+DD_DEV int tile_group(int tx, int ty, int tz) { return (tz + 4 * ty + 2 * tx) & 7; }
+DD_DEV int tile_slot(int tx, int ty, int tz) { return tx << 6 | ty << 3 | tile_group(tx, ty, tz); }
 DD_DEV void red_add_v4(float4 *addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -267,6 +278,32 @@ __global__ void __launch_bounds__(kT) k_grid(KP kp, const float4 *__restrict__ g
   grid_v[node] = make_float4(v.x, v.y, v.z, 0.f);
 }
 
+// APIC gather of g2p in separable form: per (i,j) row A = sum_k wz_k v_k and B = sum_k k wz_k v_k, then
+//   v' = sum w_ij A,   sum N k v = sum w_ij B,   sum N i v = sum (i w_ij) A,   sum N j v = sum (j w_ij) A
+// and C' = (4/dx) (those moments - v' (x) fx): ~9 instead of 16 floating-point instructions per node.
+template <class Fetch>
+DD_DEV void g2p_gather(Fetch fetch, const float (&wx)[3], const float (&wy)[3], const float (&wz)[3], V3 fx, float s4, V3 &nv, M3 &nC) {
+  V3 Cx = vzero(), Cy = vzero(), Cz = vzero();
+  nv = vzero();
+  const float kz1 = wz[1], kz2 = 2.f * wz[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float wij = wx[i] * wy[j];
+      float4 t0 = fetch(i, j, 0), t1 = fetch(i, j, 1), t2 = fetch(i, j, 2);
+      V3 A = v3(fmaf(wz[2], t2.x, fmaf(wz[1], t1.x, wz[0] * t0.x)), fmaf(wz[2], t2.y, fmaf(wz[1], t1.y, wz[0] * t0.y)), fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z)));
+      V3 B = v3(fmaf(kz2, t2.x, kz1 * t1.x), fmaf(kz2, t2.y, kz1 * t1.y), fmaf(kz2, t2.z, kz1 * t1.z));
+      nv.x = fmaf(wij, A.x, nv.x); nv.y = fmaf(wij, A.y, nv.y); nv.z = fmaf(wij, A.z, nv.z);
+      Cz.x = fmaf(wij, B.x, Cz.x); Cz.y = fmaf(wij, B.y, Cz.y); Cz.z = fmaf(wij, B.z, Cz.z);
+      if (i > 0) { float wi = wij * (float)i; Cx.x = fmaf(wi, A.x, Cx.x); Cx.y = fmaf(wi, A.y, Cx.y); Cx.z = fmaf(wi, A.z, Cx.z); }
+      if (j > 0) { float wj = wij * (float)j; Cy.x = fmaf(wj, A.x, Cy.x); Cy.y = fmaf(wj, A.y, Cy.y); Cy.z = fmaf(wj, A.z, Cy.z); }
+    }
+  }
+  V3 c0 = (Cx - nv * fx.x) * s4, c1 = (Cy - nv * fx.y) * s4, c2 = (Cz - nv * fx.z) * s4;
+  nC = m3(c0.x, c1.x, c2.x, c0.y, c1.y, c2.y, c0.z, c1.z, c2.z);
+}
+
 // g2p (integrator.cu:1059-1109).  v' = sum w v_n ; C' = 4/dx * sum (w v_n) (x) (offset - fx)
 __global__ void __launch_bounds__(kT) k_g2p(KP kp, const int *__restrict__ spos, const float *__restrict__ cur, float *__restrict__ nxt,
                                             const float4 *__restrict__ grid_v) {
@@ -278,28 +315,9 @@ __global__ void __launch_bounds__(kT) k_g2p(KP kp, const int *__restrict__ spos,
   Stencil st = make_stencil_safe(x, kp);
   const float4 *g = grid_v + (size_t)(p / kp.N) * kp.G + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
   float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
-  V3 nv = vzero();
-  M3 nC = mzero();
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    float di = (float)i - st.fx.x;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float wij = wx[i] * wy[j], dj = (float)j - st.fx.y;
-      const float4 *row = g + (i * kp.gy + j) * kp.gz;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float w = wij * wz[k], dk = (float)k - st.fx.z;
-        float4 t = __ldg(row + k);
-        V3 u = v3(t.x * w, t.y * w, t.z * w);
-        nv += u;
-        nC.a00 = fmaf(u.x, di, nC.a00); nC.a01 = fmaf(u.x, dj, nC.a01); nC.a02 = fmaf(u.x, dk, nC.a02);
-        nC.a10 = fmaf(u.y, di, nC.a10); nC.a11 = fmaf(u.y, dj, nC.a11); nC.a12 = fmaf(u.y, dk, nC.a12);
-        nC.a20 = fmaf(u.z, di, nC.a20); nC.a21 = fmaf(u.z, dj, nC.a21); nC.a22 = fmaf(u.z, dk, nC.a22);
-      }
-    }
-  }
-  nC = nC * (kp.inv_dx * 4.f);
+  V3 nv;
+  M3 nC;
+  g2p_gather([&](int i, int j, int k) { return __ldg(g + (i * kp.gy + j) * kp.gz + k); }, wx, wy, wz, st.fx, kp.inv_dx * 4.f, nv, nC);
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx;
   V3 t = x + nv * kp.dt;
@@ -553,8 +571,9 @@ __global__ void __launch_bounds__(kT) k_grid_grad(KP kp, float4 *__restrict__ gr
 //   dL/dx += sum gradN (m g_m + g_mv . (m v + A dpos))
 constexpr int kTileN = 512;          // 8^3 nodes
 constexpr int kTileWarps = 4;        // chunks per thread block
-DD_DEV int round_off(int j, int L, int q) { return j * (L - 1) + min(j, q); }
-struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, L, q, bx, by, bz; };
+// a chunk is stored as R rows of 32 particles (the last row holds the remaining `last`); row j starts at start + 32 j
+struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, last, bx, by, bz; };
+DD_DEV int row_lanes(const ChunkGeom &c, int j) { return j < c.R - 1 ? 32 : c.last; }
 DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
   ChunkGeom c;
   int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
@@ -564,8 +583,7 @@ DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
   c.ox = c.bx * 4 - 1; c.oy = c.by * 4 - 1; c.oz = c.bz * 4 - 1;
   c.start = ch.y; c.cnt = ch.z;
   c.R = (c.cnt + 31) >> 5;
-  c.L = (c.cnt + c.R - 1) / c.R;
-  c.q = c.cnt - c.R * (c.L - 1);
+  c.last = c.cnt - 32 * (c.R - 1);
   return c;
 }
 // Which of the 27 bricks around the chunk's home brick are active (bit (dx+1)*9 + (dy+1)*3 + (dz+1)); whole warp calls.
@@ -578,6 +596,28 @@ DD_DEV unsigned chunk_active_mask(const char *__restrict__ active_flag, const Ch
       on = active_flag[(size_t)cg.env * nbx * nby * nbz + (x * nby + y) * nbz + z] != 0;
   }
   return __ballot_sync(0xffffffffu, on);
+}
+// L2 prefetch of the next storage row (32 consecutive particles) of `nplanes` float4 planes of a slot, starting at plane
+// `first`: a row of one plane is 512 contiguous bytes, i.e. at most five 128-byte lines.  The tiled kernels run few warps
+// per SM, so without this every round starts with a full HBM round trip.
+DD_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+DD_DEV void prefetch_row4(const float *slot, int EN, int first, int nplanes, int p0, int lane) {
+  for (int t = lane; t < 5 * nplanes; t += 32) {
+    int k = t / 5, l = t - 5 * k;
+    prefetch_l2(reinterpret_cast<const char *>(plane4(slot, EN, first + k) + p0) + 128 * l);
+  }
+}
+DD_DEV void prefetch_row1(const float *base, int p0, int lane) { if (lane < 2) prefetch_l2(reinterpret_cast<const char *>(base + p0) + 128 * lane); }
+// Persistent chunk loop of the tiled kernels: every warp pulls chunk indices from a ticket counter until the list is
+// drained, so a launch never ends with a nearly empty last wave.  sched[0] = next ticket, sched[1] = warps that have
+// finished; the last warp to finish clears both for the next launch (launches are serialised on one stream).
+DD_DEV int next_chunk(int *sched, int lane) {
+  int c = 0;
+  if (lane == 0) c = atomicAdd(sched, 1);
+  return __shfl_sync(0xffffffffu, c, 0);
+}
+DD_DEV void chunks_done(int *sched, int lane) {
+  if (lane == 0 && atomicAdd(sched + 1, 1) == (int)(gridDim.x * (blockDim.x >> 5)) - 1) { sched[0] = 0; sched[1] = 0; }
 }
 // The active region is exactly the set of bricks some particle's stencil (+1 node of slack) touched at the last sort.  A
 // particle whose stencil now reaches a brick outside it has out-run the region: its mass would land on nodes no grid
@@ -618,34 +658,48 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   const float4 *gg = ggrid + (size_t)(p / kp.N) * kp.G + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
   int tx = st.bx - ox, ty = st.by - oy, tz = st.bz - oz;
   bool in_tile = TILE && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
-  M3 T = mzero();
-  V3 Sv = vzero(), g_x = vzero();
+  // Separable form of the 27-node gather.  With t = (g_mv, g_m) the node adjoints and val_n = base + c0 i + c1 j + c2 k:
+  //   per (i,j) row:  A = sum_k wz_k g_mv,  B = sum_k k wz_k g_mv,  M = sum_k wz_k g_m   (and E, EB, EM with dwz instead of wz)
+  //   sum_k wz_k (m g_m + g_mv . val) = m M + A . val_ij + B . c2          -> the x and y components of dL/dx
+  //   sum_k dwz_k ( ... )             = m EM + E . val_ij + EB . c2        -> the z component
+  //   Sv = sum w_ij A,  sum N k g_mv = sum w_ij B,  sum N i g_mv = sum (i w_ij) A,  sum N j g_mv = sum (j w_ij) A
+  // T = sum N g_mv (x) (offset - fx) dx follows from those four sums after the loop (~24 instead of ~33 instructions a node).
+  V3 Sv = vzero(), g_x = vzero(), Tx = vzero(), Ty = vzero(), Tz = vzero();
+  const float kz1 = wz[1], kz2 = 2.f * wz[2], ek1 = ez[1], ek2 = 2.f * ez[2];
+  auto gather = [&](auto fetch) {
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    float pi = ((float)i - st.fx.x) * kp.dx;
-    V3 vi = base + c0 * (float)i;
+    for (int i = 0; i < 3; ++i) {
+      V3 vi = base + c0 * (float)i;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float wij = wx[i] * wy[j], a1 = ex[i] * wy[j], a2 = wx[i] * ey[j], pj = ((float)j - st.fx.y) * kp.dx;
-      V3 vij = vi + c1 * (float)j;
-      const float4 *row = gg + (i * kp.gy + j) * kp.gz;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float pk = ((float)k - st.fx.z) * kp.dx;
-        float4 t = in_tile ? tile[tile_slot(tx + i, ty + j, tz + k)] : __ldg(row + k);
-        V3 val = vij + c2 * (float)k;
-        float N = wij * wz[k];
-        V3 u = v3(t.x * N, t.y * N, t.z * N);
-        T.a00 = fmaf(u.x, pi, T.a00); T.a01 = fmaf(u.x, pj, T.a01); T.a02 = fmaf(u.x, pk, T.a02);
-        T.a10 = fmaf(u.y, pi, T.a10); T.a11 = fmaf(u.y, pj, T.a11); T.a12 = fmaf(u.y, pk, T.a12);
-        T.a20 = fmaf(u.z, pi, T.a20); T.a21 = fmaf(u.z, pj, T.a21); T.a22 = fmaf(u.z, pk, T.a22);
-        Sv += u;
-        float sc = fmaf(m_p, t.w, t.x * val.x + t.y * val.y + t.z * val.z);
-        float tt = wz[k] * sc, uu = ez[k] * sc;
-        g_x.x = fmaf(a1, tt, g_x.x); g_x.y = fmaf(a2, tt, g_x.y); g_x.z = fmaf(wij, uu, g_x.z);
+      for (int j = 0; j < 3; ++j) {
+        float wij = wx[i] * wy[j], a1 = ex[i] * wy[j], a2 = wx[i] * ey[j];
+        V3 vij = vi + c1 * (float)j;
+        float4 t0 = fetch(i, j, 0), t1 = fetch(i, j, 1), t2 = fetch(i, j, 2);
+        V3 A = v3(fmaf(wz[2], t2.x, fmaf(wz[1], t1.x, wz[0] * t0.x)), fmaf(wz[2], t2.y, fmaf(wz[1], t1.y, wz[0] * t0.y)), fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z)));
+        V3 B = v3(fmaf(kz2, t2.x, kz1 * t1.x), fmaf(kz2, t2.y, kz1 * t1.y), fmaf(kz2, t2.z, kz1 * t1.z));
+        float M = fmaf(wz[2], t2.w, fmaf(wz[1], t1.w, wz[0] * t0.w));
+        V3 E = v3(fmaf(ez[2], t2.x, fmaf(ez[1], t1.x, ez[0] * t0.x)), fmaf(ez[2], t2.y, fmaf(ez[1], t1.y, ez[0] * t0.y)), fmaf(ez[2], t2.z, fmaf(ez[1], t1.z, ez[0] * t0.z)));
+        V3 EB = v3(fmaf(ek2, t2.x, ek1 * t1.x), fmaf(ek2, t2.y, ek1 * t1.y), fmaf(ek2, t2.z, ek1 * t1.z));
+        float EM = fmaf(ez[2], t2.w, fmaf(ez[1], t1.w, ez[0] * t0.w));
+        float S = fmaf(B.z, c2.z, fmaf(B.y, c2.y, fmaf(B.x, c2.x, fmaf(A.z, vij.z, fmaf(A.y, vij.y, fmaf(A.x, vij.x, m_p * M))))));
+        float SE = fmaf(EB.z, c2.z, fmaf(EB.y, c2.y, fmaf(EB.x, c2.x, fmaf(E.z, vij.z, fmaf(E.y, vij.y, fmaf(E.x, vij.x, m_p * EM))))));
+        g_x.x = fmaf(a1, S, g_x.x); g_x.y = fmaf(a2, S, g_x.y); g_x.z = fmaf(wij, SE, g_x.z);
+        Sv.x = fmaf(wij, A.x, Sv.x); Sv.y = fmaf(wij, A.y, Sv.y); Sv.z = fmaf(wij, A.z, Sv.z);
+        Tz.x = fmaf(wij, B.x, Tz.x); Tz.y = fmaf(wij, B.y, Tz.y); Tz.z = fmaf(wij, B.z, Tz.z);
+        if (i > 0) { float wi = wij * (float)i; Tx.x = fmaf(wi, A.x, Tx.x); Tx.y = fmaf(wi, A.y, Tx.y); Tx.z = fmaf(wi, A.z, Tx.z); }
+        if (j > 0) { float wj = wij * (float)j; Ty.x = fmaf(wj, A.x, Ty.x); Ty.y = fmaf(wj, A.y, Ty.y); Ty.z = fmaf(wj, A.z, Ty.z); }
       }
     }
+  };
+  if (in_tile) {
+    const float4 *trow = tile + (tx << 6 | ty << 3);
+    int g0 = tz + 4 * ty + 2 * tx;
+    gather([&](int i, int j, int k) { return trow[(i << 6 | j << 3) + ((g0 + 2 * i + 4 * j + k) & 7)]; });
+  } else {
+    gather([&](int i, int j, int k) { return __ldg(gg + (i * kp.gy + j) * kp.gz + k); });
   }
+  V3 t0 = (Tx - Sv * st.fx.x) * kp.dx, t1 = (Ty - Sv * st.fx.y) * kp.dx, t2 = (Tz - Sv * st.fx.z) * kp.dx;
+  M3 T = m3(t0.x, t1.x, t2.x, t0.y, t1.y, t2.y, t0.z, t1.z, t2.z);
   g_x -= mul_t(c.affine, Sv);
   M3 g_stress = c.scale * T, g_C = m_p * T;
   V3 g_v = m_p * Sv;
@@ -686,7 +740,9 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   {
     V3 sg = c.sigma;
     float d10 = (sg.y - sg.x) * (sg.y + sg.x), d20 = (sg.z - sg.x) * (sg.z + sg.x), d21 = (sg.z - sg.y) * (sg.z + sg.y);
-    M3 K = m3(0.f, 1.f / clamp_eps(d10), 1.f / clamp_eps(d20), 1.f / clamp_eps(-d10), 0.f, 1.f / clamp_eps(d21), 1.f / clamp_eps(-d20), 1.f / clamp_eps(-d21), 0.f);
+    float k10 = __fdividef(1.f, clamp_eps(d10)), k20 = __fdividef(1.f, clamp_eps(d20)), k21 = __fdividef(1.f, clamp_eps(d21));
+    float k01 = __fdividef(1.f, clamp_eps(-d10)), k02 = __fdividef(1.f, clamp_eps(-d20)), k12 = __fdividef(1.f, clamp_eps(-d21));
+    M3 K = m3(0.f, k10, k20, k01, 0.f, k21, k02, k12, 0.f);
     // inner = (K o (A - A^T)) Sigma + Sigma (K o (B - B^T)) + diag(g_sigma)
     M3 inner = mul_diag(hadamard(K, A - transpose(A)), sg) + diag_mul(sg, hadamard(K, B - transpose(B))) + mdiag(g_sig);
     G += mul_nt(mul(c.U, inner), c.Vm);
@@ -718,21 +774,30 @@ __global__ void __launch_bounds__(kT, DD_LB_P2G_GRAD) k_p2g_grad(KP kp, const in
 template <int SVD, bool WRITE_F>
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                  float *__restrict__ nxt, const float4 *__restrict__ mat0,
-                                                                 const float *__restrict__ yield, float4 *__restrict__ grid, const char *__restrict__ active_flag, int *overflow) {
+                                                                 const float *__restrict__ yield, float4 *__restrict__ grid, const char *__restrict__ active_flag, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int ci = blockIdx.x * kTileWarps + warp;
-  if (ci >= nchunks) return;
   float4 *tile = dd_smem + warp * kTileN;
   unsigned tbase = smem_u32(tile);
-  ChunkGeom cg = chunk_geom(chunks[ci], kp);
-  unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
+  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   float4 *g = grid + (size_t)cg.env * kp.G;
   for (int j = 0; j < cg.R; ++j) {
-    bool act = lane < cg.L - (j >= cg.q ? 1 : 0);
-    int p = act ? cg.start + round_off(j, cg.L, cg.q) + lane : cg.start;  // idle lanes shadow a valid particle, contribute nothing
+    bool act = lane < row_lanes(cg, j);
+    int p = act ? cg.start + 32 * j + lane : cg.start;  // idle lanes shadow a valid particle, contribute nothing
+#ifndef DD_NO_PREFETCH
+    if (j + 1 < cg.R) {
+      int pn = cg.start + 32 * (j + 1);
+      prefetch_row4(cur, kp.EN, 0, 6, pn, lane);                       // x, v, C, 8 of F
+      prefetch_row1(cur + (size_t)24 * kp.EN, pn, lane);               // F22
+      prefetch_row4(cur + (size_t)25 * kp.EN, kp.EN, 0, 1, pn, lane);  // warm-start quaternion
+      prefetch_row4(reinterpret_cast<const float *>(mat0), kp.EN, 0, 1, pn, lane);
+      prefetch_row1(yield, pn, lane);
+    }
+#endif
     XVC s = load_xvc(cur, kp.EN, p);
     M3 F = load_F(cur, kp.EN, p);
     float4 m0 = __ldg(mat0 + p);
@@ -790,13 +855,20 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     }
   }
   __syncwarp();
-  for (int n = lane; n < kTileN; n += 32) {
+  for (int n = lane; n < kTileN; n += 32) {  // flush, and leave the tile zeroed for the next chunk
     int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
-    float4 t = tile[tile_slot(txx, tyy, tzz)];
+    float4 *tp = tile + tile_slot(txx, tyy, tzz);
+    float4 t = *tp;
     int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
-    if ((t.w != 0.f || t.x != 0.f || t.y != 0.f || t.z != 0.f) && (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
-      red_add_v4(g + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, t.w);
+    if (t.w != 0.f || t.x != 0.f || t.y != 0.f || t.z != 0.f) {
+      *tp = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
+        red_add_v4(g + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, t.w);
+    }
   }
+  __syncwarp();
+  }
+  chunks_done(sched, lane);
 }
 
 // g2p_grad on tiles (integrator.cu:1527-1614): grid velocities are gathered from a tile copy, their adjoint is scattered
@@ -805,13 +877,14 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout,
-                                                                      float4 *__restrict__ ggrid_v, const char *__restrict__ active_flag, int *overflow) {
+                                                                      float4 *__restrict__ ggrid_v, const char *__restrict__ active_flag, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int ci = blockIdx.x * kTileWarps + warp;
-  if (ci >= nchunks) return;
   float4 *tv = dd_smem + warp * (2 * kTileN), *tg = tv + kTileN;
   unsigned vbase = smem_u32(tv), gbase = smem_u32(tg);
+  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+  float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
+  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   size_t goff = (size_t)cg.env * kp.G;
@@ -824,11 +897,17 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     tg[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncwarp();
-  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
-  float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
   for (int j = 0; j < cg.R; ++j) {
-    bool act = lane < cg.L - (j >= cg.q ? 1 : 0);
-    int p = act ? cg.start + round_off(j, cg.L, cg.q) + lane : cg.start;
+    bool act = lane < row_lanes(cg, j);
+    int p = act ? cg.start + 32 * j + lane : cg.start;
+#ifndef DD_NO_PREFETCH
+    if (j + 1 < cg.R) {
+      int pn = cg.start + 32 * (j + 1);
+      prefetch_row4(cur, kp.EN, 0, 1, pn, lane);
+      prefetch_row4(nxt, kp.EN, 0, 2, pn, lane);
+      prefetch_row4(gin, kp.EN, 0, 4, pn, lane);
+    }
+#endif
     float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
     V3 x = v3(a.x, a.y, a.z);
     float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
@@ -855,9 +934,11 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     int maxr = __reduce_max_sync(0xffffffffu, rank);
     if (!in_tile) { tx = ty = tz = 0; }
     V3 Vw = vzero(), gxs = vzero();
-    for (int r = 0; r <= maxr; ++r) {
-      bool mine = in_tile && rank == r;
-      V3 Vw_r = vzero(), gx_r = vzero();
+    const float4 *tvrow = tv + (tx << 6 | ty << 3);
+    unsigned growb = gbase + 16u * (unsigned)(tx << 6 | ty << 3);
+    int g0 = tz + 4 * ty + 2 * tx;
+    {  // first pass: the gather half (read-only tile, every lane) and the scatter of the lanes that own their cell this round
+      bool mine = in_tile && rank == 0;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         V3 hi_ = h0 + H0 * (float)i;
@@ -869,21 +950,42 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
           for (int k = 0; k < 3; ++k) {
             V3 h = hij + H2 * (float)k;
             float w = wij * wz[k];
-            int slot = tile_slot(tx + i, ty + jj, tz + k);
-            float4 t = lds_v4(vbase + 16u * (unsigned)slot);
-            unsigned ga = gbase + 16u * (unsigned)slot;
+            int so = (i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7);
+            float4 t = tvrow[so];
+            unsigned ga = growb + 16u * (unsigned)so;
             float4 o = lds_v4(ga);
             o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
             sts_v4_if(ga, o, mine);
-            Vw_r.x = fmaf(w, t.x, Vw_r.x); Vw_r.y = fmaf(w, t.y, Vw_r.y); Vw_r.z = fmaf(w, t.z, Vw_r.z);
+            Vw.x = fmaf(w, t.x, Vw.x); Vw.y = fmaf(w, t.y, Vw.y); Vw.z = fmaf(w, t.z, Vw.z);
             float qn = t.x * h.x + t.y * h.y + t.z * h.z;
             float tt = wz[k] * qn, uu = ez[k] * qn;
-            gx_r.x = fmaf(a1, tt, gx_r.x); gx_r.y = fmaf(a2, tt, gx_r.y); gx_r.z = fmaf(wij, uu, gx_r.z);
+            gxs.x = fmaf(a1, tt, gxs.x); gxs.y = fmaf(a2, tt, gxs.y); gxs.z = fmaf(wij, uu, gxs.z);
           }
         }
       }
-      if (mine) { Vw = Vw_r; gxs = gx_r; }
     }
+    for (int r = 1; r <= maxr; ++r) {  // lanes that shared a cell with a lower lane: scatter only
+      bool mine = in_tile && rank == r;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        V3 hi_ = h0 + H0 * (float)i;
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+          V3 hij = hi_ + H1 * (float)jj;
+          float wij = wx[i] * wy[jj];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            V3 h = hij + H2 * (float)k;
+            float w = wij * wz[k];
+            unsigned ga = growb + 16u * (unsigned)((i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7));
+            float4 o = lds_v4(ga);
+            o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
+            sts_v4_if(ga, o, mine);
+          }
+        }
+      }
+    }
+    if (!in_tile) { Vw = vzero(); gxs = vzero(); }
     if (act && !in_tile) {
       tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
 #pragma unroll 1
@@ -914,6 +1016,9 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     if ((t.x != 0.f || t.y != 0.f || t.z != 0.f) && (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
       red_add_v4(ggrid_v + goff + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, 0.f);
   }
+  __syncwarp();
+  }
+  chunks_done(sched, lane);
 }
 
 // load the 8^3 tile of a dense float4 grid into shared memory (swizzled slots); out-of-grid nodes read as zero
@@ -931,38 +1036,55 @@ template <int SVD>
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                                                                       const float *__restrict__ yield, const float4 *__restrict__ ggrid,
-                                                                      const float *__restrict__ gin, float *__restrict__ gout, int *overflow) {
+                                                                      const float *__restrict__ gin, float *__restrict__ gout, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int ci = blockIdx.x * kTileWarps + warp;
-  if (ci >= nchunks) return;
   float4 *tile = dd_smem + warp * kTileN;
-  ChunkGeom cg = chunk_geom(chunks[ci], kp);
-  load_tile(tile, ggrid + (size_t)cg.env * kp.G, cg, kp, lane);
-  __syncwarp();
-  for (int j = 0; j < cg.R; ++j) {
-    if (lane >= cg.L - (j >= cg.q ? 1 : 0)) continue;
-    p2g_grad_particle<SVD, true>(kp, cg.start + round_off(j, cg.L, cg.q) + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow);
+  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+    ChunkGeom cg = chunk_geom(chunks[ci], kp);
+    load_tile(tile, ggrid + (size_t)cg.env * kp.G, cg, kp, lane);
+    __syncwarp();
+    for (int j = 0; j < cg.R; ++j) {
+#ifndef DD_NO_PREFETCH
+      if (j + 1 < cg.R) {
+        int pn = cg.start + 32 * (j + 1);
+        prefetch_row4(cur, kp.EN, 0, 6, pn, lane);
+        prefetch_row1(cur + (size_t)24 * kp.EN, pn, lane);
+        prefetch_row4(nxt + (size_t)25 * kp.EN, kp.EN, 0, 1, pn, lane);
+        prefetch_row4(reinterpret_cast<const float *>(mat0), kp.EN, 0, 1, pn, lane);
+        prefetch_row1(yield, pn, lane);
+        prefetch_row4(gin, kp.EN, 0, 6, pn, lane);
+        prefetch_row1(gin + (size_t)24 * kp.EN, pn, lane);
+        prefetch_row4(gout, kp.EN, 0, 1, pn, lane);
+      }
+#endif
+      if (lane >= row_lanes(cg, j)) continue;
+      p2g_grad_particle<SVD, true>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow);
+    }
+    __syncwarp();
   }
+  chunks_done(sched, lane);
 }
 
 // g2p on tiles: the 27 node velocities come from a shared-memory copy of the brick's neighbourhood
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
-                                                                 float *__restrict__ nxt, const float4 *__restrict__ grid_v, int *overflow) {
+                                                                 float *__restrict__ nxt, const float4 *__restrict__ grid_v, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int ci = blockIdx.x * kTileWarps + warp;
-  if (ci >= nchunks) return;
   float4 *tile = dd_smem + warp * kTileN;
+  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+  float lo = kp.gh * kp.dx;
+  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   const float4 *genv = grid_v + (size_t)cg.env * kp.G;
   load_tile(tile, genv, cg, kp, lane);
   __syncwarp();
-  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
-  float lo = kp.gh * kp.dx;
   for (int j = 0; j < cg.R; ++j) {
-    if (lane >= cg.L - (j >= cg.q ? 1 : 0)) continue;
-    int p = cg.start + round_off(j, cg.L, cg.q) + lane;
+#ifndef DD_NO_PREFETCH
+    if (j + 1 < cg.R) prefetch_row4(cur, kp.EN, 0, 1, cg.start + 32 * (j + 1), lane);
+#endif
+    if (lane >= row_lanes(cg, j)) continue;
+    int p = cg.start + 32 * j + lane;
     float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
     V3 x = v3(a.x, a.y, a.z);
     Stencil st = make_stencil_safe(x, kp);
@@ -970,30 +1092,21 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
     int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
     bool in_tile = (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
     const float4 *g = genv + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
-    V3 nv = vzero();
-    M3 nC = mzero();
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      float di = (float)i - st.fx.x;
-#pragma unroll
-      for (int jj = 0; jj < 3; ++jj) {
-        float wij = wx[i] * wy[jj], dj = (float)jj - st.fx.y;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float w = wij * wz[k], dk = (float)k - st.fx.z;
-          float4 t = in_tile ? tile[tile_slot(tx + i, ty + jj, tz + k)] : __ldg(g + (i * kp.gy + jj) * kp.gz + k);
-          V3 u = v3(t.x * w, t.y * w, t.z * w);
-          nv += u;
-          nC.a00 = fmaf(u.x, di, nC.a00); nC.a01 = fmaf(u.x, dj, nC.a01); nC.a02 = fmaf(u.x, dk, nC.a02);
-          nC.a10 = fmaf(u.y, di, nC.a10); nC.a11 = fmaf(u.y, dj, nC.a11); nC.a12 = fmaf(u.y, dk, nC.a12);
-          nC.a20 = fmaf(u.z, di, nC.a20); nC.a21 = fmaf(u.z, dj, nC.a21); nC.a22 = fmaf(u.z, dk, nC.a22);
-        }
-      }
+    V3 nv;
+    M3 nC;
+    if (in_tile) {
+      const float4 *trow = tile + (tx << 6 | ty << 3);
+      int g0 = tz + 4 * ty + 2 * tx;
+      g2p_gather([&](int i, int jj, int k) { return trow[(i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7)]; }, wx, wy, wz, st.fx, kp.inv_dx * 4.f, nv, nC);
+    } else {
+      g2p_gather([&](int i, int jj, int k) { return __ldg(g + (i * kp.gy + jj) * kp.gz + k); }, wx, wy, wz, st.fx, kp.inv_dx * 4.f, nv, nC);
     }
-    nC = nC * (kp.inv_dx * 4.f);
     V3 t = x + nv * kp.dt;
     store_xvc(nxt, kp.EN, p, v3(fmaxf(fminf(t.x, hi.x), lo), fmaxf(fminf(t.y, hi.y), lo), fmaxf(fminf(t.z, hi.z), lo)), nv, nC);
   }
+  __syncwarp();
+  }
+  chunks_done(sched, lane);
 }
 
 // ---- grid kernels restricted to the active bricks (3x3x3-brick neighbourhood of every occupied brick) -----------------
@@ -1144,7 +1257,9 @@ __global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__
       cz = clampi((int)floorf(x.z * kp.inv_dx - 0.5f), 0, kp.gz - 1);
   int nby = (kp.gy + 3) >> 2, nbz = (kp.gz + 3) >> 2;
   unsigned brick = ((cx >> 2) * nby + (cy >> 2)) * nbz + (cz >> 2);
-  unsigned cell = ((cx & 3) << 4) | ((cy & 3) << 2) | (cz & 3);
+  // within the brick: bank group of the home cell (tile coordinates = local + 1) first, then the 8 cells of that group
+  int lx = cx & 3, ly = cy & 3, lz = cz & 3;
+  unsigned cell = (unsigned)tile_group(lx + 1, ly + 1, lz + 1) << 3 | (unsigned)(lx << 1 | ly >> 1);
   keys[i] = (unsigned)(i / kp.N) * (unsigned)kp.G + (brick << 6 | cell);
   idx[i] = i;
   if (active_flag) {  // active region = bricks reached by the stencil [base, base+2] padded by one node on each side
@@ -1182,18 +1297,73 @@ __global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_p
     s += n_c;
   }
 }
-// storage order: every chunk round-major (see the tiled kernels); one warp per chunk
-__global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src, const int *__restrict__ perm_in,
-                             int *__restrict__ perm_out, int *__restrict__ spos) {
+// Storage order: every chunk is an R-row x 32-column table stored row-major; a warp processes one row (round) at a time,
+// lane l = column l.  Columns l with l mod 8 = g are filled, in cell order, with the chunk's particles whose home cell
+// lies in bank group g (see tile_slot), so the eight lanes of a quarter-warp sit in eight different groups and the tile
+// accesses of a round are free of bank conflicts; the four columns of a group take consecutive quarters of the group's
+// cell-sorted list, so the lanes of a round also sit in different cells (no read-modify-write collisions).  Groups are
+// not equally populated: what does not fit into a group's own columns spills into the free slots of the others (a few
+// percent of the particles, costing at most one extra wavefront where they sit).  One warp per chunk.
+__global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src, const unsigned *__restrict__ keys_sorted,
+                             const int *__restrict__ perm_in, int *__restrict__ perm_out, int *__restrict__ spos) {
   int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (ci >= nchunks) return;
+  const unsigned full = 0xffffffffu;
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
-  int4 src = chunk_src[ci];  // (brick start, brick count, c, nsub)
-  for (int r = lane; r < cg.cnt; r += 32) {
-    int l = r / cg.R, j = r - l * cg.R;
-    int pos = cg.start + round_off(j, cg.L, cg.q) + l, from = src.x + src.z + r * src.w;
-    perm_out[pos] = perm_in[from];
-    spos[from] = pos;  // cell-sorted rank -> storage position, for the flat gather kernels
+  int4 src = chunk_src[ci];  // (brick start, brick count, c, nsub): item r of the chunk is sorted rank src.x + src.z + r * src.w
+  int cnt = cg.cnt, R = cg.R;
+  // first item of every group (lanes 0..7; lane 8 holds cnt)
+  int gs = cnt;
+  if (lane < 8) {
+    int lo = 0, hi = cnt;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if ((int)((keys_sorted[src.x + src.z + mid * src.w] >> 3) & 7u) >= lane) hi = mid; else lo = mid + 1;
+    }
+    gs = lo;
+  }
+  int g_cnt = __shfl_down_sync(full, gs, 1) - gs;                        // valid on lanes 0..7
+  int cap = lane < cg.last ? R : R - 1;                                  // capacity of column `lane`
+  int cap1 = __shfl_sync(full, cap, (lane & 7) + 8), cap2 = __shfl_sync(full, cap, (lane & 7) + 16), cap3 = __shfl_sync(full, cap, (lane & 7) + 24);
+  int cap0 = __shfl_sync(full, cap, lane & 7);
+  int capg = cap0 + cap1 + cap2 + cap3;                                  // capacity of group (lane & 7)
+  int over = lane < 8 ? max(g_cnt - capg, 0) : 0, spill_base = over;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(full, spill_base, o); if (lane >= o) spill_base += t; }
+  spill_base -= over;                                                    // exclusive prefix over groups (lanes 0..7)
+  int gc = __shfl_sync(full, g_cnt, lane & 7);                           // population of this column's group
+  int before = (lane >> 3) == 0 ? 0 : (lane >> 3) == 1 ? cap0 : (lane >> 3) == 2 ? cap0 + cap1 : cap0 + cap1 + cap2;
+  int used = min(max(gc - before, 0), cap), fr = cap - used, free_base = fr;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(full, free_base, o); if (lane >= o) free_base += t; }
+  free_base -= fr;                                                       // exclusive prefix of free slots over columns
+  for (int r0 = 0; r0 < cnt; r0 += 32) {
+    int r = r0 + lane;
+    bool live = r < cnt;
+    int from = src.x + src.z + (live ? r : 0) * src.w;
+    int g = (int)((keys_sorted[from] >> 3) & 7u);
+    int c0 = __shfl_sync(full, cap0, g), c1 = __shfl_sync(full, cap1, g), c2 = __shfl_sync(full, cap2, g);
+    int sb = __shfl_sync(full, spill_base, g), ov = __shfl_sync(full, over, g);
+    // The first `ov` items of the group spill.  They belong to the group's first cell, whose other particles sit at the
+    // top of column g, while free slots are at the bottom of other columns: a spilled particle does not share its round
+    // with a particle of its own cell.
+    int idx = r - __shfl_sync(full, gs, g) - ov;
+    int col, row;
+    bool spilled = idx < 0;
+    if (idx < c0) { col = g; row = idx; }
+    else if (idx < c0 + c1) { col = g + 8; row = idx - c0; }
+    else if (idx < c0 + c1 + c2) { col = g + 16; row = idx - c0 - c1; }
+    else { col = g + 24; row = idx - c0 - c1 - c2; }
+    int sidx = sb + idx + ov;
+    for (int l = 0; l < 32; ++l) {  // spilled items: the sidx-th free slot, columns in order
+      int fb = __shfl_sync(full, free_base, l), ff = __shfl_sync(full, fr, l), uu = __shfl_sync(full, used, l);
+      if (spilled && sidx >= fb && sidx < fb + ff) { col = l; row = uu + sidx - fb; }
+    }
+    if (live) {
+      int pos = cg.start + 32 * row + col;
+      perm_out[pos] = perm_in[from];
+      spos[from] = pos;  // sorted rank -> storage position, for the flat gather kernels
+    }
   }
 }
 
@@ -1341,6 +1511,10 @@ struct dd_sim {
   size_t stage_floats = 0;
   std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;
   long long launches = 0;    // kernels launched (or replayed through graphs) since creation
+  // persistent launch geometry of the tiled kernels (resident blocks per SM x SMs) and which gather variants run
+  int pb_p2g = 0, pb_g2pg = 0, pb_g2p = 0, pb_p2gg = 0;
+  bool g2p_tiled = false, p2gg_tiled = false;
+  int tile_blocks(int per_device) const { return std::max(1, std::min((nchunks + 3) / 4, per_device)); }
 
   float *slot(int f) const { return ckpt + (size_t)f * slot_floats; }
   float4 *G(int f) const { return grid_ckpt ? gridck + (size_t)f * kp.E * kp.G : grid; }
@@ -1365,15 +1539,16 @@ template <int SVD>
 void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk = nullptr) {
   const KP &kp = s->kp;
   if (s->cfg.tile_mode) {
-    int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
+    int nb64 = nblk((long long)s->nactive * 64);
     // invariant: the scatter target of substep f is already zero on the active bricks (cleared by the previous grid
     // kernel, or by dd_sim_forward for the first substep of a range)
-    k_p2g_tile<SVD, true><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->active_flag, s->counters + 3);
+    k_p2g_tile<SVD, true><<<s->tile_blocks(s->pb_p2g), 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->active_flag, s->counters + 3, s->counters + 4);
     mark(mk, "p2g_tile (svd+return map+scatter)");
     float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
     k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_b (grid update + contact)");
-    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->GV(f));
+    if (s->g2p_tiled) k_g2p_tile<<<s->tile_blocks(s->pb_g2p), 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), s->counters + 3, s->counters + 4);
+    else k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->GV(f));
     mark(mk, "g2p");
   } else {
     cudaMemsetAsync(s->grid, 0, sizeof(float4) * (size_t)kp.E * kp.G, st);
@@ -1390,17 +1565,18 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
   size_t eg = (size_t)kp.E * kp.G, ep = (size_t)kp.E * kp.nb;
   float4 *gp = s->gpos + (size_t)f * ep, *gr = s->grot + (size_t)f * ep, *gnp = s->gpos + (size_t)(f + 1) * ep, *gnr = s->grot + (size_t)(f + 1) * ep;
   if (s->cfg.tile_mode) {
-    int nb64 = nblk((long long)s->nactive * 64), ncb = (s->nchunks + kTileWarps - 1) / kTileWarps;
+    int nb64 = nblk((long long)s->nactive * 64);
     // invariant: ggrid_v is zero on the active bricks (k_grid_grad_b clears what it consumes)
     if (!s->grid_ckpt) {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
-      k_p2g_tile<SVD, false><<<ncb, 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->active_flag, s->counters + 3);
+      k_p2g_tile<SVD, false><<<s->tile_blocks(s->pb_p2g), 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->active_flag, s->counters + 3, s->counters + 4);
       k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
-    k_g2p_grad_tile<<<ncb, 32 * kTileWarps, 2 * kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3);
+    k_g2p_grad_tile<<<s->tile_blocks(s->pb_g2pg), 32 * kTileWarps, 2 * kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3, s->counters + 4);
     mark(mk, "g2p_grad_tile");
     k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
-    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
+    if (s->p2gg_tiled) k_p2g_grad_tile<SVD><<<s->tile_blocks(s->pb_p2gg), 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout, s->counters + 3, s->counters + 4);
+    else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
     mark(mk, "p2g_grad (+svd adjoint)");
   } else {
     cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st);
@@ -1539,6 +1715,20 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
     if ((kp.gx | kp.gy | kp.gz) & 3) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode needs grid dimensions that are multiples of 4"); }
     s->NBtot = kp.E * (kp.gx >> 2) * (kp.gy >> 2) * (kp.gz >> 2);
     cudaFuncSetAttribute(k_g2p_grad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTileWarps * kTileN * sizeof(float4)));
+    {
+      int dev = 0, sms = 1, occ = 1;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      size_t one = kTileWarps * kTileN * sizeof(float4);
+      auto per_device = [&](auto kernel, size_t smem) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * kTileWarps, smem); return std::max(occ, 1) * sms; };
+      if (cfg->svd_mode == 0) { s->pb_p2g = per_device(k_p2g_tile<0, true>, one); s->pb_p2gg = per_device(k_p2g_grad_tile<0>, one); }
+      else { s->pb_p2g = per_device(k_p2g_tile<1, true>, one); s->pb_p2gg = per_device(k_p2g_grad_tile<1>, one); }
+      s->pb_g2pg = per_device(k_g2p_grad_tile, 2 * one);
+      s->pb_g2p = per_device(k_g2p_tile, one);
+      const char *e1 = getenv("DD_G2P_TILE"), *e2 = getenv("DD_P2GG_TILE");
+      s->g2p_tiled = !(e1 && atoi(e1) == 0);  // default: tiled gather
+      s->p2gg_tiled = e2 && atoi(e2) != 0;
+    }
     s->chunk_max = cfg->chunk_max > 0 ? cfg->chunk_max : 160;  // ~3 thinned chunks per dense brick: several waves of warps (profiles/)
     int occ_cap = std::min(kp.EN, s->NBtot);
     s->chunk_cap = kp.EN / s->chunk_max + occ_cap + 1;
@@ -1654,7 +1844,7 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
       s->nchunks = host[0];
       s->nactive = host[1];
       if (s->nchunks > s->chunk_cap) return fail("dd_sim_set_state: chunk list overflow");
-      k_interleave<<<nblk((long long)s->nchunks * 32), kT, 0, st>>>(kp, s->nchunks, s->chunks, s->chunk_src, s->perm, s->idx_alt, s->spos);
+      k_interleave<<<nblk((long long)s->nchunks * 32), kT, 0, st>>>(kp, s->nchunks, s->chunks, s->chunk_src, s->keys_alt, s->perm, s->idx_alt, s->spos);
       std::swap(s->perm, s->idx_alt);
       // the active region changed: drop stale graphs (they captured the old launch geometry) and stale grid contents
       for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
