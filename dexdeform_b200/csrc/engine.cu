@@ -53,7 +53,7 @@ constexpr int kT = 256;
 #ifndef DD_LB_P2G_GRAD
 #define DD_LB_P2G_GRAD 2
 #endif
-constexpr int kPlaneFloats = 29;  // 16 (x,v,C + pad) + 9 (F) + 4 (SVD warm-start quaternion)
+constexpr int kPlaneFloats = 45;  // 16 (x,v,C + pad) + 9 (F) + 4 (quaternion of V) + 16 (constitutive checkpoint: affine, sigma, quaternion of U)
 
 struct KP {            // kernel parameters shared by all kernels
   int E, N, EN, nb, G, gx, gy, gz;
@@ -65,6 +65,8 @@ struct KP {            // kernel parameters shared by all kernels
 // slot layout (floats): [0,4EN) P0=(x.x,x.y,x.z,v.x)  [4EN,8EN) P1=(v.y,v.z,C00,C01)  [8EN,12EN) P2=(C02,C10,C11,C12)
 //                       [12EN,16EN) P3=(C20,C21,C22,0) [16EN,20EN) F0=(F00..F10) [20EN,24EN) F1=(F11..F21) [24EN,25EN) F2=F22
 //                       [25EN,29EN) Q=(qx,qy,qz,qw): quaternion of V of the SVD that produced this slot's F (warm start / replay)
+//                       [29EN,45EN) constitutive checkpoint of the substep that produced this slot, for the adjoint:
+//                                   A0=(a00,a01,a02,a10) A1=(a11,a12,a20,a21) A2=(a22,sig.x,sig.y,sig.z) A3=quaternion of U; a = affine matrix of p2g
 struct XVC { V3 x, v; M3 C; };
 DD_DEV const float4 *plane4(const float *slot, int EN, int k) { return reinterpret_cast<const float4 *>(slot + (size_t)4 * k * EN); }
 DD_DEV float4 *plane4(float *slot, int EN, int k) { return reinterpret_cast<float4 *>(slot + (size_t)4 * k * EN); }
@@ -100,6 +102,8 @@ DD_DEV void store_F(float *slot, int EN, int p, const M3 &F) {
 }
 DD_DEV float4 load_q(const float *slot, int EN, int p) { return ldg_stream(reinterpret_cast<const float4 *>(slot + (size_t)25 * EN) + p); }
 DD_DEV void store_q(float *slot, int EN, int p, float4 q) { reinterpret_cast<float4 *>(slot + (size_t)25 * EN)[p] = q; }
+DD_DEV const float4 *aux4(const float *slot, int EN, int k) { return reinterpret_cast<const float4 *>(slot + (size_t)(29 + 4 * k) * EN); }
+DD_DEV float4 *aux4(float *slot, int EN, int k) { return reinterpret_cast<float4 *>(slot + (size_t)(29 + 4 * k) * EN); }
 // shared-memory access that the compiler may neither reorder nor merge (the tile updates of one warp rely on program order).
 // Volatile asm statements keep their mutual order; plain accesses to the tiles (fill, flush) are fenced by __syncwarp().
 #ifdef DD_TILE_MEMCLOBBER
@@ -145,15 +149,24 @@ struct Constit {
   Plastic pl;
   float J, scale;
 };
-// q: warm-start quaternion in, converged quaternion out (svd_mode 1); max_sweeps = 0 replays a stored factorisation
+// q: warm-start quaternion in, converged quaternion out (svd_mode 1); max_sweeps = 0 replays a stored factorisation.
+// qu: quaternion of U (svd_mode 1 only)
 template <int SVD>
-DD_DEV void constitutive(const XVC &s, const M3 &F, float4 m0, float yield, const KP &kp, Constit &c, float4 &q, int max_sweeps) {
+DD_DEV void constitutive(const XVC &s, const M3 &F, float4 m0, float yield, const KP &kp, Constit &c, float4 &q, int max_sweeps, float4 *qu = nullptr) {
   c.Ft = mul(mdiag(1.f) + s.C * kp.dt, F);
-  if (SVD == 0) svd3_f64(c.Ft, c.U, c.sigma, c.Vm); else svd3_warm(c.Ft, q.x, q.y, q.z, q.w, c.U, c.sigma, c.Vm, max_sweeps);
+  if (SVD == 0) svd3_f64(c.Ft, c.U, c.sigma, c.Vm);
+  else svd3_warm<false>(c.Ft, q.x, q.y, q.z, q.w, c.U, c.sigma, c.Vm, max_sweeps, reinterpret_cast<float *>(qu));
   c.J = von_mises(c.Ft, c.U, c.sigma, c.Vm, yield, m0.z, c.nF, c.pl);
   c.r = mul_nt(c.U, c.Vm);
   c.scale = -kp.dt * m0.y * 4.f * kp.inv_dx * kp.inv_dx;
   c.affine = c.scale * fixed_corotated(c.nF, c.r, c.J, m0.z, m0.w) + m0.x * s.C;
+}
+// what the forward pass leaves for the adjoint in the next slot (svd_mode 1): no SVD, QR or stress evaluation in the backward pass
+DD_DEV void store_constit(float *nxt, int EN, int p, const Constit &c, float4 qu) {
+  aux4(nxt, EN, 0)[p] = make_float4(c.affine.a00, c.affine.a01, c.affine.a02, c.affine.a10);
+  aux4(nxt, EN, 1)[p] = make_float4(c.affine.a11, c.affine.a12, c.affine.a20, c.affine.a21);
+  aux4(nxt, EN, 2)[p] = make_float4(c.affine.a22, c.sigma.x, c.sigma.y, c.sigma.z);
+  aux4(nxt, EN, 3)[p] = qu;
 }
 
 // ---- forward kernels -------------------------------------------------------------------------------------------
@@ -167,9 +180,9 @@ __global__ void __launch_bounds__(kT) k_p2g(KP kp, const float *__restrict__ cur
   M3 F = load_F(cur, kp.EN, p);
   float4 m0 = __ldg(mat0 + p);
   Constit c;
-  float4 q = load_q(cur, kp.EN, p);
-  constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c, q, 6);
-  if (WRITE_F) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); }
+  float4 q = load_q(cur, kp.EN, p), qu;
+  constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c, q, 6, &qu);
+  if (WRITE_F) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); if (SVD == 1) store_constit(nxt, kp.EN, p, c, qu); }
   Stencil st = make_stencil_safe(s.x, kp);
   float m = m0.x;
   V3 mv = m * s.v;
@@ -597,17 +610,6 @@ DD_DEV unsigned chunk_active_mask(const char *__restrict__ active_flag, const Ch
   }
   return __ballot_sync(0xffffffffu, on);
 }
-// L2 prefetch of the next storage row (32 consecutive particles) of `nplanes` float4 planes of a slot, starting at plane
-// `first`: a row of one plane is 512 contiguous bytes, i.e. at most five 128-byte lines.  The tiled kernels run few warps
-// per SM, so without this every round starts with a full HBM round trip.
-DD_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-DD_DEV void prefetch_row4(const float *slot, int EN, int first, int nplanes, int p0, int lane) {
-  for (int t = lane; t < 5 * nplanes; t += 32) {
-    int k = t / 5, l = t - 5 * k;
-    prefetch_l2(reinterpret_cast<const char *>(plane4(slot, EN, first + k) + p0) + 128 * l);
-  }
-}
-DD_DEV void prefetch_row1(const float *base, int p0, int lane) { if (lane < 2) prefetch_l2(reinterpret_cast<const char *>(base + p0) + 128 * lane); }
 // Persistent chunk loop of the tiled kernels: every warp pulls chunk indices from a ticket counter until the list is
 // drained, so a launch never ends with a nearly empty last wave.  sched[0] = next ticket, sched[1] = warps that have
 // finished; the last warp to finish clears both for the next launch (launches are serialised on one stream).
@@ -623,9 +625,9 @@ DD_DEV void chunks_done(int *sched, int lane) {
 // particle whose stencil now reaches a brick outside it has out-run the region: its mass would land on nodes no grid
 // kernel processes, so the step is flagged invalid (reported at the next sync).  (tx,ty,tz) = stencil base in tile coordinates.
 DD_DEV void check_active(unsigned amask, int tx, int ty, int tz, int *overflow) {
-  int ax = (tx + 3) >> 2, bx = (tx + 5) >> 2, ay = (ty + 3) >> 2, by = (ty + 5) >> 2, az = (tz + 3) >> 2, bz = (tz + 5) >> 2;
-  bool ok = ax >= 0 && bx <= 2 && ay >= 0 && by <= 2 && az >= 0 && bz <= 2;
-  if (ok) {
+  bool ok = (unsigned)(tx + 3) <= 9u && (unsigned)(ty + 3) <= 9u && (unsigned)(tz + 3) <= 9u;  // inside the 3x3x3 brick neighbourhood
+  if (ok && amask != 0x7ffffffu) {  // (warp-uniform) some neighbour brick is inactive: test the bricks this stencil needs
+    int ax = (tx + 3) >> 2, bx = (tx + 5) >> 2, ay = (ty + 3) >> 2, by = (ty + 5) >> 2, az = (tz + 3) >> 2, bz = (tz + 5) >> 2;
     unsigned need = 0u;
     need |= 1u << (ax * 9 + ay * 3 + az); need |= 1u << (ax * 9 + ay * 3 + bz); need |= 1u << (ax * 9 + by * 3 + az); need |= 1u << (ax * 9 + by * 3 + bz);
     need |= 1u << (bx * 9 + ay * 3 + az); need |= 1u << (bx * 9 + ay * 3 + bz); need |= 1u << (bx * 9 + by * 3 + az); need |= 1u << (bx * 9 + by * 3 + bz);
@@ -639,13 +641,28 @@ template <int SVD, bool TILE>
 DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur, const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                               const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *tile, int ox, int oy, int oz,
                               const float *__restrict__ gin, float *__restrict__ gout, int *overflow) {
-  XVC s = load_xvc(cur, kp.EN, p);
-  M3 F = load_F(cur, kp.EN, p);
+  // svd_mode 1: the gather needs only x, v, the mass and the affine matrix the forward pass left in the next slot; everything
+  // else (F, C, the SVD factors, the incoming F gradient) is loaded after the gather so that it does not sit in registers
+  XVC s;
+  M3 F;
   float4 m0 = __ldg(mat0 + p);
-  float yl = __ldg(yield + p);
+  float yl = 0.f;
   Constit c;
-  float4 q = load_q(nxt, kp.EN, p);  // the forward pass left the converged quaternion of this very SVD in the next slot
-  constitutive<SVD>(s, F, m0, yl, kp, c, q, 0);
+  float4 aux2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (SVD == 1) {
+    float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p), b = ldg_stream(plane4(cur, kp.EN, 1) + p);
+    s.x = v3(a.x, a.y, a.z);
+    s.v = v3(a.w, b.x, b.y);
+    float4 a0 = ldg_stream(aux4(nxt, kp.EN, 0) + p), a1 = ldg_stream(aux4(nxt, kp.EN, 1) + p);
+    aux2 = ldg_stream(aux4(nxt, kp.EN, 2) + p);
+    c.affine = m3(a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, aux2.x);
+  } else {
+    s = load_xvc(cur, kp.EN, p);
+    F = load_F(cur, kp.EN, p);
+    yl = __ldg(yield + p);
+    float4 q = load_q(nxt, kp.EN, p);
+    constitutive<SVD>(s, F, m0, yl, kp, c, q, 0);
+  }
   float mu = m0.z, lam = m0.w, m_p = m0.x;
   Stencil st = make_stencil_safe(s.x, kp);
   V3 d0, d1, d2;
@@ -666,37 +683,64 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   // T = sum N g_mv (x) (offset - fx) dx follows from those four sums after the loop (~24 instead of ~33 instructions a node).
   V3 Sv = vzero(), g_x = vzero(), Tx = vzero(), Ty = vzero(), Tz = vzero();
   const float kz1 = wz[1], kz2 = 2.f * wz[2], ek1 = ez[1], ek2 = 2.f * ez[2];
-  auto gather = [&](auto fetch) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      V3 vi = base + c0 * (float)i;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float wij = wx[i] * wy[j], a1 = ex[i] * wy[j], a2 = wx[i] * ey[j];
-        V3 vij = vi + c1 * (float)j;
-        float4 t0 = fetch(i, j, 0), t1 = fetch(i, j, 1), t2 = fetch(i, j, 2);
-        V3 A = v3(fmaf(wz[2], t2.x, fmaf(wz[1], t1.x, wz[0] * t0.x)), fmaf(wz[2], t2.y, fmaf(wz[1], t1.y, wz[0] * t0.y)), fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z)));
-        V3 B = v3(fmaf(kz2, t2.x, kz1 * t1.x), fmaf(kz2, t2.y, kz1 * t1.y), fmaf(kz2, t2.z, kz1 * t1.z));
-        float M = fmaf(wz[2], t2.w, fmaf(wz[1], t1.w, wz[0] * t0.w));
-        V3 E = v3(fmaf(ez[2], t2.x, fmaf(ez[1], t1.x, ez[0] * t0.x)), fmaf(ez[2], t2.y, fmaf(ez[1], t1.y, ez[0] * t0.y)), fmaf(ez[2], t2.z, fmaf(ez[1], t1.z, ez[0] * t0.z)));
-        V3 EB = v3(fmaf(ek2, t2.x, ek1 * t1.x), fmaf(ek2, t2.y, ek1 * t1.y), fmaf(ek2, t2.z, ek1 * t1.z));
-        float EM = fmaf(ez[2], t2.w, fmaf(ez[1], t1.w, ez[0] * t0.w));
-        float S = fmaf(B.z, c2.z, fmaf(B.y, c2.y, fmaf(B.x, c2.x, fmaf(A.z, vij.z, fmaf(A.y, vij.y, fmaf(A.x, vij.x, m_p * M))))));
-        float SE = fmaf(EB.z, c2.z, fmaf(EB.y, c2.y, fmaf(EB.x, c2.x, fmaf(E.z, vij.z, fmaf(E.y, vij.y, fmaf(E.x, vij.x, m_p * EM))))));
-        g_x.x = fmaf(a1, S, g_x.x); g_x.y = fmaf(a2, S, g_x.y); g_x.z = fmaf(wij, SE, g_x.z);
-        Sv.x = fmaf(wij, A.x, Sv.x); Sv.y = fmaf(wij, A.y, Sv.y); Sv.z = fmaf(wij, A.z, Sv.z);
-        Tz.x = fmaf(wij, B.x, Tz.x); Tz.y = fmaf(wij, B.y, Tz.y); Tz.z = fmaf(wij, B.z, Tz.z);
-        if (i > 0) { float wi = wij * (float)i; Tx.x = fmaf(wi, A.x, Tx.x); Tx.y = fmaf(wi, A.y, Tx.y); Tx.z = fmaf(wi, A.z, Tx.z); }
-        if (j > 0) { float wj = wij * (float)j; Ty.x = fmaf(wj, A.x, Ty.x); Ty.y = fmaf(wj, A.y, Ty.y); Ty.z = fmaf(wj, A.z, Ty.z); }
-      }
-    }
+  auto row = [&](int i, int j, float wxi, float wyj, float exi, float eyj, float4 t0, float4 t1, float4 t2) {
+    float wij = wxi * wyj, a1 = exi * wyj, a2 = wxi * eyj;
+    V3 vij = base + c0 * (float)i + c1 * (float)j;
+    V3 A = v3(fmaf(wz[2], t2.x, fmaf(wz[1], t1.x, wz[0] * t0.x)), fmaf(wz[2], t2.y, fmaf(wz[1], t1.y, wz[0] * t0.y)), fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z)));
+    V3 B = v3(fmaf(kz2, t2.x, kz1 * t1.x), fmaf(kz2, t2.y, kz1 * t1.y), fmaf(kz2, t2.z, kz1 * t1.z));
+    float M = fmaf(wz[2], t2.w, fmaf(wz[1], t1.w, wz[0] * t0.w));
+    V3 E = v3(fmaf(ez[2], t2.x, fmaf(ez[1], t1.x, ez[0] * t0.x)), fmaf(ez[2], t2.y, fmaf(ez[1], t1.y, ez[0] * t0.y)), fmaf(ez[2], t2.z, fmaf(ez[1], t1.z, ez[0] * t0.z)));
+    V3 EB = v3(fmaf(ek2, t2.x, ek1 * t1.x), fmaf(ek2, t2.y, ek1 * t1.y), fmaf(ek2, t2.z, ek1 * t1.z));
+    float EM = fmaf(ez[2], t2.w, fmaf(ez[1], t1.w, ez[0] * t0.w));
+    float S = fmaf(B.z, c2.z, fmaf(B.y, c2.y, fmaf(B.x, c2.x, fmaf(A.z, vij.z, fmaf(A.y, vij.y, fmaf(A.x, vij.x, m_p * M))))));
+    float SE = fmaf(EB.z, c2.z, fmaf(EB.y, c2.y, fmaf(EB.x, c2.x, fmaf(E.z, vij.z, fmaf(E.y, vij.y, fmaf(E.x, vij.x, m_p * EM))))));
+    g_x.x = fmaf(a1, S, g_x.x); g_x.y = fmaf(a2, S, g_x.y); g_x.z = fmaf(wij, SE, g_x.z);
+    Sv.x = fmaf(wij, A.x, Sv.x); Sv.y = fmaf(wij, A.y, Sv.y); Sv.z = fmaf(wij, A.z, Sv.z);
+    Tz.x = fmaf(wij, B.x, Tz.x); Tz.y = fmaf(wij, B.y, Tz.y); Tz.z = fmaf(wij, B.z, Tz.z);
+    if (i > 0) { float wi = wij * (float)i; Tx.x = fmaf(wi, A.x, Tx.x); Tx.y = fmaf(wi, A.y, Tx.y); Tx.z = fmaf(wi, A.z, Tx.z); }
+    if (j > 0) { float wj = wij * (float)j; Ty.x = fmaf(wj, A.x, Ty.x); Ty.y = fmaf(wj, A.y, Ty.y); Ty.z = fmaf(wj, A.z, Ty.z); }
   };
   if (in_tile) {
     const float4 *trow = tile + (tx << 6 | ty << 3);
     int g0 = tz + 4 * ty + 2 * tx;
-    gather([&](int i, int j, int k) { return trow[(i << 6 | j << 3) + ((g0 + 2 * i + 4 * j + k) & 7)]; });
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float4 *r_ = trow + (i << 6 | j << 3);
+        int g = g0 + 2 * i + 4 * j;
+        row(i, j, wx[i], wy[j], ex[i], ey[j], r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7]);
+      }
+  } else if (TILE) {  // left the tile since the last sort (rare): rolled loop over the dense grid, kept small on purpose
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i)
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        const float4 *r_ = gg + (i * kp.gy + j) * kp.gz;
+        row(i, j, pick(st.w0, st.w1, st.w2, i, 0), pick(st.w0, st.w1, st.w2, j, 1), pick(d0, d1, d2, i, 0), pick(d0, d1, d2, j, 1), __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2));
+      }
   } else {
-    gather([&](int i, int j, int k) { return __ldg(gg + (i * kp.gy + j) * kp.gz + k); });
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float4 *r_ = gg + (i * kp.gy + j) * kp.gz;
+        row(i, j, wx[i], wy[j], ex[i], ey[j], __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2));
+      }
+  }
+  if (SVD == 1) {  // second half of the loads, then the factors from their checkpoints (no SVD, no QR, no stress evaluation)
+    float4 b = ldg_stream(plane4(cur, kp.EN, 1) + p), cc = ldg_stream(plane4(cur, kp.EN, 2) + p), d = ldg_stream(plane4(cur, kp.EN, 3) + p);
+    s.C = m3(b.z, b.w, cc.x, cc.y, cc.z, cc.w, d.x, d.y, d.z);
+    F = load_F(cur, kp.EN, p);
+    yl = __ldg(yield + p);
+    float4 qu = ldg_stream(aux4(nxt, kp.EN, 3) + p), q = load_q(nxt, kp.EN, p);
+    c.Ft = mul(mdiag(1.f) + s.C * kp.dt, F);
+    c.sigma = v3(aux2.y, aux2.z, aux2.w);
+    c.U = quat_to_m3(qu.x, qu.y, qu.z, qu.w);
+    c.Vm = quat_to_m3(q.x, q.y, q.z, q.w);
+    c.J = von_mises(c.Ft, c.U, c.sigma, c.Vm, yl, m0.z, c.nF, c.pl);
+    c.r = mul_nt(c.U, c.Vm);
+    c.scale = -kp.dt * m0.y * 4.f * kp.inv_dx * kp.inv_dx;
   }
   V3 t0 = (Tx - Sv * st.fx.x) * kp.dx, t1 = (Ty - Sv * st.fx.y) * kp.dx, t2 = (Tz - Sv * st.fx.z) * kp.dx;
   M3 T = m3(t0.x, t1.x, t2.x, t0.y, t1.y, t2.y, t0.z, t1.z, t2.z);
@@ -788,23 +832,13 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane < row_lanes(cg, j);
     int p = act ? cg.start + 32 * j + lane : cg.start;  // idle lanes shadow a valid particle, contribute nothing
-#ifndef DD_NO_PREFETCH
-    if (j + 1 < cg.R) {
-      int pn = cg.start + 32 * (j + 1);
-      prefetch_row4(cur, kp.EN, 0, 6, pn, lane);                       // x, v, C, 8 of F
-      prefetch_row1(cur + (size_t)24 * kp.EN, pn, lane);               // F22
-      prefetch_row4(cur + (size_t)25 * kp.EN, kp.EN, 0, 1, pn, lane);  // warm-start quaternion
-      prefetch_row4(reinterpret_cast<const float *>(mat0), kp.EN, 0, 1, pn, lane);
-      prefetch_row1(yield, pn, lane);
-    }
-#endif
     XVC s = load_xvc(cur, kp.EN, p);
     M3 F = load_F(cur, kp.EN, p);
     float4 m0 = __ldg(mat0 + p);
-    float4 q = load_q(cur, kp.EN, p);
+    float4 q = load_q(cur, kp.EN, p), qu;
     Constit c;
-    constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c, q, 6);
-    if (WRITE_F && act) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); }
+    constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c, q, 6, &qu);
+    if (WRITE_F && act) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); if (SVD == 1) store_constit(nxt, kp.EN, p, c, qu); }
     Stencil st = make_stencil_safe(s.x, kp);
     float m = m0.x;
     V3 c0 = v3(c.affine.a00, c.affine.a10, c.affine.a20) * kp.dx, c1 = v3(c.affine.a01, c.affine.a11, c.affine.a21) * kp.dx,
@@ -900,14 +934,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane < row_lanes(cg, j);
     int p = act ? cg.start + 32 * j + lane : cg.start;
-#ifndef DD_NO_PREFETCH
-    if (j + 1 < cg.R) {
-      int pn = cg.start + 32 * (j + 1);
-      prefetch_row4(cur, kp.EN, 0, 1, pn, lane);
-      prefetch_row4(nxt, kp.EN, 0, 2, pn, lane);
-      prefetch_row4(gin, kp.EN, 0, 4, pn, lane);
-    }
-#endif
     float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
     V3 x = v3(a.x, a.y, a.z);
     float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
@@ -1045,19 +1071,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
     load_tile(tile, ggrid + (size_t)cg.env * kp.G, cg, kp, lane);
     __syncwarp();
     for (int j = 0; j < cg.R; ++j) {
-#ifndef DD_NO_PREFETCH
-      if (j + 1 < cg.R) {
-        int pn = cg.start + 32 * (j + 1);
-        prefetch_row4(cur, kp.EN, 0, 6, pn, lane);
-        prefetch_row1(cur + (size_t)24 * kp.EN, pn, lane);
-        prefetch_row4(nxt + (size_t)25 * kp.EN, kp.EN, 0, 1, pn, lane);
-        prefetch_row4(reinterpret_cast<const float *>(mat0), kp.EN, 0, 1, pn, lane);
-        prefetch_row1(yield, pn, lane);
-        prefetch_row4(gin, kp.EN, 0, 6, pn, lane);
-        prefetch_row1(gin + (size_t)24 * kp.EN, pn, lane);
-        prefetch_row4(gout, kp.EN, 0, 1, pn, lane);
-      }
-#endif
       if (lane >= row_lanes(cg, j)) continue;
       p2g_grad_particle<SVD, true>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow);
     }
@@ -1080,9 +1093,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
   load_tile(tile, genv, cg, kp, lane);
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
-#ifndef DD_NO_PREFETCH
-    if (j + 1 < cg.R) prefetch_row4(cur, kp.EN, 0, 1, cg.start + 32 * (j + 1), lane);
-#endif
     if (lane >= row_lanes(cg, j)) continue;
     int p = cg.start + 32 * j + lane;
     float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
@@ -1367,6 +1377,20 @@ __global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks
   }
 }
 
+// largest chunks first: the persistent tiled kernels hand chunks out in list order, so the launch ends on the small ones
+__global__ void k_chunk_keys(int nchunks, const int4 *__restrict__ chunks, int *__restrict__ keys, int *__restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nchunks) return;
+  keys[i] = chunks[i].z;
+  idx[i] = i;
+}
+__global__ void k_chunk_permute(int nchunks, const int *__restrict__ order, const int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src,
+                                int4 *__restrict__ chunks_out, int4 *__restrict__ chunk_src_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nchunks) return;
+  chunks_out[i] = chunks[order[i]];
+  chunk_src_out[i] = chunk_src[order[i]];
+}
 __global__ void k_pad4(int n, const float *__restrict__ src, int w, float4 *dst) {  // (n, w<=4) floats -> float4
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1494,7 +1518,10 @@ struct dd_sim {
   void *cub_tmp = nullptr;
   size_t cub_bytes = 0;
   // tiled mode: chunk list, active bricks, per-substep grid checkpoints
-  int4 *chunks = nullptr, *chunk_src = nullptr;
+  int4 *chunks = nullptr, *chunk_src = nullptr, *chunks_alt = nullptr, *chunk_src_alt = nullptr;
+  int *chunk_sort = nullptr;  // 4 * chunk_cap ints: sizes, sorted sizes, indices, sorted indices
+  void *csort_tmp = nullptr;
+  size_t csort_bytes = 0;
   int chunk_cap = 0, nchunks = 0, chunk_max = 512;
   int *head_pos = nullptr, *spos = nullptr;
   char *head_flags = nullptr, *active_flag = nullptr;
@@ -1729,11 +1756,16 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       s->g2p_tiled = !(e1 && atoi(e1) == 0);  // default: tiled gather
       s->p2gg_tiled = e2 && atoi(e2) != 0;
     }
-    s->chunk_max = cfg->chunk_max > 0 ? cfg->chunk_max : 160;  // ~3 thinned chunks per dense brick: several waves of warps (profiles/)
+    s->chunk_max = cfg->chunk_max > 0 ? cfg->chunk_max : 256;  // ~2 thinned chunks per dense brick; measured optimum at config D (profiles/)
     int occ_cap = std::min(kp.EN, s->NBtot);
     s->chunk_cap = kp.EN / s->chunk_max + occ_cap + 1;
     DD_ALLOC(s->chunks, sizeof(int4) * s->chunk_cap);
     DD_ALLOC(s->chunk_src, sizeof(int4) * s->chunk_cap);
+    DD_ALLOC(s->chunks_alt, sizeof(int4) * s->chunk_cap);
+    DD_ALLOC(s->chunk_src_alt, sizeof(int4) * s->chunk_cap);
+    DD_ALLOC(s->chunk_sort, sizeof(int) * 4 * s->chunk_cap);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, s->csort_bytes, s->chunk_sort, s->chunk_sort, s->chunk_sort, s->chunk_sort, s->chunk_cap);
+    DD_ALLOC(s->csort_tmp, s->csort_bytes + 16);
     DD_ALLOC(s->head_pos, sizeof(int) * (occ_cap + 1));
     DD_ALLOC(s->spos, sizeof(int) * ENp);
     DD_ALLOC(s->head_flags, ENp);
@@ -1770,7 +1802,7 @@ void dd_sim_destroy(dd_sim *s) {
   for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
   void *ptrs[] = {s->ckpt, s->grad[0], s->grad[1], s->mat0, s->yield, s->grid, s->grid_v, s->ggrid_v, s->ggrid, s->pos, s->rot, s->gpos, s->grot,
                   s->tfsr, s->args, s->cull, s->perm, s->stage, s->keys, s->keys_alt, s->idx_alt, s->cub_tmp, s->mat_aos,
-                  s->chunks, s->chunk_src, s->head_pos, s->spos, s->head_flags, s->active_flag, s->active, s->counters, s->sel_tmp, s->gridck, s->gridvck};
+                  s->chunks, s->chunk_src, s->chunks_alt, s->chunk_src_alt, s->chunk_sort, s->csort_tmp, s->head_pos, s->spos, s->head_flags, s->active_flag, s->active, s->counters, s->sel_tmp, s->gridck, s->gridvck};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -1844,6 +1876,15 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
       s->nchunks = host[0];
       s->nactive = host[1];
       if (s->nchunks > s->chunk_cap) return fail("dd_sim_set_state: chunk list overflow");
+      {
+        int nc = s->nchunks, cap = s->chunk_cap;
+        int *ck = s->chunk_sort, *cks = ck + cap, *ci = ck + 2 * cap, *cis = ck + 3 * cap;
+        k_chunk_keys<<<nblk(nc), kT, 0, st>>>(nc, s->chunks, ck, ci);
+        DD_CUDA(cub::DeviceRadixSort::SortPairsDescending(s->csort_tmp, s->csort_bytes, ck, cks, ci, cis, nc, 0, 32, st));
+        k_chunk_permute<<<nblk(nc), kT, 0, st>>>(nc, cis, s->chunks, s->chunk_src, s->chunks_alt, s->chunk_src_alt);
+        std::swap(s->chunks, s->chunks_alt);
+        std::swap(s->chunk_src, s->chunk_src_alt);
+      }
       k_interleave<<<nblk((long long)s->nchunks * 32), kT, 0, st>>>(kp, s->nchunks, s->chunks, s->chunk_src, s->keys_alt, s->perm, s->idx_alt, s->spos);
       std::swap(s->perm, s->idx_alt);
       // the active region changed: drop stale graphs (they captured the old launch geometry) and stale grid contents

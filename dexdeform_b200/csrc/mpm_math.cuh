@@ -445,7 +445,11 @@ DD_HD void svd3_f32(const M3 &A, M3 &U, V3 &sig, M3 &Vo) {
 //     mass is at rounding level, so a particle whose F changed little converges in 0-1 sweeps instead of 5.  On return
 //     q holds the converged quaternion.  Calling it again with that q and the same A reproduces U, sig, V bit for bit
 //     with zero sweeps -- which is how the adjoint kernel re-creates the forward factors without re-iterating.
-DD_HD int svd3_warm(const M3 &A, float &qx, float &qy, float &qz, float &qw, M3 &U, V3 &sig, M3 &Vo, int max_sweeps = 6) {
+// SORT = false skips the ordering of the singular values (every consumer here is invariant under a consistent
+// permutation of the triplets); then `q` is also the quaternion of the returned V.  qu receives the quaternion (x,y,z,w) of U,
+// the product of the three Givens rotations of the QR step: U = Rz(t1) Ry(-t2) Rx(t3) with (ch_i, sh_i) = (cos, sin)(t_i / 2).
+template <bool SORT = true>
+DD_HD int svd3_warm(const M3 &A, float &qx, float &qy, float &qz, float &qw, M3 &U, V3 &sig, M3 &Vo, int max_sweeps = 6, float *qu = nullptr) {
   float v11, v12, v13, v21, v22, v23, v31, v32, v33;
   float b11, b12, b13, b21, b22, b23, b31, b32, b33;
   int sweeps = 0;
@@ -482,7 +486,7 @@ DD_HD int svd3_warm(const M3 &A, float &qx, float &qy, float &qz, float &qw, M3 
     b21 = A.a10 * v11 + A.a11 * v21 + A.a12 * v31; b22 = A.a10 * v12 + A.a11 * v22 + A.a12 * v32; b23 = A.a10 * v13 + A.a11 * v23 + A.a12 * v33;
     b31 = A.a20 * v11 + A.a21 * v21 + A.a22 * v31; b32 = A.a20 * v12 + A.a21 * v22 + A.a22 * v32; b33 = A.a20 * v13 + A.a21 * v23 + A.a22 * v33;
   }
-  {
+  if (SORT) {
     float r1 = b11 * b11 + b21 * b21 + b31 * b31, r2 = b12 * b12 + b22 * b22 + b32 * b32, r3 = b13 * b13 + b23 * b23 + b33 * b33;
     bool c = r1 < r2;
     cnswap32(c, b11, b12); cnswap32(c, v11, v12); cnswap32(c, b21, b22); cnswap32(c, v21, v22); cnswap32(c, b31, b32); cnswap32(c, v31, v32);
@@ -520,7 +524,21 @@ DD_HD int svd3_warm(const M3 &A, float &qx, float &qy, float &qz, float &qw, M3 
   U.a22 = (-1.f + 2.f * sh22) * (-1.f + 2.f * sh32);
   Vo.a00 = v11; Vo.a01 = v12; Vo.a02 = v13; Vo.a10 = v21; Vo.a11 = v22; Vo.a12 = v23; Vo.a20 = v31; Vo.a21 = v32; Vo.a22 = v33;
   sig.x = b11; sig.y = r22; sig.z = r33;
+  if (qu) {
+    float a = ch1 * ch2, bb = sh1 * sh2, c_ = -ch1 * sh2, d = sh1 * ch2;  // Rz(t1) Ry(-t2) as (w, x, y, z) = (a, bb, c_, d)
+    qu[3] = a * ch3 - bb * sh3; qu[0] = a * sh3 + bb * ch3; qu[1] = c_ * ch3 + d * sh3; qu[2] = d * ch3 - c_ * sh3;
+  }
   return sweeps;
+}
+
+// rotation matrix of a unit quaternion (x, y, z, w)
+DD_HD M3 quat_to_m3(float qx, float qy, float qz, float qw) {
+  float qxx = qx * qx, qyy = qy * qy, qzz = qz * qz, qxz = qx * qz, qxy = qx * qy, qyz = qy * qz, qwx = qw * qx, qwy = qw * qy, qwz = qw * qz;
+  M3 m;
+  m.a00 = 1.f - 2.f * (qyy + qzz); m.a01 = 2.f * (qxy - qwz); m.a02 = 2.f * (qxz + qwy);
+  m.a10 = 2.f * (qxy + qwz); m.a11 = 1.f - 2.f * (qxx + qzz); m.a12 = 2.f * (qyz - qwx);
+  m.a20 = 2.f * (qxz - qwy); m.a21 = 2.f * (qyz + qwx); m.a22 = 1.f - 2.f * (qxx + qyy);
+  return m;
 }
 
 // ---------------------------------------------------------------------------------------------- constitutive model

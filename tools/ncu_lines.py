@@ -78,17 +78,21 @@ rng = os.environ.get("LINES")  # e.g. LINES=engine.cu:599-698 -> inclusive count
 if rng:
     f0, r = rng.split(":")
     lo, hi = [int(v) for v in r.split("-")]
-    inc = Counter()
+    inc, smp, lsb, ssb = Counter(), Counter(), Counter(), Counter()
     for r_, (off, sass, chain) in zip(b["rows"], info):
         c = int(r_[h["Instructions Executed"]])
         for (f, l) in chain:
             if f == f0 and lo <= l <= hi:
                 inc[l] += c
+                smp[l] += int(r_[h["# Samples"]])
+                lsb[l] += int(r_[h["stall_long_sb"]])
+                ssb[l] += int(r_[h["stall_short_sb"]]) + int(r_[h["stall_mio"]])
                 break
+    stot = sum(smp.values())
     src = open(os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", f0)).read().splitlines() if os.path.exists(os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", f0)) else None
     for l in sorted(inc):
-        if inc[l] * 200 >= tot:
-            print(f"  {l:5d} {inc[l]:11d} {100 * inc[l] / tot:5.1f}%  {src[l - 1].strip()[:110] if src else ''}")
+        if inc[l] * 200 >= tot or smp[l] * 100 >= stot:
+            print(f"  {l:5d} {inc[l]:11d} {100 * inc[l] / tot:5.1f}% smp {100 * smp[l] / max(stot, 1):5.1f}% (long {100 * lsb[l] / max(stot, 1):4.1f} short/mio {100 * ssb[l] / max(stot, 1):4.1f})  {src[l - 1].strip()[:90] if src else ''}")
     sys.exit(0)
 print("-- by innermost source line")
 for (f, l), c in per_line.most_common(topn):
