@@ -583,7 +583,10 @@ __global__ void __launch_bounds__(kT) k_grid_grad(KP kp, float4 *__restrict__ gr
 //   Sv = sum N g_mv                     -> dL/dv = m Sv, and the -N A^T g_mv term of dL/dx is -A^T Sv
 //   dL/dx += sum gradN (m g_m + g_mv . (m v + A dpos))
 constexpr int kTileN = 512;          // 8^3 nodes
-constexpr int kTileWarps = 4;        // chunks per thread block
+constexpr int kTileWarps = 4;        // chunks per thread block (launch-bound hint; the launch picks the real number)
+constexpr int kStageP2G = 9;         // staged float4 slots per lane: p2g_tile
+constexpr int kStageG2PG = 7;        // g2p_grad_tile
+constexpr int kStageG2P = 1;         // g2p_tile
 // a chunk is stored as R rows of 32 particles (the last row holds the remaining `last`); row j starts at start + 32 j
 struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, last, bx, by, bz; };
 DD_DEV int row_lanes(const ChunkGeom &c, int j) { return j < c.R - 1 ? 32 : c.last; }
@@ -609,6 +612,32 @@ DD_DEV unsigned chunk_active_mask(const char *__restrict__ active_flag, const Ch
       on = active_flag[(size_t)cg.env * nbx * nby * nbz + (x * nby + y) * nbz + z] != 0;
   }
   return __ballot_sync(0xffffffffu, on);
+}
+// Asynchronous row staging for the tiled kernels.  A warp runs few rounds concurrently with few other warps, so a round that
+// starts with loads from HBM stalls for a full memory round trip.  Instead every lane copies the float4s of ITS particle of
+// the NEXT round into a per-warp staging area with cp.async (no registers, completes in the background of the current round)
+// and picks them up at the start of that round.  A lane only ever touches its own staging slots.
+DD_DEV void cp_async16(float4 *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+DD_DEV void cp_async4(float *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+DD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DD_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// fill the 8^3 tile from a dense grid (swizzled slots); out-of-grid nodes read as zero
+DD_DEV void fill_tile(float4 *tile, const float4 *__restrict__ grid_env, const KP &kp, int ox, int oy, int oz, int lane, float4 *zero_too = nullptr) {
+#ifdef DD_FILL_BATCH
+#pragma unroll DD_FILL_BATCH
+#endif
+  for (int n = lane; n < kTileN; n += 32) {
+    int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
+    int nx = ox + txx, ny = oy + tyy, nz = oz + tzz;
+    bool ok = (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz;
+    int slot = tile_slot(txx, tyy, tzz);
+    tile[slot] = ok ? __ldg(grid_env + (nx * kp.gy + ny) * kp.gz + nz) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (zero_too) zero_too[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 // Persistent chunk loop of the tiled kernels: every warp pulls chunk indices from a ticket counter until the list is
 // drained, so a launch never ends with a nearly empty last wave.  sched[0] = next ticket, sched[1] = warps that have
@@ -821,23 +850,42 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
                                                                  const float *__restrict__ yield, float4 *__restrict__ grid, const char *__restrict__ active_flag, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tile = dd_smem + warp * kTileN;
+  float4 *tile = dd_smem + warp * (kTileN + kStageP2G * 32), *stage = tile + kTileN + lane;
   unsigned tbase = smem_u32(tile);
   for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
-  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
-  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  auto stage_row = [&](int p) {  // x,v,C | 8 of F | quaternion | material: 8 float4; then F22 and the yield stress
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cp_async16(stage + 32 * k, plane4(cur, kp.EN, k) + p);
+    cp_async16(stage + 192, reinterpret_cast<const float4 *>(cur + (size_t)25 * kp.EN) + p);
+    cp_async16(stage + 224, mat0 + p);
+    cp_async4(reinterpret_cast<float *>(stage + 256), cur + (size_t)24 * kp.EN + p);
+    cp_async4(reinterpret_cast<float *>(stage + 256) + 1, yield + p);
+    cp_async_commit();
+  };
+  int ci = next_chunk(sched, lane);
+  int4 ch = ci < nchunks ? chunks[ci] : make_int4(0, 0, 0, 0);
+  if (ci < nchunks) stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
+  while (ci < nchunks) {
+  int cin = next_chunk(sched, lane);  // one chunk of look-ahead
+  int4 chn = cin < nchunks ? chunks[cin] : make_int4(0, 0, 0, 0);
+  ChunkGeom cg = chunk_geom(ch, kp);
   unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   float4 *g = grid + (size_t)cg.env * kp.G;
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane < row_lanes(cg, j);
     int p = act ? cg.start + 32 * j + lane : cg.start;  // idle lanes shadow a valid particle, contribute nothing
-    XVC s = load_xvc(cur, kp.EN, p);
-    M3 F = load_F(cur, kp.EN, p);
-    float4 m0 = __ldg(mat0 + p);
-    float4 q = load_q(cur, kp.EN, p), qu;
+    cp_async_wait_all();
+    float4 r0 = stage[0], r1 = stage[32], r2 = stage[64], r3 = stage[96], r4 = stage[128], r5 = stage[160], q = stage[192], m0 = stage[224], r8 = stage[256], qu;
+    if (j + 1 < cg.R) stage_row(lane < row_lanes(cg, j + 1) ? cg.start + 32 * (j + 1) + lane : cg.start);
+    else if (cin < nchunks) stage_row(chn.y + (lane < min(chn.z, 32) ? lane : 0));
+    XVC s;
+    s.x = v3(r0.x, r0.y, r0.z);
+    s.v = v3(r0.w, r1.x, r1.y);
+    s.C = m3(r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z);
+    M3 F = m3(r4.x, r4.y, r4.z, r4.w, r5.x, r5.y, r5.z, r5.w, r8.x);
     Constit c;
-    constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c, q, 6, &qu);
+    constitutive<SVD>(s, F, m0, r8.y, kp, c, q, 6, &qu);
     if (WRITE_F && act) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); if (SVD == 1) store_constit(nxt, kp.EN, p, c, qu); }
     Stencil st = make_stencil_safe(s.x, kp);
     float m = m0.x;
@@ -901,6 +949,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     }
   }
   __syncwarp();
+  ci = cin; ch = chn;
   }
   chunks_done(sched, lane);
 }
@@ -914,30 +963,42 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
                                                                       float4 *__restrict__ ggrid_v, const char *__restrict__ active_flag, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tv = dd_smem + warp * (2 * kTileN), *tg = tv + kTileN;
+  constexpr int kStage = kStageG2PG;  // staged float4s per particle: x | next (x,v) | incoming (gx, gv, gC)
+  float4 *tv = dd_smem + warp * (2 * kTileN + kStage * 32), *tg = tv + kTileN, *stage = tg + kTileN + lane;
   unsigned vbase = smem_u32(tv), gbase = smem_u32(tg);
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
-  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
-  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  auto stage_row = [&](int p) {
+    cp_async16(stage, plane4(cur, kp.EN, 0) + p);
+    cp_async16(stage + 32, plane4(nxt, kp.EN, 0) + p);
+    cp_async16(stage + 64, plane4(nxt, kp.EN, 1) + p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cp_async16(stage + 96 + 32 * k, plane4(gin, kp.EN, k) + p);
+    cp_async_commit();
+  };
+  int ci = next_chunk(sched, lane);
+  int4 ch = ci < nchunks ? chunks[ci] : make_int4(0, 0, 0, 0);
+  if (ci < nchunks) stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
+  while (ci < nchunks) {
+  int cin = next_chunk(sched, lane);  // one chunk of look-ahead: its descriptor arrives while this chunk is processed
+  int4 chn = cin < nchunks ? chunks[cin] : make_int4(0, 0, 0, 0);
+  ChunkGeom cg = chunk_geom(ch, kp);
   unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   size_t goff = (size_t)cg.env * kp.G;
-  for (int n = lane; n < kTileN; n += 32) {
-    int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
-    int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
-    bool ok = (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz;
-    int slot = tile_slot(txx, tyy, tzz);
-    tv[slot] = ok ? __ldg(grid_v + goff + (nx * kp.gy + ny) * kp.gz + nz) : make_float4(0.f, 0.f, 0.f, 0.f);
-    tg[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  fill_tile(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane < row_lanes(cg, j);
     int p = act ? cg.start + 32 * j + lane : cg.start;
-    float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
+    cp_async_wait_all();
+    float4 a = stage[0], n0 = stage[32], n1 = stage[64], g0_ = stage[96], g1_ = stage[128], g2_ = stage[160], g3_ = stage[192];
+    if (j + 1 < cg.R) stage_row(lane < row_lanes(cg, j + 1) ? cg.start + 32 * (j + 1) + lane : cg.start);
+    else if (cin < nchunks) stage_row(chn.y + (lane < min(chn.z, 32) ? lane : 0));
     V3 x = v3(a.x, a.y, a.z);
-    float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
-    XVC g = load_xvc(gin, kp.EN, p);
+    XVC g;
+    g.x = v3(g0_.x, g0_.y, g0_.z);
+    g.v = v3(g0_.w, g1_.x, g1_.y);
+    g.C = m3(g1_.z, g1_.w, g2_.x, g2_.y, g2_.z, g2_.w, g3_.x, g3_.y, g3_.z);
     V3 gx = g.x, gnv = g.v;
     V3 nx = x + v3(n0.w, n1.x, n1.y) * kp.dt;
     if (nx.x > hi.x || nx.x < lo) gx.x = 0;
@@ -1043,18 +1104,9 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
       red_add_v4(ggrid_v + goff + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, 0.f);
   }
   __syncwarp();
+  ci = cin; ch = chn;
   }
   chunks_done(sched, lane);
-}
-
-// load the 8^3 tile of a dense float4 grid into shared memory (swizzled slots); out-of-grid nodes read as zero
-DD_DEV void load_tile(float4 *tile, const float4 *__restrict__ grid_env, const ChunkGeom &cg, const KP &kp, int lane) {
-  for (int n = lane; n < kTileN; n += 32) {
-    int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
-    int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
-    bool ok = (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz;
-    tile[tile_slot(txx, tyy, tzz)] = ok ? __ldg(grid_env + (nx * kp.gy + ny) * kp.gz + nz) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
 }
 
 // p2g_grad on tiles
@@ -1068,7 +1120,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
   float4 *tile = dd_smem + warp * kTileN;
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
     ChunkGeom cg = chunk_geom(chunks[ci], kp);
-    load_tile(tile, ggrid + (size_t)cg.env * kp.G, cg, kp, lane);
+    fill_tile(tile, ggrid + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
     __syncwarp();
     for (int j = 0; j < cg.R; ++j) {
       if (lane >= row_lanes(cg, j)) continue;
@@ -1084,18 +1136,35 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
                                                                  float *__restrict__ nxt, const float4 *__restrict__ grid_v, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tile = dd_smem + warp * kTileN;
+  float4 *tile = dd_smem + warp * (kTileN + kStageG2P * 32), *stage = tile + kTileN + lane;
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx;
-  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
-  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  auto stage_row = [&](int p) { cp_async16(stage, plane4(cur, kp.EN, 0) + p); cp_async_commit(); };
+  int ci = next_chunk(sched, lane);
+  int4 ch = ci < nchunks ? chunks[ci] : make_int4(0, 0, 0, 0);
+#ifdef DD_G2P_STAGE
+  if (ci < nchunks) stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
+#endif
+  while (ci < nchunks) {
+  int cin = next_chunk(sched, lane);  // one chunk of look-ahead
+  int4 chn = cin < nchunks ? chunks[cin] : make_int4(0, 0, 0, 0);
+  ChunkGeom cg = chunk_geom(ch, kp);
   const float4 *genv = grid_v + (size_t)cg.env * kp.G;
-  load_tile(tile, genv, cg, kp, lane);
+  fill_tile(tile, genv, kp, cg.ox, cg.oy, cg.oz, lane);
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
+#ifdef DD_G2P_STAGE
+    cp_async_wait_all();
+    float4 a = stage[0];
+    if (j + 1 < cg.R) stage_row(lane < row_lanes(cg, j + 1) ? cg.start + 32 * (j + 1) + lane : cg.start);
+    else if (cin < nchunks) stage_row(chn.y + (lane < min(chn.z, 32) ? lane : 0));
+    if (lane >= row_lanes(cg, j)) continue;
+    int p = cg.start + 32 * j + lane;
+#else
     if (lane >= row_lanes(cg, j)) continue;
     int p = cg.start + 32 * j + lane;
     float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
+#endif
     V3 x = v3(a.x, a.y, a.z);
     Stencil st = make_stencil_safe(x, kp);
     float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
@@ -1115,6 +1184,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
     store_xvc(nxt, kp.EN, p, v3(fmaxf(fminf(t.x, hi.x), lo), fmaxf(fminf(t.y, hi.y), lo), fmaxf(fminf(t.z, hi.z), lo)), nv, nC);
   }
   __syncwarp();
+  ci = cin; ch = chn;
   }
   chunks_done(sched, lane);
 }
@@ -1153,11 +1223,13 @@ DD_DEV unsigned long long stage_bodies(GridSm &sm, const KP &kp, const BodyTable
     int pb = env * kp.nb + g;
     float4 p = bt.pos[pb];
     sm.pos[grp][g] = p; sm.rot[grp][g] = bt.rot[pb]; sm.npos[grp][g] = bt.npos[pb]; sm.nrot[grp][g] = bt.nrot[pb];
-    // squared distance from the body centre to the brick's node box [lo, lo + 3 dx]
-    float lx = (float)((bb / (nby * nbz)) * 4) * kp.dx, ly = (float)(((bb / nbz) % nby) * 4) * kp.dx, lz = (float)((bb % nbz) * 4) * kp.dx, w = 3.f * kp.dx;
-    float dx_ = fmaxf(fmaxf(lx - p.x, p.x - (lx + w)), 0.f), dy_ = fmaxf(fmaxf(ly - p.y, p.y - (ly + w)), 0.f), dz_ = fmaxf(fmaxf(lz - p.z, p.z - (lz + w)), 0.f);
-    float c = bt.cull[g] * 1.0001f + 1e-6f;
-    if (dx_ * dx_ + dy_ * dy_ + dz_ * dz_ <= c * c) atomicOr(&sm.cand[grp], 1ull << g);
+    // Exact signed distances are 1-Lipschitz: if the distance at the centre of the brick's node box [lo, lo + 3 dx]^3 exceeds
+    // the activation band by more than the half diagonal of the box, no node of the brick can touch this body.
+    float lx = (float)((bb / (nby * nbz)) * 4) * kp.dx, ly = (float)(((bb / nbz) % nby) * 4) * kp.dx, lz = (float)((bb % nbz) * 4) * kp.dx, h = 1.5f * kp.dx;
+    Q4 tf = q4f(bt.tfsr[g]);
+    float dist = shape_sdf(tf, q4f(bt.args[g]), qrot(qconj(q4f(sm.rot[grp][g])), v3(lx + h, ly + h, lz + h) - v3(p.x, p.y, p.z)));
+    float band = tf.y > 0.f ? 2.5f / tf.y : 0.f;
+    if (dist <= band + 2.5981f * kp.dx * 1.001f + 1e-6f) atomicOr(&sm.cand[grp], 1ull << g);
   }
   __syncthreads();
   // body index inside the kernels is env*nb + b: bias the shared-memory pointers so the same expression lands on [b]
@@ -1541,7 +1613,8 @@ struct dd_sim {
   // persistent launch geometry of the tiled kernels (resident blocks per SM x SMs) and which gather variants run
   int pb_p2g = 0, pb_g2pg = 0, pb_g2p = 0, pb_p2gg = 0;
   bool g2p_tiled = false, p2gg_tiled = false;
-  int tile_blocks(int per_device) const { return std::max(1, std::min((nchunks + 3) / 4, per_device)); }
+  int w_p2g = 4, w_g2pg = 1, w_g2p = 4, w_p2gg = 4;  // warps per block (the warps of a block are independent; this only sets the shared-memory granularity)
+  int tile_blocks(int per_device, int wpb) const { return std::max(1, std::min((nchunks + wpb - 1) / wpb, per_device)); }
 
   float *slot(int f) const { return ckpt + (size_t)f * slot_floats; }
   float4 *G(int f) const { return grid_ckpt ? gridck + (size_t)f * kp.E * kp.G : grid; }
@@ -1569,12 +1642,12 @@ void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk =
     int nb64 = nblk((long long)s->nactive * 64);
     // invariant: the scatter target of substep f is already zero on the active bricks (cleared by the previous grid
     // kernel, or by dd_sim_forward for the first substep of a range)
-    k_p2g_tile<SVD, true><<<s->tile_blocks(s->pb_p2g), 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->active_flag, s->counters + 3, s->counters + 4);
+    k_p2g_tile<SVD, true><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->active_flag, s->counters + 3, s->counters + 4);
     mark(mk, "p2g_tile (svd+return map+scatter)");
     float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
     k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_b (grid update + contact)");
-    if (s->g2p_tiled) k_g2p_tile<<<s->tile_blocks(s->pb_g2p), 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), s->counters + 3, s->counters + 4);
+    if (s->g2p_tiled) k_g2p_tile<<<s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * (kTileN + kStageG2P * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), s->counters + 3, s->counters + 4);
     else k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->GV(f));
     mark(mk, "g2p");
   } else {
@@ -1595,14 +1668,14 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
     int nb64 = nblk((long long)s->nactive * 64);
     // invariant: ggrid_v is zero on the active bricks (k_grid_grad_b clears what it consumes)
     if (!s->grid_ckpt) {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
-      k_p2g_tile<SVD, false><<<s->tile_blocks(s->pb_p2g), 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->active_flag, s->counters + 3, s->counters + 4);
+      k_p2g_tile<SVD, false><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->active_flag, s->counters + 3, s->counters + 4);
       k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
-    k_g2p_grad_tile<<<s->tile_blocks(s->pb_g2pg), 32 * kTileWarps, 2 * kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3, s->counters + 4);
+    k_g2p_grad_tile<<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3, s->counters + 4);
     mark(mk, "g2p_grad_tile");
     k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
-    if (s->p2gg_tiled) k_p2g_grad_tile<SVD><<<s->tile_blocks(s->pb_p2gg), 32 * kTileWarps, kTileWarps * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout, s->counters + 3, s->counters + 4);
+    if (s->p2gg_tiled) k_p2g_grad_tile<SVD><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout, s->counters + 3, s->counters + 4);
     else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
     mark(mk, "p2g_grad (+svd adjoint)");
   } else {
@@ -1741,17 +1814,29 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
     if (!cfg->sort_particles) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode requires sort_particles"); }
     if ((kp.gx | kp.gy | kp.gz) & 3) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode needs grid dimensions that are multiples of 4"); }
     s->NBtot = kp.E * (kp.gx >> 2) * (kp.gy >> 2) * (kp.gz >> 2);
-    cudaFuncSetAttribute(k_g2p_grad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTileWarps * kTileN * sizeof(float4)));
+    {
+      int big = 8 * (kTileN + kStageP2G * 32) * (int)sizeof(float4), big2 = std::min(8 * (2 * kTileN + kStageG2PG * 32) * (int)sizeof(float4), 227 * 1024);
+      cudaFuncSetAttribute(k_g2p_grad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, big2);
+      cudaFuncSetAttribute(k_g2p_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_grad_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_grad_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    }
     {
       int dev = 0, sms = 1, occ = 1;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      size_t one = kTileWarps * kTileN * sizeof(float4);
-      auto per_device = [&](auto kernel, size_t smem) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * kTileWarps, smem); return std::max(occ, 1) * sms; };
-      if (cfg->svd_mode == 0) { s->pb_p2g = per_device(k_p2g_tile<0, true>, one); s->pb_p2gg = per_device(k_p2g_grad_tile<0>, one); }
-      else { s->pb_p2g = per_device(k_p2g_tile<1, true>, one); s->pb_p2gg = per_device(k_p2g_grad_tile<1>, one); }
-      s->pb_g2pg = per_device(k_g2p_grad_tile, 2 * one);
-      s->pb_g2p = per_device(k_g2p_tile, one);
+      auto knob = [](const char *name, int dflt) { const char *e = getenv(name); int v = e ? atoi(e) : dflt; return v >= 1 && v <= 8 ? v : dflt; };
+      s->w_p2g = knob("DD_WPB_P2G", s->w_p2g); s->w_g2pg = knob("DD_WPB_G2PG", s->w_g2pg); s->w_g2p = knob("DD_WPB_G2P", s->w_g2p); s->w_p2gg = knob("DD_WPB_P2GG", s->w_p2gg);
+      size_t one = kTileN * sizeof(float4), two = (2 * kTileN + kStageG2PG * 32) * sizeof(float4), one_p2g = (kTileN + kStageP2G * 32) * sizeof(float4), one_g2p = (kTileN + kStageG2P * 32) * sizeof(float4);
+      auto per_device = [&](auto kernel, int wpb, size_t smem) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * wpb, smem * wpb); return std::max(occ, 1) * sms; };
+      if (cfg->svd_mode == 0) { s->pb_p2g = per_device(k_p2g_tile<0, true>, s->w_p2g, one_p2g); s->pb_p2gg = per_device(k_p2g_grad_tile<0>, s->w_p2gg, one); }
+      else { s->pb_p2g = per_device(k_p2g_tile<1, true>, s->w_p2g, one_p2g); s->pb_p2gg = per_device(k_p2g_grad_tile<1>, s->w_p2gg, one); }
+      s->pb_g2pg = per_device(k_g2p_grad_tile, s->w_g2pg, two);
+      s->pb_g2p = per_device(k_g2p_tile, s->w_g2p, one_g2p);
       const char *e1 = getenv("DD_G2P_TILE"), *e2 = getenv("DD_P2GG_TILE");
       s->g2p_tiled = !(e1 && atoi(e1) == 0);  // default: tiled gather
       s->p2gg_tiled = e2 && atoi(e2) != 0;
