@@ -586,7 +586,7 @@ constexpr int kTileN = 512;          // 8^3 nodes
 constexpr int kTileWarps = 4;        // chunks per thread block (launch-bound hint; the launch picks the real number)
 constexpr int kStageP2G = 9;         // staged float4 slots per lane: p2g_tile
 constexpr int kStageG2PG = 7;        // g2p_grad_tile
-constexpr int kStageG2P = 1;         // g2p_tile
+constexpr int kStageG2P = 0;         // g2p_tile (staging did not pay there: measured)
 // a chunk is stored as R rows of 32 particles (the last row holds the remaining `last`); row j starts at start + 32 j
 struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, last, bx, by, bz; };
 DD_DEV int row_lanes(const ChunkGeom &c, int j) { return j < c.R - 1 ? 32 : c.last; }
@@ -863,12 +863,10 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     cp_async4(reinterpret_cast<float *>(stage + 256) + 1, yield + p);
     cp_async_commit();
   };
-  int ci = next_chunk(sched, lane);
-  int4 ch = ci < nchunks ? chunks[ci] : make_int4(0, 0, 0, 0);
-  if (ci < nchunks) stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
-  while (ci < nchunks) {
-  int cin = next_chunk(sched, lane);  // one chunk of look-ahead
-  int4 chn = cin < nchunks ? chunks[cin] : make_int4(0, 0, 0, 0);
+  // (no look-ahead across chunks: a warp that holds a chunk in reserve lengthens the tail of the launch -- measured)
+  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+  int4 ch = chunks[ci];
+  stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
   ChunkGeom cg = chunk_geom(ch, kp);
   unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   float4 *g = grid + (size_t)cg.env * kp.G;
@@ -878,7 +876,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     cp_async_wait_all();
     float4 r0 = stage[0], r1 = stage[32], r2 = stage[64], r3 = stage[96], r4 = stage[128], r5 = stage[160], q = stage[192], m0 = stage[224], r8 = stage[256], qu;
     if (j + 1 < cg.R) stage_row(lane < row_lanes(cg, j + 1) ? cg.start + 32 * (j + 1) + lane : cg.start);
-    else if (cin < nchunks) stage_row(chn.y + (lane < min(chn.z, 32) ? lane : 0));
     XVC s;
     s.x = v3(r0.x, r0.y, r0.z);
     s.v = v3(r0.w, r1.x, r1.y);
@@ -949,7 +946,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     }
   }
   __syncwarp();
-  ci = cin; ch = chn;
   }
   chunks_done(sched, lane);
 }
@@ -976,12 +972,10 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     for (int k = 0; k < 4; ++k) cp_async16(stage + 96 + 32 * k, plane4(gin, kp.EN, k) + p);
     cp_async_commit();
   };
-  int ci = next_chunk(sched, lane);
-  int4 ch = ci < nchunks ? chunks[ci] : make_int4(0, 0, 0, 0);
-  if (ci < nchunks) stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
-  while (ci < nchunks) {
-  int cin = next_chunk(sched, lane);  // one chunk of look-ahead: its descriptor arrives while this chunk is processed
-  int4 chn = cin < nchunks ? chunks[cin] : make_int4(0, 0, 0, 0);
+  // (no look-ahead across chunks: a warp that holds a chunk in reserve lengthens the tail of the launch -- measured)
+  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+  int4 ch = chunks[ci];
+  stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
   ChunkGeom cg = chunk_geom(ch, kp);
   unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   size_t goff = (size_t)cg.env * kp.G;
@@ -993,7 +987,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     cp_async_wait_all();
     float4 a = stage[0], n0 = stage[32], n1 = stage[64], g0_ = stage[96], g1_ = stage[128], g2_ = stage[160], g3_ = stage[192];
     if (j + 1 < cg.R) stage_row(lane < row_lanes(cg, j + 1) ? cg.start + 32 * (j + 1) + lane : cg.start);
-    else if (cin < nchunks) stage_row(chn.y + (lane < min(chn.z, 32) ? lane : 0));
     V3 x = v3(a.x, a.y, a.z);
     XVC g;
     g.x = v3(g0_.x, g0_.y, g0_.z);
@@ -1104,7 +1097,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
       red_add_v4(ggrid_v + goff + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, 0.f);
   }
   __syncwarp();
-  ci = cin; ch = chn;
   }
   chunks_done(sched, lane);
 }
@@ -1136,35 +1128,18 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
                                                                  float *__restrict__ nxt, const float4 *__restrict__ grid_v, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tile = dd_smem + warp * (kTileN + kStageG2P * 32), *stage = tile + kTileN + lane;
+  float4 *tile = dd_smem + warp * kTileN;
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx;
-  auto stage_row = [&](int p) { cp_async16(stage, plane4(cur, kp.EN, 0) + p); cp_async_commit(); };
-  int ci = next_chunk(sched, lane);
-  int4 ch = ci < nchunks ? chunks[ci] : make_int4(0, 0, 0, 0);
-#ifdef DD_G2P_STAGE
-  if (ci < nchunks) stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
-#endif
-  while (ci < nchunks) {
-  int cin = next_chunk(sched, lane);  // one chunk of look-ahead
-  int4 chn = cin < nchunks ? chunks[cin] : make_int4(0, 0, 0, 0);
-  ChunkGeom cg = chunk_geom(ch, kp);
+  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
   const float4 *genv = grid_v + (size_t)cg.env * kp.G;
   fill_tile(tile, genv, kp, cg.ox, cg.oy, cg.oz, lane);
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
-#ifdef DD_G2P_STAGE
-    cp_async_wait_all();
-    float4 a = stage[0];
-    if (j + 1 < cg.R) stage_row(lane < row_lanes(cg, j + 1) ? cg.start + 32 * (j + 1) + lane : cg.start);
-    else if (cin < nchunks) stage_row(chn.y + (lane < min(chn.z, 32) ? lane : 0));
-    if (lane >= row_lanes(cg, j)) continue;
-    int p = cg.start + 32 * j + lane;
-#else
     if (lane >= row_lanes(cg, j)) continue;
     int p = cg.start + 32 * j + lane;
     float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
-#endif
     V3 x = v3(a.x, a.y, a.z);
     Stencil st = make_stencil_safe(x, kp);
     float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
@@ -1184,7 +1159,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
     store_xvc(nxt, kp.EN, p, v3(fmaxf(fminf(t.x, hi.x), lo), fmaxf(fminf(t.y, hi.y), lo), fmaxf(fminf(t.z, hi.z), lo)), nv, nC);
   }
   __syncwarp();
-  ci = cin; ch = chn;
   }
   chunks_done(sched, lane);
 }
