@@ -44,6 +44,9 @@ constexpr int kT = 256;
 #ifndef DD_LB_G2PG_TILE
 #define DD_LB_G2PG_TILE 4
 #endif
+#ifndef DD_LB_G2PG_SCATTER
+#define DD_LB_G2PG_SCATTER 6
+#endif
 #ifndef DD_LB_G2P_TILE
 #define DD_LB_G2P_TILE 5
 #endif
@@ -666,10 +669,14 @@ DD_DEV void check_active(unsigned amask, int tx, int ty, int tz, int *overflow) 
 }
 
 // TILE = true: node adjoints are read from a swizzled shared-memory tile at (tx,ty,tz); otherwise from the dense grid
-template <int SVD, bool TILE>
+// G2PG = true: the gather half of the g2p adjoint (integrator.cu:1527-1614) is done here as well, from a second tile holding the
+// grid velocities: dL/dx += gx' (clamp-masked) + sum gradN_n (v_n . h_n) - (4/dx^2) gC'^T v',  h_n = gv' + dt gx' + (4/dx) gC' (offset_n - fx),
+// with sum w_n v_n = v' taken from the next slot.  k_g2p_grad_tile then only scatters, with one tile instead of two.
+template <int SVD, bool TILE, bool G2PG = false>
 DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur, const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                               const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *tile, int ox, int oy, int oz,
-                              const float *__restrict__ gin, float *__restrict__ gout, int *overflow) {
+                              const float *__restrict__ gin, float *__restrict__ gout, int *overflow, const float4 *tile_v = nullptr,
+                              const float4 *__restrict__ grid_v = nullptr) {
   // svd_mode 1: the gather needs only x, v, the mass and the affine matrix the forward pass left in the next slot; everything
   // else (F, C, the SVD factors, the incoming F gradient) is loaded after the gather so that it does not sit in registers
   XVC s;
@@ -712,8 +719,29 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   // T = sum N g_mv (x) (offset - fx) dx follows from those four sums after the loop (~24 instead of ~33 instructions a node).
   V3 Sv = vzero(), g_x = vzero(), Tx = vzero(), Ty = vzero(), Tz = vzero();
   const float kz1 = wz[1], kz2 = 2.f * wz[2], ek1 = ez[1], ek2 = 2.f * ez[2];
-  auto row = [&](int i, int j, float wxi, float wyj, float exi, float eyj, float4 t0, float4 t1, float4 t2) {
+  V3 h0 = vzero(), H0 = vzero(), H1 = vzero(), H2 = vzero(), gxs = vzero(), g2p_x = vzero();
+  if (G2PG) {  // inputs of the g2p adjoint: gradients of state t+1 and the clamp mask of its position update
+    XVC g = load_xvc(gin, kp.EN, p);
+    float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
+    V3 nvel = v3(n0.w, n1.x, n1.y), nx = s.x + nvel * kp.dt;
+    V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+    float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
+    V3 gx = g.x;
+    if (nx.x > hi.x || nx.x < lo) gx.x = 0;
+    if (nx.y > hi.y || nx.y < lo) gx.y = 0;
+    if (nx.z > hi.z || nx.z < lo) gx.z = 0;
+    H0 = v3(g.C.a00, g.C.a10, g.C.a20) * s4; H1 = v3(g.C.a01, g.C.a11, g.C.a21) * s4; H2 = v3(g.C.a02, g.C.a12, g.C.a22) * s4;
+    h0 = g.v + gx * kp.dt - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
+    g2p_x = gx - (kp.inv_dx * s4) * mul_t(g.C, nvel);
+  }
+  auto row = [&](int i, int j, float wxi, float wyj, float exi, float eyj, float4 t0, float4 t1, float4 t2, float4 u0, float4 u1, float4 u2) {
     float wij = wxi * wyj, a1 = exi * wyj, a2 = wxi * eyj;
+    if (G2PG) {
+      V3 hij = h0 + H0 * (float)i + H1 * (float)j, hk1 = hij + H2, hk2 = hk1 + H2;
+      float q0 = u0.x * hij.x + u0.y * hij.y + u0.z * hij.z, q1 = u1.x * hk1.x + u1.y * hk1.y + u1.z * hk1.z, q2 = u2.x * hk2.x + u2.y * hk2.y + u2.z * hk2.z;
+      float Sq = fmaf(wz[2], q2, fmaf(wz[1], q1, wz[0] * q0)), SEq = fmaf(ez[2], q2, fmaf(ez[1], q1, ez[0] * q0));
+      gxs.x = fmaf(a1, Sq, gxs.x); gxs.y = fmaf(a2, Sq, gxs.y); gxs.z = fmaf(wij, SEq, gxs.z);
+    }
     V3 vij = base + c0 * (float)i + c1 * (float)j;
     V3 A = v3(fmaf(wz[2], t2.x, fmaf(wz[1], t1.x, wz[0] * t0.x)), fmaf(wz[2], t2.y, fmaf(wz[1], t1.y, wz[0] * t0.y)), fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z)));
     V3 B = v3(fmaf(kz2, t2.x, kz1 * t1.x), fmaf(kz2, t2.y, kz1 * t1.y), fmaf(kz2, t2.z, kz1 * t1.z));
@@ -738,7 +766,13 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
       for (int j = 0; j < 3; ++j) {
         const float4 *r_ = trow + (i << 6 | j << 3);
         int g = g0 + 2 * i + 4 * j;
-        row(i, j, wx[i], wy[j], ex[i], ey[j], r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7]);
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (G2PG) {
+          const float4 *v_ = tile_v + (tx << 6 | ty << 3) + (i << 6 | j << 3);
+          row(i, j, wx[i], wy[j], ex[i], ey[j], r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7], v_[g & 7], v_[(g + 1) & 7], v_[(g + 2) & 7]);
+        } else {
+          row(i, j, wx[i], wy[j], ex[i], ey[j], r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7], z4, z4, z4);
+        }
       }
   } else if (TILE) {  // left the tile since the last sort (rare): rolled loop over the dense grid, kept small on purpose
 #pragma unroll 1
@@ -746,7 +780,9 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
         const float4 *r_ = gg + (i * kp.gy + j) * kp.gz;
-        row(i, j, pick(st.w0, st.w1, st.w2, i, 0), pick(st.w0, st.w1, st.w2, j, 1), pick(d0, d1, d2, i, 0), pick(d0, d1, d2, j, 1), __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2));
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), u0 = z4, u1 = z4, u2 = z4;
+        if (G2PG) { const float4 *v_ = grid_v + (r_ - ggrid); u0 = __ldg(v_); u1 = __ldg(v_ + 1); u2 = __ldg(v_ + 2); }
+        row(i, j, pick(st.w0, st.w1, st.w2, i, 0), pick(st.w0, st.w1, st.w2, j, 1), pick(d0, d1, d2, i, 0), pick(d0, d1, d2, j, 1), __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2), u0, u1, u2);
       }
   } else {
 #pragma unroll
@@ -754,7 +790,8 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const float4 *r_ = gg + (i * kp.gy + j) * kp.gz;
-        row(i, j, wx[i], wy[j], ex[i], ey[j], __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2));
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        row(i, j, wx[i], wy[j], ex[i], ey[j], __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2), z4, z4, z4);
       }
   }
   if (SVD == 1) {  // second half of the loads, then the factors from their checkpoints (no SVD, no QR, no stress evaluation)
@@ -776,8 +813,12 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   g_x -= mul_t(c.affine, Sv);
   M3 g_stress = c.scale * T, g_C = m_p * T;
   V3 g_v = m_p * Sv;
-  float4 part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by the g2p adjoint
-  g_x += v3(part.x, part.y, part.z);
+  if (G2PG) {
+    g_x += g2p_x + gxs;
+  } else {
+    float4 part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by the g2p adjoint
+    g_x += v3(part.x, part.y, part.z);
+  }
   M3 gF_next = load_F(gin, kp.EN, p);
   // Adjoint of stress -> (F_new, R = U V^T, J) and of the return map, then through the SVD (integrator.cu:541-620, 131-159),
   // regrouped: with W = U^T g_R V and Y = U^T g_Fnew V every U/V gradient the reference materialises is
@@ -953,14 +994,16 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
 // g2p_grad on tiles (integrator.cu:1527-1614): grid velocities are gathered from a tile copy, their adjoint is scattered
 // into a second tile.  With h_n = gv' + (4/dx) gC' (offset_n - fx) (affine in the offset, so evaluated incrementally):
 //   d/d v_n  = w_n h_n ;  dL/dx = -(4/dx^2) gC'^T (sum w_n v_n) + sum gradN_n (v_n . h_n)
-__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+// GATHER = false: scatter only (one tile); the gather half then runs inside k_p2g_grad_tile<.., true>
+template <bool GATHER>
+__global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD_LB_G2PG_SCATTER) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout,
                                                                       float4 *__restrict__ ggrid_v, const char *__restrict__ active_flag, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kStage = kStageG2PG;  // staged float4s per particle: x | next (x,v) | incoming (gx, gv, gC)
-  float4 *tv = dd_smem + warp * (2 * kTileN + kStage * 32), *tg = tv + kTileN, *stage = tg + kTileN + lane;
+  float4 *tv = dd_smem + warp * ((GATHER ? 2 : 1) * kTileN + kStage * 32), *tg = GATHER ? tv + kTileN : tv, *stage = tg + kTileN + lane;
   unsigned vbase = smem_u32(tv), gbase = smem_u32(tg);
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
@@ -979,7 +1022,8 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
   ChunkGeom cg = chunk_geom(ch, kp);
   unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   size_t goff = (size_t)cg.env * kp.G;
-  fill_tile(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
+  if (GATHER) fill_tile(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
+  else for (int n = lane; n < kTileN; n += 32) tg[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane < row_lanes(cg, j);
@@ -1031,15 +1075,17 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
             V3 h = hij + H2 * (float)k;
             float w = wij * wz[k];
             int so = (i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7);
-            float4 t = tvrow[so];
+            float4 t = GATHER ? tvrow[so] : make_float4(0.f, 0.f, 0.f, 0.f);
             unsigned ga = growb + 16u * (unsigned)so;
             float4 o = lds_v4(ga);
             o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
             sts_v4_if(ga, o, mine);
-            Vw.x = fmaf(w, t.x, Vw.x); Vw.y = fmaf(w, t.y, Vw.y); Vw.z = fmaf(w, t.z, Vw.z);
-            float qn = t.x * h.x + t.y * h.y + t.z * h.z;
-            float tt = wz[k] * qn, uu = ez[k] * qn;
-            gxs.x = fmaf(a1, tt, gxs.x); gxs.y = fmaf(a2, tt, gxs.y); gxs.z = fmaf(wij, uu, gxs.z);
+            if (GATHER) {
+              Vw.x = fmaf(w, t.x, Vw.x); Vw.y = fmaf(w, t.y, Vw.y); Vw.z = fmaf(w, t.z, Vw.z);
+              float qn = t.x * h.x + t.y * h.y + t.z * h.z;
+              float tt = wz[k] * qn, uu = ez[k] * qn;
+              gxs.x = fmaf(a1, tt, gxs.x); gxs.y = fmaf(a2, tt, gxs.y); gxs.z = fmaf(wij, uu, gxs.z);
+            }
           }
         }
       }
@@ -1078,7 +1124,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
             float w = wxi * wyj * wzk;
             V3 h = h0 + H0 * (float)i + H1 * (float)jj + H2 * (float)k;
             size_t node = goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k;
-            float4 t = __ldg(grid_v + node);
+            float4 t = GATHER ? __ldg(grid_v + node) : make_float4(0.f, 0.f, 0.f, 0.f);
             red_add_v4(ggrid_v + node, w * h.x, w * h.y, w * h.z, 0.f);
             Vw += v3(t.x, t.y, t.z) * w;
             float qn = t.x * h.x + t.y * h.y + t.z * h.z;
@@ -1086,7 +1132,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
           }
     }
     gx += gxs - (kp.inv_dx * s4) * mul_t(g.C, Vw);
-    if (act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
+    if (GATHER && act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
   }
   __syncwarp();
   for (int n = lane; n < kTileN; n += 32) {
@@ -1102,21 +1148,22 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
 }
 
 // p2g_grad on tiles
-template <int SVD>
+template <int SVD, bool G2PG>
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ mat0,
-                                                                      const float *__restrict__ yield, const float4 *__restrict__ ggrid,
+                                                                      const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tile = dd_smem + warp * kTileN;
+  float4 *tile = dd_smem + warp * (G2PG ? 2 : 1) * kTileN, *tile_v = tile + kTileN;
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
     ChunkGeom cg = chunk_geom(chunks[ci], kp);
     fill_tile(tile, ggrid + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
+    if (G2PG) fill_tile(tile_v, grid_v + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
     __syncwarp();
     for (int j = 0; j < cg.R; ++j) {
       if (lane >= row_lanes(cg, j)) continue;
-      p2g_grad_particle<SVD, true>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow);
+      p2g_grad_particle<SVD, true, G2PG>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v);
     }
     __syncwarp();
   }
@@ -1586,7 +1633,7 @@ struct dd_sim {
   long long launches = 0;    // kernels launched (or replayed through graphs) since creation
   // persistent launch geometry of the tiled kernels (resident blocks per SM x SMs) and which gather variants run
   int pb_p2g = 0, pb_g2pg = 0, pb_g2p = 0, pb_p2gg = 0;
-  bool g2p_tiled = false, p2gg_tiled = false;
+  bool g2p_tiled = false, p2gg_tiled = false, fuse_gather = false;  // fuse_gather: gather half of the g2p adjoint inside k_p2g_grad_tile
   int w_p2g = 4, w_g2pg = 1, w_g2p = 4, w_p2gg = 4;  // warps per block (the warps of a block are independent; this only sets the shared-memory granularity)
   int tile_blocks(int per_device, int wpb) const { return std::max(1, std::min((nchunks + wpb - 1) / wpb, per_device)); }
 
@@ -1645,11 +1692,13 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
       k_p2g_tile<SVD, false><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->active_flag, s->counters + 3, s->counters + 4);
       k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
-    k_g2p_grad_tile<<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3, s->counters + 4);
+    if (s->fuse_gather) k_g2p_grad_tile<false><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3, s->counters + 4);
+    else k_g2p_grad_tile<true><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3, s->counters + 4);
     mark(mk, "g2p_grad_tile");
     k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
-    if (s->p2gg_tiled) k_p2g_grad_tile<SVD><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout, s->counters + 3, s->counters + 4);
+    if (s->fuse_gather) k_p2g_grad_tile<SVD, true><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * 2 * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, s->GV(f), gin, gout, s->counters + 3, s->counters + 4);
+    else if (s->p2gg_tiled) k_p2g_grad_tile<SVD, false><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, nullptr, gin, gout, s->counters + 3, s->counters + 4);
     else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
     mark(mk, "p2g_grad (+svd adjoint)");
   } else {
@@ -1790,14 +1839,17 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
     s->NBtot = kp.E * (kp.gx >> 2) * (kp.gy >> 2) * (kp.gz >> 2);
     {
       int big = 8 * (kTileN + kStageP2G * 32) * (int)sizeof(float4), big2 = std::min(8 * (2 * kTileN + kStageG2PG * 32) * (int)sizeof(float4), 227 * 1024);
-      cudaFuncSetAttribute(k_g2p_grad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, big2);
+      cudaFuncSetAttribute(k_g2p_grad_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big2);
+      cudaFuncSetAttribute(k_g2p_grad_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       cudaFuncSetAttribute(k_g2p_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       cudaFuncSetAttribute(k_p2g_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       cudaFuncSetAttribute(k_p2g_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       cudaFuncSetAttribute(k_p2g_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       cudaFuncSetAttribute(k_p2g_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_grad_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_grad_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_grad_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_grad_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_grad_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * big);
+      cudaFuncSetAttribute(k_p2g_grad_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * big);
     }
     {
       int dev = 0, sms = 1, occ = 1;
@@ -1807,9 +1859,16 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       s->w_p2g = knob("DD_WPB_P2G", s->w_p2g); s->w_g2pg = knob("DD_WPB_G2PG", s->w_g2pg); s->w_g2p = knob("DD_WPB_G2P", s->w_g2p); s->w_p2gg = knob("DD_WPB_P2GG", s->w_p2gg);
       size_t one = kTileN * sizeof(float4), two = (2 * kTileN + kStageG2PG * 32) * sizeof(float4), one_p2g = (kTileN + kStageP2G * 32) * sizeof(float4), one_g2p = (kTileN + kStageG2P * 32) * sizeof(float4);
       auto per_device = [&](auto kernel, int wpb, size_t smem) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * wpb, smem * wpb); return std::max(occ, 1) * sms; };
-      if (cfg->svd_mode == 0) { s->pb_p2g = per_device(k_p2g_tile<0, true>, s->w_p2g, one_p2g); s->pb_p2gg = per_device(k_p2g_grad_tile<0>, s->w_p2gg, one); }
-      else { s->pb_p2g = per_device(k_p2g_tile<1, true>, s->w_p2g, one_p2g); s->pb_p2gg = per_device(k_p2g_grad_tile<1>, s->w_p2gg, one); }
-      s->pb_g2pg = per_device(k_g2p_grad_tile, s->w_g2pg, two);
+      const char *e3 = getenv("DD_FUSE_GATHER");
+      s->fuse_gather = e3 && atoi(e3) != 0;  // default off: measured slower at config D (p2g_grad_tile loses more than g2p_grad_tile gains)
+      if (cfg->svd_mode == 0) s->pb_p2g = per_device(k_p2g_tile<0, true>, s->w_p2g, one_p2g); else s->pb_p2g = per_device(k_p2g_tile<1, true>, s->w_p2g, one_p2g);
+      if (s->fuse_gather) {
+        s->pb_p2gg = cfg->svd_mode == 0 ? per_device(k_p2g_grad_tile<0, true>, s->w_p2gg, 2 * one) : per_device(k_p2g_grad_tile<1, true>, s->w_p2gg, 2 * one);
+        s->pb_g2pg = per_device(k_g2p_grad_tile<false>, s->w_g2pg, one + kStageG2PG * 32 * sizeof(float4));
+      } else {
+        s->pb_p2gg = cfg->svd_mode == 0 ? per_device(k_p2g_grad_tile<0, false>, s->w_p2gg, one) : per_device(k_p2g_grad_tile<1, false>, s->w_p2gg, one);
+        s->pb_g2pg = per_device(k_g2p_grad_tile<true>, s->w_g2pg, two);
+      }
       s->pb_g2p = per_device(k_g2p_tile, s->w_g2p, one_g2p);
       const char *e1 = getenv("DD_G2P_TILE"), *e2 = getenv("DD_P2GG_TILE");
       s->g2p_tiled = !(e1 && atoi(e1) == 0);  // default: tiled gather
