@@ -672,26 +672,33 @@ DD_DEV void check_active(unsigned amask, int tx, int ty, int tz, int *overflow) 
 // G2PG = true: the gather half of the g2p adjoint (integrator.cu:1527-1614) is done here as well, from a second tile holding the
 // grid velocities: dL/dx += gx' (clamp-masked) + sum gradN_n (v_n . h_n) - (4/dx^2) gC'^T v',  h_n = gv' + dt gx' + (4/dx) gC' (offset_n - fx),
 // with sum w_n v_n = v' taken from the next slot.  k_g2p_grad_tile then only scatters, with one tile instead of two.
-template <int SVD, bool TILE, bool G2PG = false>
+// Staged inputs (tiled kernel, svd_mode 1): `stg` points at this lane's first staging slot (stride 32 float4); slots as in
+// kP2ggSlot*.  hook.phase1_done() / hook.phase2_done() are called as soon as the respective slots have been read, so that the
+// caller can start the asynchronous copies of the next round into them.
+struct NoHook { DD_DEV void phase1_done() const {} DD_DEV void phase2_done() const {} };
+constexpr int kStageP2GG = 16;  // 0 x|v  1 v|C  2 material  3-5 affine, sigma | 6,7 C  8,9 F  10 qU  11 qV  12,13 gF  14 partial gx  15 (F22, yield, gF22, -)
+template <int SVD, bool TILE, bool G2PG = false, class Hook = NoHook>
 DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur, const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                               const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *tile, int ox, int oy, int oz,
                               const float *__restrict__ gin, float *__restrict__ gout, int *overflow, const float4 *tile_v = nullptr,
-                              const float4 *__restrict__ grid_v = nullptr) {
+                              const float4 *__restrict__ grid_v = nullptr, const float4 *stg = nullptr, const Hook &hook = Hook()) {
   // svd_mode 1: the gather needs only x, v, the mass and the affine matrix the forward pass left in the next slot; everything
   // else (F, C, the SVD factors, the incoming F gradient) is loaded after the gather so that it does not sit in registers
   XVC s;
   M3 F;
-  float4 m0 = __ldg(mat0 + p);
+  float4 m0 = stg ? stg[2 * 32] : __ldg(mat0 + p);
   float yl = 0.f;
   Constit c;
-  float4 aux2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 aux2 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = aux2;
   if (SVD == 1) {
-    float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p), b = ldg_stream(plane4(cur, kp.EN, 1) + p);
+    float4 a = stg ? stg[0] : ldg_stream(plane4(cur, kp.EN, 0) + p);
+    p1 = stg ? stg[32] : ldg_stream(plane4(cur, kp.EN, 1) + p);
     s.x = v3(a.x, a.y, a.z);
-    s.v = v3(a.w, b.x, b.y);
-    float4 a0 = ldg_stream(aux4(nxt, kp.EN, 0) + p), a1 = ldg_stream(aux4(nxt, kp.EN, 1) + p);
-    aux2 = ldg_stream(aux4(nxt, kp.EN, 2) + p);
+    s.v = v3(a.w, p1.x, p1.y);
+    float4 a0 = stg ? stg[3 * 32] : ldg_stream(aux4(nxt, kp.EN, 0) + p), a1 = stg ? stg[4 * 32] : ldg_stream(aux4(nxt, kp.EN, 1) + p);
+    aux2 = stg ? stg[5 * 32] : ldg_stream(aux4(nxt, kp.EN, 2) + p);
     c.affine = m3(a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, aux2.x);
+    hook.phase1_done();
   } else {
     s = load_xvc(cur, kp.EN, p);
     F = load_F(cur, kp.EN, p);
@@ -794,12 +801,26 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
         row(i, j, wx[i], wy[j], ex[i], ey[j], __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2), z4, z4, z4);
       }
   }
+  M3 gF_next;
+  float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
   if (SVD == 1) {  // second half of the loads, then the factors from their checkpoints (no SVD, no QR, no stress evaluation)
-    float4 b = ldg_stream(plane4(cur, kp.EN, 1) + p), cc = ldg_stream(plane4(cur, kp.EN, 2) + p), d = ldg_stream(plane4(cur, kp.EN, 3) + p);
-    s.C = m3(b.z, b.w, cc.x, cc.y, cc.z, cc.w, d.x, d.y, d.z);
-    F = load_F(cur, kp.EN, p);
-    yl = __ldg(yield + p);
-    float4 qu = ldg_stream(aux4(nxt, kp.EN, 3) + p), q = load_q(nxt, kp.EN, p);
+    float4 cc, d, f0, f1, qu, q, g0, g1, sc;
+    if (stg) {
+      cc = stg[6 * 32]; d = stg[7 * 32]; f0 = stg[8 * 32]; f1 = stg[9 * 32]; qu = stg[10 * 32]; q = stg[11 * 32]; g0 = stg[12 * 32]; g1 = stg[13 * 32];
+      part = stg[14 * 32]; sc = stg[15 * 32];
+    } else {
+      cc = ldg_stream(plane4(cur, kp.EN, 2) + p); d = ldg_stream(plane4(cur, kp.EN, 3) + p);
+      f0 = ldg_stream(plane4(cur, kp.EN, 4) + p); f1 = ldg_stream(plane4(cur, kp.EN, 5) + p);
+      qu = ldg_stream(aux4(nxt, kp.EN, 3) + p); q = load_q(nxt, kp.EN, p);
+      g0 = ldg_stream(plane4(gin, kp.EN, 4) + p); g1 = ldg_stream(plane4(gin, kp.EN, 5) + p);
+      sc = make_float4(__ldg(cur + (size_t)24 * kp.EN + p), __ldg(yield + p), __ldg(gin + (size_t)24 * kp.EN + p), 0.f);
+      if (!G2PG) part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by the g2p adjoint
+    }
+    hook.phase2_done();
+    s.C = m3(p1.z, p1.w, cc.x, cc.y, cc.z, cc.w, d.x, d.y, d.z);
+    F = m3(f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, sc.x);
+    yl = sc.y;
+    gF_next = m3(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, sc.z);
     c.Ft = mul(mdiag(1.f) + s.C * kp.dt, F);
     c.sigma = v3(aux2.y, aux2.z, aux2.w);
     c.U = quat_to_m3(qu.x, qu.y, qu.z, qu.w);
@@ -813,13 +834,11 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   g_x -= mul_t(c.affine, Sv);
   M3 g_stress = c.scale * T, g_C = m_p * T;
   V3 g_v = m_p * Sv;
-  if (G2PG) {
-    g_x += g2p_x + gxs;
-  } else {
-    float4 part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by the g2p adjoint
-    g_x += v3(part.x, part.y, part.z);
+  if (SVD != 1) {
+    gF_next = load_F(gin, kp.EN, p);
+    if (!G2PG) part = plane4(gout, kp.EN, 0)[p];
   }
-  M3 gF_next = load_F(gin, kp.EN, p);
+  if (G2PG) g_x += g2p_x + gxs; else g_x += v3(part.x, part.y, part.z);
   // Adjoint of stress -> (F_new, R = U V^T, J) and of the return map, then through the SVD (integrator.cu:541-620, 131-159),
   // regrouped: with W = U^T g_R V and Y = U^T g_Fnew V every U/V gradient the reference materialises is
   //   U^T gU = W + Y E,   V^T gV = W^T + Y^T E      (E = diag(exp eps), plastic branch only)
@@ -1148,22 +1167,61 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
 }
 
 // p2g_grad on tiles
+// asynchronous copies of one particle's inputs into its staging slots, in the two groups the adjoint consumes them in
+struct P2ggStager {
+  const KP &kp;
+  const float *cur, *nxt, *gin, *yield;
+  const float4 *mat0;
+  float *gout;
+  float4 *stg;
+  int p_next;  // particle of the next round, or -1
+  DD_DEV void stage1(int p) const {
+    cp_async16(stg, plane4(cur, kp.EN, 0) + p); cp_async16(stg + 32, plane4(cur, kp.EN, 1) + p); cp_async16(stg + 2 * 32, mat0 + p);
+    cp_async16(stg + 3 * 32, aux4(nxt, kp.EN, 0) + p); cp_async16(stg + 4 * 32, aux4(nxt, kp.EN, 1) + p); cp_async16(stg + 5 * 32, aux4(nxt, kp.EN, 2) + p);
+    cp_async_commit();
+  }
+  DD_DEV void stage2(int p) const {
+    cp_async16(stg + 6 * 32, plane4(cur, kp.EN, 2) + p); cp_async16(stg + 7 * 32, plane4(cur, kp.EN, 3) + p);
+    cp_async16(stg + 8 * 32, plane4(cur, kp.EN, 4) + p); cp_async16(stg + 9 * 32, plane4(cur, kp.EN, 5) + p);
+    cp_async16(stg + 10 * 32, aux4(nxt, kp.EN, 3) + p); cp_async16(stg + 11 * 32, reinterpret_cast<const float4 *>(nxt + (size_t)25 * kp.EN) + p);
+    cp_async16(stg + 12 * 32, plane4(gin, kp.EN, 4) + p); cp_async16(stg + 13 * 32, plane4(gin, kp.EN, 5) + p);
+    cp_async16(stg + 14 * 32, plane4(gout, kp.EN, 0) + p);
+    float *sc = reinterpret_cast<float *>(stg + 15 * 32);
+    cp_async4(sc, cur + (size_t)24 * kp.EN + p); cp_async4(sc + 1, yield + p); cp_async4(sc + 2, gin + (size_t)24 * kp.EN + p);
+    cp_async_commit();
+  }
+  DD_DEV void phase1_done() const { if (p_next >= 0) stage1(p_next); }
+  DD_DEV void phase2_done() const { if (p_next >= 0) stage2(p_next); }
+};
+
 template <int SVD, bool G2PG>
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                                                                       const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout, int *overflow, int *sched) {
   extern __shared__ float4 dd_smem[];
+  constexpr bool STAGED = SVD == 1 && !G2PG;
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tile = dd_smem + warp * (G2PG ? 2 : 1) * kTileN, *tile_v = tile + kTileN;
+  float4 *tile = dd_smem + warp * ((G2PG ? 2 : 1) * kTileN + (STAGED ? kStageP2GG * 32 : 0)), *tile_v = tile + kTileN;
+  P2ggStager stager{kp, cur, nxt, gin, yield, mat0, gout, tile + kTileN + lane, -1};
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
     ChunkGeom cg = chunk_geom(chunks[ci], kp);
+    if (STAGED) { int p0 = cg.start + (lane < row_lanes(cg, 0) ? lane : 0); stager.stage1(p0); stager.stage2(p0); }
     fill_tile(tile, ggrid + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
     if (G2PG) fill_tile(tile_v, grid_v + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
     __syncwarp();
     for (int j = 0; j < cg.R; ++j) {
-      if (lane >= row_lanes(cg, j)) continue;
-      p2g_grad_particle<SVD, true, G2PG>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v);
+      if (STAGED) {
+        // every lane takes part (idle lanes of a short last row shadow the chunk's first particle and write nothing)
+        bool act = lane < row_lanes(cg, j);
+        stager.p_next = j + 1 < cg.R ? cg.start + (lane < row_lanes(cg, j + 1) ? 32 * (j + 1) + lane : 0) : -1;
+        cp_async_wait_all();
+        if (act) p2g_grad_particle<SVD, true, G2PG, P2ggStager>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v, stager.stg, stager);
+        else { stager.phase1_done(); stager.phase2_done(); }
+      } else {
+        if (lane >= row_lanes(cg, j)) continue;
+        p2g_grad_particle<SVD, true, G2PG>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v);
+      }
     }
     __syncwarp();
   }
@@ -1698,7 +1756,7 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
     k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
     if (s->fuse_gather) k_p2g_grad_tile<SVD, true><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * 2 * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, s->GV(f), gin, gout, s->counters + 3, s->counters + 4);
-    else if (s->p2gg_tiled) k_p2g_grad_tile<SVD, false><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, nullptr, gin, gout, s->counters + 3, s->counters + 4);
+    else if (s->p2gg_tiled) k_p2g_grad_tile<SVD, false><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * (kTileN + (SVD == 1 ? kStageP2GG * 32 : 0)) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, nullptr, gin, gout, s->counters + 3, s->counters + 4);
     else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
     mark(mk, "p2g_grad (+svd adjoint)");
   } else {
@@ -1847,7 +1905,7 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       cudaFuncSetAttribute(k_p2g_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       cudaFuncSetAttribute(k_p2g_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       cudaFuncSetAttribute(k_p2g_grad_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_grad_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      cudaFuncSetAttribute(k_p2g_grad_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(8 * (kTileN + kStageP2GG * 32) * (int)sizeof(float4), 227 * 1024));
       cudaFuncSetAttribute(k_p2g_grad_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * big);
       cudaFuncSetAttribute(k_p2g_grad_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * big);
     }
@@ -1866,13 +1924,13 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
         s->pb_p2gg = cfg->svd_mode == 0 ? per_device(k_p2g_grad_tile<0, true>, s->w_p2gg, 2 * one) : per_device(k_p2g_grad_tile<1, true>, s->w_p2gg, 2 * one);
         s->pb_g2pg = per_device(k_g2p_grad_tile<false>, s->w_g2pg, one + kStageG2PG * 32 * sizeof(float4));
       } else {
-        s->pb_p2gg = cfg->svd_mode == 0 ? per_device(k_p2g_grad_tile<0, false>, s->w_p2gg, one) : per_device(k_p2g_grad_tile<1, false>, s->w_p2gg, one);
+        s->pb_p2gg = cfg->svd_mode == 0 ? per_device(k_p2g_grad_tile<0, false>, s->w_p2gg, one) : per_device(k_p2g_grad_tile<1, false>, s->w_p2gg, one + kStageP2GG * 32 * sizeof(float4));
         s->pb_g2pg = per_device(k_g2p_grad_tile<true>, s->w_g2pg, two);
       }
       s->pb_g2p = per_device(k_g2p_tile, s->w_g2p, one_g2p);
       const char *e1 = getenv("DD_G2P_TILE"), *e2 = getenv("DD_P2GG_TILE");
       s->g2p_tiled = !(e1 && atoi(e1) == 0);  // default: tiled gather
-      s->p2gg_tiled = e2 && atoi(e2) != 0;
+      s->p2gg_tiled = e2 ? atoi(e2) != 0 : cfg->svd_mode == 1;  // default: the staged tile kernel with the fp32 SVD, the flat kernel otherwise
     }
     s->chunk_max = cfg->chunk_max > 0 ? cfg->chunk_max : 256;  // ~2 thinned chunks per dense brick; measured optimum at config D (profiles/)
     int occ_cap = std::min(kp.EN, s->NBtot);
