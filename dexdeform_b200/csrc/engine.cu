@@ -36,6 +36,11 @@ int fail(const std::string &msg) { g_last_error = msg; return 1; }
     if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+#ifdef DD_COLLIDE_REPASS
+#define DD_REPASS_MAX(m) (m)
+#else
+#define DD_REPASS_MAX(m) 0
+#endif
 constexpr int kT = 256;
 // occupancy knobs (min resident blocks per SM) -- tuned with ncu, see profiles/
 #ifndef DD_LB_P2G_TILE
@@ -958,7 +963,9 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     int rank = __popc(peers & ((1u << lane) - 1u));
     int maxr = __reduce_max_sync(0xffffffffu, rank);
     if (!in_tile) { tx = ty = tz = 0; }
-    for (int r = 0; r <= maxr; ++r) {  // one pass unless two lanes of this round share a cell
+    // one pass unless two lanes of this round share a cell (measured: cheaper here than sending the collided lanes' 27
+    // contributions straight to the grid, which is what the lighter g2p adjoint does)
+    for (int r = 0; r <= maxr; ++r) {
       bool mine = in_tile && rank == r;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -1109,7 +1116,22 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
         }
       }
     }
-    for (int r = 1; r <= maxr; ++r) {  // lanes that shared a cell with a lower lane: scatter only
+#ifndef DD_COLLIDE_REPASS
+    (void)maxr;
+    if (in_tile && rank > 0) {  // cell shared with a lower lane: scatter straight to the grid (rolled, rare)
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i)
+#pragma unroll 1
+        for (int jj = 0; jj < 3; ++jj)
+#pragma unroll 1
+          for (int k = 0; k < 3; ++k) {
+            float w = pick(st.w0, st.w1, st.w2, i, 0) * pick(st.w0, st.w1, st.w2, jj, 1) * pick(st.w0, st.w1, st.w2, k, 2);
+            V3 h = h0 + H0 * (float)i + H1 * (float)jj + H2 * (float)k;
+            red_add_v4(ggrid_v + goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, w * h.x, w * h.y, w * h.z, 0.f);
+          }
+    }
+#endif
+    for (int r = 1; r <= DD_REPASS_MAX(maxr); ++r) {  // (DD_COLLIDE_REPASS) lanes that shared a cell with a lower lane: scatter only
       bool mine = in_tile && rank == r;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
