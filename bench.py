@@ -230,7 +230,7 @@ def run_ours(args):
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "impl": "ours",
                "config": {"workload": desc, "particles_per_gpu": n, "substeps_per_step": S, "grid": int(sc["grid_dim"][0]),
-                          "l2_policy": "inputs larger than L2 (per-substep checkpoints: 116 MB/substep, 9.3 GB/step)",
+                          "l2_policy": "inputs larger than L2 (per-substep checkpoints: 180 MB/substep + 67 MB grids, 19.8 GB/step)",
                           "parallelism": f"env-batch x{world}, NCCL all-reduce of loss + pose gradients" if world > 1 else "single GPU"},
                "clocks": sampler.summary(),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "loss": loss},

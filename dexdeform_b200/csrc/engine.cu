@@ -1452,7 +1452,10 @@ __global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__
         lz = max(b0z - 1, 0) >> 2, hz = min((b0z + 3) >> 2, nbz - 1);
     for (int x_ = lx; x_ <= hx; ++x_)
       for (int y_ = ly; y_ <= hy; ++y_)
-        for (int z_ = lz; z_ <= hz; ++z_) active_flag[(size_t)env * NB + (x_ * nby + y_) * nbz + z_] = 1;
+        for (int z_ = lz; z_ <= hz; ++z_) {  // test first: a million particles mark a few thousand flags
+          char *fl = active_flag + (size_t)env * NB + (x_ * nby + y_) * nbz + z_;
+          if (!*fl) *fl = 1;
+        }
   }
 }
 
