@@ -164,7 +164,7 @@ DD_DEV void constitutive(const XVC &s, const M3 &F, float4 m0, float yield, cons
   c.Ft = mul(mdiag(1.f) + s.C * kp.dt, F);
   if (SVD == 0) svd3_f64(c.Ft, c.U, c.sigma, c.Vm);
   else svd3_warm<false>(c.Ft, q.x, q.y, q.z, q.w, c.U, c.sigma, c.Vm, max_sweeps, reinterpret_cast<float *>(qu));
-  c.J = von_mises(c.Ft, c.U, c.sigma, c.Vm, yield, m0.z, c.nF, c.pl);
+  c.J = von_mises<SVD == 1>(c.Ft, c.U, c.sigma, c.Vm, yield, m0.z, c.nF, c.pl);
   c.r = mul_nt(c.U, c.Vm);
   c.scale = -kp.dt * m0.y * 4.f * kp.inv_dx * kp.inv_dx;
   c.affine = c.scale * fixed_corotated(c.nF, c.r, c.J, m0.z, m0.w) + m0.x * s.C;
@@ -830,7 +830,7 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
     c.sigma = v3(aux2.y, aux2.z, aux2.w);
     c.U = quat_to_m3(qu.x, qu.y, qu.z, qu.w);
     c.Vm = quat_to_m3(q.x, q.y, q.z, q.w);
-    c.J = von_mises(c.Ft, c.U, c.sigma, c.Vm, yl, m0.z, c.nF, c.pl);
+    c.J = von_mises<true>(c.Ft, c.U, c.sigma, c.Vm, yl, m0.z, c.nF, c.pl);
     c.r = mul_nt(c.U, c.Vm);
     c.scale = -kp.dt * m0.y * 4.f * kp.inv_dx * kp.inv_dx;
   }

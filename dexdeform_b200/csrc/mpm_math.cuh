@@ -545,17 +545,20 @@ DD_HD M3 quat_to_m3(float qx, float qy, float qz, float qw) {
 // von-Mises return mapping in log-strain space (integrator.cu:42-67).  Returns J and writes F_new; `plastic`
 // and `ee` (= exp of the projected log strains) are kept for the adjoint.
 struct Plastic { bool plastic; V3 eps, eh, ee; float ehn, dg; };
+// FAST (fused engine, fp32 SVD): MUFU-based log / exp / reciprocals.  Absolute error of __logf on [0.05, 20] is < 4e-7, i.e. a
+// relative error of that size in F_new -- below the error of the fp32 SVD itself; the per-stage ABI keeps the exact forms.
+template <bool FAST = false>
 DD_DEV float von_mises(const M3 &Ft, const M3 &U, V3 s, const M3 &Vm, float yield, float mu, M3 &outF, Plastic &pl) {
   V3 sn = vmax(s, 0.05f);
-  pl.eps = v3(logf(sn.x), logf(sn.y), logf(sn.z));
-  float mean = (pl.eps.x + pl.eps.y + pl.eps.z) / 3.f;
+  pl.eps = FAST ? v3(__logf(sn.x), __logf(sn.y), __logf(sn.z)) : v3(logf(sn.x), logf(sn.y), logf(sn.z));
+  float mean = FAST ? (pl.eps.x + pl.eps.y + pl.eps.z) * (1.f / 3.f) : (pl.eps.x + pl.eps.y + pl.eps.z) / 3.f;
   pl.eh = v3(pl.eps.x - mean, pl.eps.y - mean, pl.eps.z - mean);
   pl.ehn = sqrtf(dot(pl.eh, pl.eh) + 1e-8f);  // norm(), integrator.cu:28-31
-  pl.dg = pl.ehn - yield / (2 * mu);
+  pl.dg = pl.ehn - (FAST ? __fdividef(yield, 2 * mu) : yield / (2 * mu));
   pl.plastic = pl.dg > 0.f;
   if (pl.plastic) {
-    V3 e = pl.eps - (pl.dg / pl.ehn) * pl.eh;
-    pl.ee = v3(expf(e.x), expf(e.y), expf(e.z));
+    V3 e = pl.eps - (FAST ? __fdividef(pl.dg, pl.ehn) : pl.dg / pl.ehn) * pl.eh;
+    pl.ee = FAST ? v3(__expf(e.x), __expf(e.y), __expf(e.z)) : v3(expf(e.x), expf(e.y), expf(e.z));
     outF = mul_nt(mul_diag(U, pl.ee), Vm);
     return pl.ee.x * pl.ee.y * pl.ee.z;
   }

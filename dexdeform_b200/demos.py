@@ -93,7 +93,7 @@ def chamfer_scores(final_x, goal_x, device="cuda", chunk=4096):
     def one_way(p, q):  # mean over p of the distance to the nearest q, chunked so that (chunk, M) fits easily
         acc = torch.zeros(p.shape[0], device=p.device)
         for i in range(0, p.shape[1], chunk):
-            acc += torch.cdist(p[:, i:i + chunk], q).min(dim=2).values.sum(dim=1)
+            acc += torch.cdist(p[:, i:i + chunk], q, compute_mode="donot_use_mm_for_euclid_dist").min(dim=2).values.sum(dim=1)
         return acc / p.shape[1]
 
     return one_way(a, b) + one_way(b, a)

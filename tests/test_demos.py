@@ -56,7 +56,15 @@ def test_chamfer_scores_cpu():
 def test_batched_replay_equals_single_env_replays_and_scores():
     from dexdeform_b200.engine import FusedSim
     S, E = 6, 3
-    scenes = [make_scene(3000, 32, box_width=(0.12, 0.12, 0.12), steps=S, perturb=0.02, vel_scale=0.3, on_floor=True, seed=10 + e) for e in range(E)]
+    base = make_scene(3000, 32, box_width=(0.12, 0.12, 0.12), steps=S, perturb=0.02, vel_scale=0.3, on_floor=True, seed=10)
+    rng = np.random.default_rng(3)
+    scenes = []
+    for e in range(E):  # same material and body shapes (they are per engine), different particle states and hand trajectories
+        sc = dict(base)
+        sc["x"] = (base["x"] + np.float32(0.004 * e) * np.array([1, 0, 1], np.float32)).astype(np.float32)
+        sc["v"] = (base["v"] + 0.1 * rng.standard_normal(base["v"].shape)).astype(np.float32)
+        sc["pos"] = (base["pos"] + np.float32(0.003 * e)).astype(np.float32)
+        scenes.append(sc)
     pos = np.stack([sc["pos"][:S + 1] for sc in scenes], axis=1)
     rot = np.stack([sc["rot"][:S + 1] for sc in scenes], axis=1)
     as_state = lambda sc: (sc["x"], sc["v"], sc["F"].reshape(-1, 3, 3), sc["C"].reshape(-1, 3, 3), sc["pos"][0], sc["rot"][0])
