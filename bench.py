@@ -132,12 +132,12 @@ def run_ours(args):
     gx_dev = torch.from_numpy(gx_host).cuda()
     packed = torch.zeros(1 + (S + 1) * nb * 7, dtype=torch.float32, device="cuda")  # [loss | pose grads] all-reduced over ranks
 
-    def step():
+    def step(collective=True):
         sim.forward(0, S)
         sim.zero_grad(S)
         sim._check(sim.lib.dd_sim_add_state_grad(sim._h, S, gx_dev.data_ptr(), None, None, None, sim.stream))
         sim.backward(0, S)
-        if world > 1:  # NCCL over NVLink: loss and pose (action) gradients only; environments never exchange state
+        if world > 1 and collective:  # NCCL over NVLink: loss and pose (action) gradients only; environments never exchange state
             import torch.distributed as dist
             base = packed.data_ptr() + 4  # [0] is the loss; pose gradients are written device-to-device behind it
             sim._check(sim.lib.dd_sim_get_pose_grads(sim._h, 0, S + 1, base, base + 4 * 3 * (S + 1) * nb, sim.stream))
@@ -159,7 +159,7 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     t_load = time.perf_counter()
     while len(sampler.samples) < 6 and time.perf_counter() - t_load < 4.0:  # short timed region: keep the same load up (untimed) for more clock samples
-        step()
+        step(collective=False)  # rank-local trip count: no collective in here, or the ranks' NCCL sequences diverge
     torch.cuda.synchronize()
     sampler.stop_flag = True
     launches = sim.launch_count() - launches0
