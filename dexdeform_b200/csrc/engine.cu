@@ -2067,6 +2067,7 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
       k_mark_heads<<<nblk(EN), kT, 0, st>>>(EN, s->keys_alt, s->head_flags);
       DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, s->counters + 2, EN, st));
       DD_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(int) * 2, st));
+      DD_CUDA(cudaMemsetAsync(s->counters + 4, 0, sizeof(int) * 2, st));  // chunk tickets: start clean even after an aborted launch
       DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
       DD_CUDA(cudaStreamSynchronize(st));
       int nbricks = host[2];
