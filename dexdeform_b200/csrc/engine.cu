@@ -1988,7 +1988,7 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       DD_ALLOC(s->gridvck, sizeof(float4) * eg * (size_t)cfg->max_steps);
     }
   }
-  s->stage_floats = (size_t)kp.EN * (24 > kp.nb ? 24 : kp.nb);
+  s->stage_floats = std::max((size_t)kp.EN * (24 > kp.nb ? 24 : kp.nb), (size_t)7 * s->slots * kp.E * kp.nb);  // states / distances, or every pose of every slot
   DD_ALLOC(s->stage, sizeof(float) * s->stage_floats);
 #undef DD_ALLOC
   std::vector<int> ident(kp.EN);

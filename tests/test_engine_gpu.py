@@ -166,7 +166,8 @@ def test_engine_error_reporting():
     sim.close()
 
 
-def test_tiled_path_equals_dense_path_with_drift_and_dense_cells():
+@pytest.mark.parametrize("svd_mode", [0, 1])
+def test_tiled_path_equals_dense_path_with_drift_and_dense_cells(svd_mode):
     """The shared-memory tile path (conflict serialisation, drift fallback to the grid) against the plain global-reduction
     path on a scene built to stress it: 40 particles per cell (many same-cell lanes per round) moving fast enough that
     most of them change cell (and many leave the tile interior) within the two substeps."""
@@ -177,7 +178,7 @@ def test_tiled_path_equals_dense_path_with_drift_and_dense_cells():
     seedg = loss_seed(4000, 5)
     outs = {}
     for tile in (False, True):
-        outs[tile] = run_engine(sc, S, seedg, svd_mode=0, tile_mode=tile, use_graphs=False, grid_ckpt=tile)
+        outs[tile] = run_engine(sc, S, seedg, svd_mode=svd_mode, tile_mode=tile, use_graphs=False, grid_ckpt=tile)
     a, b = outs[False], outs[True]
     for k in ("x", "v", "F", "C"):
         assert rel_err(b["state"][k], a["state"][k]) < 2e-5, (k, rel_err(b["state"][k], a["state"][k]))
@@ -205,3 +206,21 @@ def test_recompute_mode_matches_checkpoint_mode():
     for k in ("x", "v", "F", "C"):
         assert_close_rows(b["grad"][k][0], a["grad"][k][0], 1e-4, k + "_grad")
     assert a["launches"] == 6 * S + 1 and b["launches"] == 8 * S + 1
+
+
+@pytest.mark.parametrize("n,E,chunk_max", [(4, 1, 32), (36, 2, 32), (1000, 3, 32), (5000, 1, 96), (5000, 2, 0)])
+def test_tiled_rows_small_ragged_and_short_chunks(n, E, chunk_max):
+    """Row tables with one short row, chunks much smaller than a brick (many spills into foreign columns), several
+    environments: the production tile path (fp32 SVD, staged kernels, ticket scheduling) against the dense path."""
+    S = 4
+    w = 0.05 + 0.1 * min(1.0, n / 5000.0)
+    sc = make_scene(n, 32, box_center=(0.5, 0.3, 0.5), box_width=(w, w, w), steps=S, perturb=0.02, vel_scale=0.5, on_floor=True, nb=4, seed=77)
+    seedg = loss_seed(n, 9)
+    a = run_engine(sc, S, seedg, E=E, tile_mode=False, use_graphs=False, grid_ckpt=False)
+    b = run_engine(sc, S, seedg, E=E, tile_mode=True, chunk_max=chunk_max)
+    for k in ("x", "v", "F", "C"):
+        assert rel_err(b["state"][k], a["state"][k]) < 2e-5, (k, rel_err(b["state"][k], a["state"][k]))
+    for e in range(E):
+        for k in ("x", "v"):
+            assert_close_rows(b["grad"][k][e], a["grad"][k][e], 1e-3, k + "_grad")
+    assert np.abs(b["gpos"] - a["gpos"]).max() < 2e-3 * max(np.abs(a["gpos"]).max(), 1.0)
