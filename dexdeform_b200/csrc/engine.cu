@@ -36,11 +36,6 @@ int fail(const std::string &msg) { g_last_error = msg; return 1; }
     if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
-#ifdef DD_COLLIDE_REPASS
-#define DD_REPASS_MAX(m) (m)
-#else
-#define DD_REPASS_MAX(m) 0
-#endif
 constexpr int kT = 256;
 // occupancy knobs (min resident blocks per SM) -- tuned with ncu, see profiles/
 #ifndef DD_LB_P2G_TILE
@@ -594,7 +589,6 @@ constexpr int kTileN = 512;          // 8^3 nodes
 constexpr int kTileWarps = 4;        // chunks per thread block (launch-bound hint; the launch picks the real number)
 constexpr int kStageP2G = 9;         // staged float4 slots per lane: p2g_tile
 constexpr int kStageG2PG = 7;        // g2p_grad_tile
-constexpr int kStageG2P = 0;         // g2p_tile (staging did not pay there: measured)
 // a chunk is stored as R rows of 32 particles (the last row holds the remaining `last`); row j starts at start + 32 j
 struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, last, bx, by, bz; };
 DD_DEV int row_lanes(const ChunkGeom &c, int j) { return j < c.R - 1 ? 32 : c.last; }
@@ -635,9 +629,6 @@ DD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memor
 DD_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // fill the 8^3 tile from a dense grid (swizzled slots); out-of-grid nodes read as zero
 DD_DEV void fill_tile(float4 *tile, const float4 *__restrict__ grid_env, const KP &kp, int ox, int oy, int oz, int lane, float4 *zero_too = nullptr) {
-#ifdef DD_FILL_BATCH
-#pragma unroll DD_FILL_BATCH
-#endif
   for (int n = lane; n < kTileN; n += 32) {
     int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
     int nx = ox + txx, ny = oy + tyy, nz = oz + tzz;
@@ -1081,7 +1072,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
     int rank = __popc(peers & ((1u << lane) - 1u));
-    int maxr = __reduce_max_sync(0xffffffffu, rank);
     if (!in_tile) { tx = ty = tz = 0; }
     V3 Vw = vzero(), gxs = vzero();
     const float4 *tvrow = tv + (tx << 6 | ty << 3);
@@ -1116,8 +1106,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
         }
       }
     }
-#ifndef DD_COLLIDE_REPASS
-    (void)maxr;
     if (in_tile && rank > 0) {  // cell shared with a lower lane: scatter straight to the grid (rolled, rare)
 #pragma unroll 1
       for (int i = 0; i < 3; ++i)
@@ -1129,28 +1117,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
             V3 h = h0 + H0 * (float)i + H1 * (float)jj + H2 * (float)k;
             red_add_v4(ggrid_v + goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, w * h.x, w * h.y, w * h.z, 0.f);
           }
-    }
-#endif
-    for (int r = 1; r <= DD_REPASS_MAX(maxr); ++r) {  // (DD_COLLIDE_REPASS) lanes that shared a cell with a lower lane: scatter only
-      bool mine = in_tile && rank == r;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        V3 hi_ = h0 + H0 * (float)i;
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-          V3 hij = hi_ + H1 * (float)jj;
-          float wij = wx[i] * wy[jj];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            V3 h = hij + H2 * (float)k;
-            float w = wij * wz[k];
-            unsigned ga = growb + 16u * (unsigned)((i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7));
-            float4 o = lds_v4(ga);
-            o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
-            sts_v4_if(ga, o, mine);
-          }
-        }
-      }
     }
     if (!in_tile) { Vw = vzero(); gxs = vzero(); }
     if (act && !in_tile) {
@@ -1751,7 +1717,7 @@ void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk =
     float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
     k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_b (grid update + contact)");
-    if (s->g2p_tiled) k_g2p_tile<<<s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * (kTileN + kStageG2P * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), s->counters + 3, s->counters + 4);
+    if (s->g2p_tiled) k_g2p_tile<<<s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), s->counters + 3, s->counters + 4);
     else k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->GV(f));
     mark(mk, "g2p");
   } else {
@@ -1940,7 +1906,7 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       auto knob = [](const char *name, int dflt) { const char *e = getenv(name); int v = e ? atoi(e) : dflt; return v >= 1 && v <= 8 ? v : dflt; };
       s->w_p2g = knob("DD_WPB_P2G", s->w_p2g); s->w_g2pg = knob("DD_WPB_G2PG", s->w_g2pg); s->w_g2p = knob("DD_WPB_G2P", s->w_g2p); s->w_p2gg = knob("DD_WPB_P2GG", s->w_p2gg);
-      size_t one = kTileN * sizeof(float4), two = (2 * kTileN + kStageG2PG * 32) * sizeof(float4), one_p2g = (kTileN + kStageP2G * 32) * sizeof(float4), one_g2p = (kTileN + kStageG2P * 32) * sizeof(float4);
+      size_t one = kTileN * sizeof(float4), two = (2 * kTileN + kStageG2PG * 32) * sizeof(float4), one_p2g = (kTileN + kStageP2G * 32) * sizeof(float4), one_g2p = kTileN * sizeof(float4);
       auto per_device = [&](auto kernel, int wpb, size_t smem) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * wpb, smem * wpb); return std::max(occ, 1) * sms; };
       const char *e3 = getenv("DD_FUSE_GATHER");
       s->fuse_gather = e3 && atoi(e3) != 0;  // default off: measured slower at config D (p2g_grad_tile loses more than g2p_grad_tile gains)
