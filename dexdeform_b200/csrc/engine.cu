@@ -1073,7 +1073,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
     unsigned peers = __match_any_sync(0xffffffffu, key);
     int rank = __popc(peers & ((1u << lane) - 1u));
     if (!in_tile) { tx = ty = tz = 0; }
-    V3 Vw = vzero(), gxs = vzero();
+    V3 gxs = vzero();
     const float4 *tvrow = tv + (tx << 6 | ty << 3);
     unsigned growb = gbase + 16u * (unsigned)(tx << 6 | ty << 3);
     int g0 = tz + 4 * ty + 2 * tx;
@@ -1097,7 +1097,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
             o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
             sts_v4_if(ga, o, mine);
             if (GATHER) {
-              Vw.x = fmaf(w, t.x, Vw.x); Vw.y = fmaf(w, t.y, Vw.y); Vw.z = fmaf(w, t.z, Vw.z);
               float qn = t.x * h.x + t.y * h.y + t.z * h.z;
               float tt = wz[k] * qn, uu = ez[k] * qn;
               gxs.x = fmaf(a1, tt, gxs.x); gxs.y = fmaf(a2, tt, gxs.y); gxs.z = fmaf(wij, uu, gxs.z);
@@ -1118,7 +1117,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
             red_add_v4(ggrid_v + goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, w * h.x, w * h.y, w * h.z, 0.f);
           }
     }
-    if (!in_tile) { Vw = vzero(); gxs = vzero(); }
+    if (!in_tile) gxs = vzero();
     if (act && !in_tile) {
       tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
 #pragma unroll 1
@@ -1133,12 +1132,11 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
             size_t node = goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k;
             float4 t = GATHER ? __ldg(grid_v + node) : make_float4(0.f, 0.f, 0.f, 0.f);
             red_add_v4(ggrid_v + node, w * h.x, w * h.y, w * h.z, 0.f);
-            Vw += v3(t.x, t.y, t.z) * w;
             float qn = t.x * h.x + t.y * h.y + t.z * h.z;
             gxs += v3(pick(d0, d1, d2, i, 0) * wyj * wzk, wxi * pick(d0, d1, d2, jj, 1) * wzk, wxi * wyj * pick(d0, d1, d2, k, 2)) * qn;
           }
     }
-    gx += gxs - (kp.inv_dx * s4) * mul_t(g.C, Vw);
+    gx += gxs - (kp.inv_dx * s4) * mul_t(g.C, v3(n0.w, n1.x, n1.y));  // sum_n w_n v_n is the velocity g2p stored in the next slot
     if (GATHER && act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
   }
   __syncwarp();
