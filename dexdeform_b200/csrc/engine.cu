@@ -1921,7 +1921,14 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       s->g2p_tiled = !(e1 && atoi(e1) == 0);  // default: tiled gather
       s->p2gg_tiled = e2 ? atoi(e2) != 0 : cfg->svd_mode == 1;  // default: the staged tile kernel with the fp32 SVD, the flat kernel otherwise
     }
-    s->chunk_max = cfg->chunk_max > 0 ? cfg->chunk_max : 256;  // ~2 thinned chunks per dense brick; measured optimum at config D (profiles/)
+    // Particles per chunk (one warp, one tile).  Large chunks amortise the tile fill / flush (256 is the measured optimum at
+    // config D); a batch that cannot give every resident warp about two chunks gets smaller ones, because a warp walks the
+    // rows of its chunk one after the other and a nearly empty machine is then bound by that latency.
+    if (cfg->chunk_max > 0) s->chunk_max = cfg->chunk_max;
+    else {
+      int warps = std::max(1, s->pb_p2g * s->w_p2g), per_warp = kp.EN / warps;
+      s->chunk_max = per_warp >= 256 ? 256 : std::min(256, std::max(64, (per_warp / 2 + 31) / 32 * 32));
+    }
     int occ_cap = std::min(kp.EN, s->NBtot);
     s->chunk_cap = kp.EN / s->chunk_max + occ_cap + 1;
     DD_ALLOC(s->chunks, sizeof(int4) * s->chunk_cap);
