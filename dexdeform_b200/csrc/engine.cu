@@ -1642,7 +1642,7 @@ struct dd_sim {
   dd_sim_config cfg;
   KP kp;
   int slots;                 // max_steps + 1
-  size_t slot_floats;        // 25 * ENp
+  size_t slot_floats;        // kPlaneFloats * ENp
   float *ckpt = nullptr;     // slots * slot_floats
   float *grad[2] = {nullptr, nullptr};
   int grad_holds[2] = {-1, -1};
