@@ -2,7 +2,13 @@
 //
 // What differs from the reference pipeline (mpm/simulator.py:561-585, integrator.cu):
 //   * particle state lives in float4 SoA planes, one checkpoint slot per substep (x,v,C | F), E environments batched
-//   * compute_svd + p2g are one kernel; U, V, sigma, F~ never touch HBM (the reference writes/reads 120 B/particle)
+//   * compute_svd + p2g are one kernel; F~ and the matrices U, V never touch HBM (the reference writes/reads 120 B/particle).
+//     What the adjoint needs of them is checkpointed compactly per substep: two quaternions, sigma and the affine matrix of the
+//     scatter (64 B), so the backward pass runs no SVD, no QR and no stress evaluation
+//   * tiled kernels: a warp owns a chunk of one 4^3-cell brick and a private 8^3-node shared-memory tile; particles are stored
+//     in 32-wide rows laid out so that the lanes of a row sit in different cells AND different shared-memory bank groups
+//     (no atomics, no bank conflicts); persistent launches hand chunks out through a ticket counter, largest first;
+//     the inputs of the next row are staged with cp.async
 //   * a grid node is one float4 (mv.xyz, m), scattered with one red.global.add.v4.f32 instead of four scalar atomics
 //   * the per-body input velocities (grid_body_v_in, (nb+1)*12 B per node) are not stored: the adjoint re-derives them
 //     from a contact bit-mask (contacts are velocity independent) by replaying the few contacting bodies
