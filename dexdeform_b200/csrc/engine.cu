@@ -140,6 +140,9 @@ DD_DEV void red_add_v4(float4 *addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 DD_DEV int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// a + n b for a stencil offset n in {0,1,2} known after unrolling: nothing, one add or one fma per component (a plain a + b * 0.f
+// costs an fma per component, which IEEE rules keep the compiler from dropping)
+DD_DEV V3 step_n(V3 a, V3 b, int n) { return n == 0 ? a : n == 1 ? a + b : v3(fmaf(b.x, 2.f, a.x), fmaf(b.y, 2.f, a.y), fmaf(b.z, 2.f, a.z)); }
 
 // stencil with the base clamped into the grid (identical to the reference for every in-domain particle)
 DD_DEV Stencil make_stencil_safe(V3 x, const KP &kp) {
@@ -746,12 +749,12 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   auto row = [&](int i, int j, float wxi, float wyj, float exi, float eyj, float4 t0, float4 t1, float4 t2, float4 u0, float4 u1, float4 u2) {
     float wij = wxi * wyj, a1 = exi * wyj, a2 = wxi * eyj;
     if (G2PG) {
-      V3 hij = h0 + H0 * (float)i + H1 * (float)j, hk1 = hij + H2, hk2 = hk1 + H2;
+      V3 hij = step_n(step_n(h0, H0, i), H1, j), hk1 = hij + H2, hk2 = hk1 + H2;
       float q0 = u0.x * hij.x + u0.y * hij.y + u0.z * hij.z, q1 = u1.x * hk1.x + u1.y * hk1.y + u1.z * hk1.z, q2 = u2.x * hk2.x + u2.y * hk2.y + u2.z * hk2.z;
       float Sq = fmaf(wz[2], q2, fmaf(wz[1], q1, wz[0] * q0)), SEq = fmaf(ez[2], q2, fmaf(ez[1], q1, ez[0] * q0));
       gxs.x = fmaf(a1, Sq, gxs.x); gxs.y = fmaf(a2, Sq, gxs.y); gxs.z = fmaf(wij, SEq, gxs.z);
     }
-    V3 vij = base + c0 * (float)i + c1 * (float)j;
+    V3 vij = step_n(step_n(base, c0, i), c1, j);
     V3 A = v3(fmaf(wz[2], t2.x, fmaf(wz[1], t1.x, wz[0] * t0.x)), fmaf(wz[2], t2.y, fmaf(wz[1], t1.y, wz[0] * t0.y)), fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z)));
     V3 B = v3(fmaf(kz2, t2.x, kz1 * t1.x), fmaf(kz2, t2.y, kz1 * t1.y), fmaf(kz2, t2.z, kz1 * t1.z));
     float M = fmaf(wz[2], t2.w, fmaf(wz[1], t1.w, wz[0] * t0.w));
@@ -966,14 +969,14 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
       bool mine = in_tile && rank == r;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        V3 vi = base + c0 * (float)i;
+        V3 vi = step_n(base, c0, i);
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) {
-          V3 vij = vi + c1 * (float)jj;
+          V3 vij = step_n(vi, c1, jj);
           float wij = wx[i] * wy[jj];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            V3 val = vij + c2 * (float)k;
+            V3 val = step_n(vij, c2, k);
             float w = wij * wz[k];
             unsigned a = tbase + 16u * (unsigned)tile_slot(tx + i, ty + jj, tz + k);
             float4 t = lds_v4(a);
@@ -1087,14 +1090,14 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
       bool mine = in_tile && rank == 0;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        V3 hi_ = h0 + H0 * (float)i;
+        V3 hi_ = step_n(h0, H0, i);
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) {
-          V3 hij = hi_ + H1 * (float)jj;
+          V3 hij = step_n(hi_, H1, jj);
           float wij = wx[i] * wy[jj], a1 = ex[i] * wy[jj], a2 = wx[i] * ey[jj];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            V3 h = hij + H2 * (float)k;
+            V3 h = step_n(hij, H2, k);
             float w = wij * wz[k];
             int so = (i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7);
             float4 t = GATHER ? tvrow[so] : make_float4(0.f, 0.f, 0.f, 0.f);
