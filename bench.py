@@ -9,7 +9,8 @@ Workload (N=1 and per rank for N>1, i.e. weak scaling over independent environme
 per-substep checkpoints + 80 substeps backward (loss = -mean(y) of the final state).  Synthetic, seeded.
 
 One JSON line on stdout (rank 0).  `value` = particle-substeps/s with state resident in HBM (CUDA events, max over ranks);
-`e2e` = the same metric through the public host API with pinned host buffers in the timed region; `roofline` = the
+`e2e` = the same metric through the public host API: state, poses and loss gradient uploaded from pinned host buffers every step
+(plus the re-sort), loss taken on the device and read back with the pose gradients; `roofline` = the
 dominant kernel's algorithmic bytes / its device time against the measured HBM peak; `cpu_baseline` = the reference's
 kernels built for the host (oracle/_ref) or the C oracle port on a bounded sample.
 """
@@ -171,19 +172,22 @@ def run_ours(args):
     hx, hv, hF, hC = (pin(sc[k][None]) for k in ("x", "v", "F", "C"))
     hpos, hrot = pin(sc["pos"][:, None]), pin(sc["rot"][:, None])
     hgx = pin(gx_host)
-    x_out = torch.empty((1, n, 3), dtype=torch.float32).pin_memory()
+    x_dev = torch.empty((1, n, 3), dtype=torch.float32, device="cuda")   # final positions stay on the device: the loss is taken there
+    loss_out = torch.empty(1, dtype=torch.float32).pin_memory()
     gp_out = torch.empty((S + 1, 1, nb, 3), dtype=torch.float32).pin_memory()
     gr_out = torch.empty((S + 1, 1, nb, 4), dtype=torch.float32).pin_memory()
     h2d = sum(t.numel() * 4 for t in (hx, hv, hF, hC, hpos, hrot, hgx))
-    d2h = sum(t.numel() * 4 for t in (x_out, gp_out, gr_out))
+    d2h = sum(t.numel() * 4 for t in (loss_out, gp_out, gr_out))
     P = lambda t: t.data_ptr()
 
     def e2e_step():
         sim._check(sim.lib.dd_sim_set_state(sim._h, 0, P(hx), P(hv), P(hF), P(hC), sim.stream))   # H2D + re-sort
         sim._check(sim.lib.dd_sim_set_poses(sim._h, 0, S + 1, P(hpos), P(hrot), sim.stream))
         sim.forward(0, S)
-        sim._check(sim.lib.dd_sim_get_state(sim._h, S, P(x_out), None, None, None, sim.stream))     # D2H, syncs
-        loss = -float(x_out[0, :, 1].mean())                                                          # host-side loss
+        sim._check(sim.lib.dd_sim_get_state(sim._h, S, P(x_dev), None, None, None, sim.stream))     # caller's particle order, on the device
+        loss_out.copy_(-x_dev[0, :, 1].mean(), non_blocking=True)                                     # loss on the device (as GradModel users do), D2H of the scalar
+        torch.cuda.current_stream().synchronize()
+        loss = float(loss_out[0])
         sim.zero_grad(S)
         sim._check(sim.lib.dd_sim_add_state_grad(sim._h, S, P(hgx), None, None, None, sim.stream))
         sim.backward(0, S)

@@ -1687,6 +1687,8 @@ struct dd_sim {
   size_t stage_floats = 0;
   std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;
   long long launches = 0;    // kernels launched (or replayed through graphs) since creation
+  cudaStream_t side = nullptr;  // uploads that may overlap the sort in dd_sim_set_state
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // persistent launch geometry of the tiled kernels (resident blocks per SM x SMs) and which gather variants run
   int pb_p2g = 0, pb_g2pg = 0, pb_g2p = 0, pb_p2gg = 0;
   bool g2p_tiled = false, p2gg_tiled = false, fuse_gather = false;  // fuse_gather: gather half of the g2p adjoint inside k_p2g_grad_tile
@@ -1850,6 +1852,9 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail("dd_sim_create: no CUDA device (dexdeform_b200 has no CPU fallback)");
   dd_sim *s = new dd_sim();
   s->cfg = *cfg;
+  cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
   KP &kp = s->kp;
   kp.E = cfg->n_envs; kp.N = cfg->n_particles; kp.EN = kp.E * kp.N; kp.nb = cfg->n_bodies;
   kp.gx = cfg->grid_x; kp.gy = cfg->grid_y; kp.gz = cfg->grid_z; kp.G = kp.gx * kp.gy * kp.gz;
@@ -1981,6 +1986,9 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
 void dd_sim_destroy(dd_sim *s) {
   if (!s) return;
   for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
+  if (s->side) cudaStreamDestroy(s->side);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
   void *ptrs[] = {s->ckpt, s->grad[0], s->grad[1], s->mat0, s->yield, s->grid, s->grid_v, s->ggrid_v, s->ggrid, s->pos, s->rot, s->gpos, s->grot,
                   s->tfsr, s->args, s->cull, s->perm, s->stage, s->keys, s->keys_alt, s->idx_alt, s->cub_tmp, s->mat_aos,
                   s->chunks, s->chunk_src, s->chunks_alt, s->chunk_src_alt, s->chunk_sort, s->csort_tmp, s->head_pos, s->spos, s->head_flags, s->active_flag, s->active, s->counters, s->sel_tmp, s->gridck, s->gridvck};
@@ -2030,10 +2038,14 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
   if (!x || !v || !F || !C) return fail("dd_sim_set_state: x, v, F, C are all required");
   int EN = s->kp.EN;
   float *sx = s->stage, *sv = sx + 3 * (size_t)EN, *sF = sv + 3 * (size_t)EN, *sC = sF + 9 * (size_t)EN;
+  // positions first: the sort needs nothing else, so v, F and C are copied on a side stream while the sort kernels run
   DD_CUDA(cudaMemcpyAsync(sx, x, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
-  DD_CUDA(cudaMemcpyAsync(sv, v, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
-  DD_CUDA(cudaMemcpyAsync(sF, F, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
-  DD_CUDA(cudaMemcpyAsync(sC, C, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
+  DD_CUDA(cudaEventRecord(s->ev_fork, st));
+  DD_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));  // the staging buffer is free again once earlier work on st is done
+  DD_CUDA(cudaMemcpyAsync(sv, v, sizeof(float) * 3 * EN, cudaMemcpyDefault, s->side));
+  DD_CUDA(cudaMemcpyAsync(sF, F, sizeof(float) * 9 * EN, cudaMemcpyDefault, s->side));
+  DD_CUDA(cudaMemcpyAsync(sC, C, sizeof(float) * 9 * EN, cudaMemcpyDefault, s->side));
+  DD_CUDA(cudaEventRecord(s->ev_join, s->side));
   if (s->cfg.sort_particles) {
     // cell-sorted particle order: environment, 4^3-cell brick, cell.  perm maps sorted -> original index.
     if (s->cfg.tile_mode) DD_CUDA(cudaMemsetAsync(s->active_flag, 0, s->NBtot, st));
@@ -2084,6 +2096,7 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
     }
     for (int k = 0; k < 2; ++k) s->grad_holds[k] = -1;  // gradient slots refer to the previous ordering
   }
+  DD_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   k_pack<<<nblk(EN), kT, 0, st>>>(EN, s->perm, sx, sv, sF, sC, s->slot(f));
   DD_CUDA(cudaGetLastError());
   return 0;
