@@ -171,12 +171,11 @@ def run_ours(args):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     hx, hv, hF, hC = (pin(sc[k][None]) for k in ("x", "v", "F", "C"))
     hpos, hrot = pin(sc["pos"][:, None]), pin(sc["rot"][:, None])
-    hgx = pin(gx_host)
     x_dev = torch.empty((1, n, 3), dtype=torch.float32, device="cuda")   # final positions stay on the device: the loss is taken there
     loss_out = torch.empty(1, dtype=torch.float32).pin_memory()
     gp_out = torch.empty((S + 1, 1, nb, 3), dtype=torch.float32).pin_memory()
     gr_out = torch.empty((S + 1, 1, nb, 4), dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * 4 for t in (hx, hv, hF, hC, hpos, hrot, hgx))
+    h2d = sum(t.numel() * 4 for t in (hx, hv, hF, hC, hpos, hrot))
     d2h = sum(t.numel() * 4 for t in (loss_out, gp_out, gr_out))
     P = lambda t: t.data_ptr()
 
@@ -189,7 +188,7 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()
         loss = float(loss_out[0])
         sim.zero_grad(S)
-        sim._check(sim.lib.dd_sim_add_state_grad(sim._h, S, P(hgx), None, None, None, sim.stream))
+        sim._check(sim.lib.dd_sim_add_state_grad(sim._h, S, gx_dev.data_ptr(), None, None, None, sim.stream))  # d loss / d x, produced on the device like the loss
         sim.backward(0, S)
         sim._check(sim.lib.dd_sim_get_pose_grads(sim._h, 0, S + 1, P(gp_out), P(gr_out), sim.stream))
         return loss
