@@ -1405,7 +1405,7 @@ __global__ void k_pack_mat(int EN, const int *__restrict__ perm, const float *__
   yield[i] = mly[3 * s + 2];
 }
 // sort key of a particle: environment-major, then 4x4x4-cell brick (x-major like the grid), then cell inside the brick
-__global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__restrict__ keys, int *__restrict__ idx, char *__restrict__ active_flag) {
+__global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__restrict__ keys, int *__restrict__ idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kp.EN) return;
   V3 x = ld_v3(x_aos, i);
@@ -1418,24 +1418,30 @@ __global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__
   unsigned cell = (unsigned)tile_group(lx + 1, ly + 1, lz + 1) << 3 | (unsigned)(lx << 1 | ly >> 1);
   keys[i] = (unsigned)(i / kp.N) * (unsigned)kp.G + (brick << 6 | cell);
   idx[i] = i;
-  if (active_flag) {  // active region = bricks reached by the stencil [base, base+2] padded by one node on each side
-    int nbx = kp.gx >> 2, NB = nbx * nby * nbz, env = i / kp.N;
-    int b0x = clampi(cx, 0, kp.gx - 3), b0y = clampi(cy, 0, kp.gy - 3), b0z = clampi(cz, 0, kp.gz - 3);
-    int lx = max(b0x - 1, 0) >> 2, hx = min((b0x + 3) >> 2, nbx - 1), ly = max(b0y - 1, 0) >> 2, hy = min((b0y + 3) >> 2, nby - 1),
-        lz = max(b0z - 1, 0) >> 2, hz = min((b0z + 3) >> 2, nbz - 1);
-    for (int x_ = lx; x_ <= hx; ++x_)
-      for (int y_ = ly; y_ <= hy; ++y_)
-        for (int z_ = lz; z_ <= hz; ++z_) {  // test first: a million particles mark a few thousand flags
-          char *fl = active_flag + (size_t)env * NB + (x_ * nby + y_) * nbz + z_;
-          if (!*fl) *fl = 1;
-        }
-  }
 }
 
-__global__ void k_mark_heads(int EN, const unsigned *__restrict__ keys, char *__restrict__ flags) {
+// On the sorted keys: flags the first particle of every brick, and -- once per occupied cell, the active region depends on the
+// cell only -- marks the bricks reached by that cell's stencil [base, base + 2] padded by one node on each side.
+__global__ void k_mark_heads(KP kp, const unsigned *__restrict__ keys, char *__restrict__ flags, char *__restrict__ active_flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= EN) return;
-  flags[i] = (i == 0) || (keys[i] >> 6) != (keys[i - 1] >> 6);
+  if (i >= kp.EN) return;
+  unsigned key = keys[i], prev = i ? keys[i - 1] : ~key;
+  flags[i] = (i == 0) || (key >> 6) != (prev >> 6);
+  if (key == prev) return;
+  int nbx = kp.gx >> 2, nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = nbx * nby * nbz;
+  int env = (int)(key / (unsigned)kp.G), within = (int)(key - (unsigned)env * (unsigned)kp.G), brick = within >> 6, code = within & 63;
+  // invert the in-brick code of k_sort_keys: group g = (lz + 4 ly + 2 lx + 7) mod 8, sub = lx << 1 | ly >> 1
+  int g = code >> 3, lx = (code >> 1) & 3, t = (g - 2 * lx - 7) & 7, lz = t & 3, ly = (code & 1) << 1 | t >> 2;
+  int cx = (brick / (nby * nbz)) * 4 + lx, cy = ((brick / nbz) % nby) * 4 + ly, cz = (brick % nbz) * 4 + lz;
+  int b0x = clampi(cx, 0, kp.gx - 3), b0y = clampi(cy, 0, kp.gy - 3), b0z = clampi(cz, 0, kp.gz - 3);
+  int x0 = max(b0x - 1, 0) >> 2, x1 = min((b0x + 3) >> 2, nbx - 1), y0 = max(b0y - 1, 0) >> 2, y1 = min((b0y + 3) >> 2, nby - 1),
+      z0 = max(b0z - 1, 0) >> 2, z1 = min((b0z + 3) >> 2, nbz - 1);
+  for (int x_ = x0; x_ <= x1; ++x_)
+    for (int y_ = y0; y_ <= y1; ++y_)
+      for (int z_ = z0; z_ <= z1; ++z_) {
+        char *fl = active_flag + (size_t)env * NB + (x_ * nby + y_) * nbz + z_;
+        if (!*fl) *fl = 1;
+      }
 }
 // one thread per occupied brick: split its particles into `nsub` chunks.
 // Chunk c takes the cell-sorted ranks r = c (mod nsub) of the brick -- a thinned copy of the whole brick, so that the
@@ -2049,14 +2055,14 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
   if (s->cfg.sort_particles) {
     // cell-sorted particle order: environment, 4^3-cell brick, cell.  perm maps sorted -> original index.
     if (s->cfg.tile_mode) DD_CUDA(cudaMemsetAsync(s->active_flag, 0, s->NBtot, st));
-    k_sort_keys<<<nblk(EN), kT, 0, st>>>(s->kp, sx, s->keys, s->idx_alt, s->cfg.tile_mode ? s->active_flag : nullptr);
+    k_sort_keys<<<nblk(EN), kT, 0, st>>>(s->kp, sx, s->keys, s->idx_alt);
     int bits = 1;
     while (bits < 32 && (1ull << bits) < (unsigned long long)s->kp.E * s->kp.G) ++bits;
     DD_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_tmp, s->cub_bytes, s->keys, s->keys_alt, s->idx_alt, s->perm, EN, 0, bits, st));
     if (s->cfg.tile_mode) {
       const KP &kp = s->kp;
       int host[4] = {0, 0, 0, 0};
-      k_mark_heads<<<nblk(EN), kT, 0, st>>>(EN, s->keys_alt, s->head_flags);
+      k_mark_heads<<<nblk(EN), kT, 0, st>>>(kp, s->keys_alt, s->head_flags, s->active_flag);
       DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, s->counters + 2, EN, st));
       DD_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(int) * 2, st));
       DD_CUDA(cudaMemsetAsync(s->counters + 4, 0, sizeof(int) * 2, st));  // chunk tickets: start clean even after an aborted launch
