@@ -599,8 +599,14 @@ constexpr int kTileWarps = 4;        // chunks per thread block (launch-bound hi
 constexpr int kStageP2G = 9;         // staged float4 slots per lane: p2g_tile
 constexpr int kStageG2PG = 7;        // g2p_grad_tile
 // a chunk is stored as R rows of 32 particles (the last row holds the remaining `last`); row j starts at start + 32 j
-struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, last, bx, by, bz; };
-DD_DEV int row_lanes(const ChunkGeom &c, int j) { return j < c.R - 1 ? 32 : c.last; }
+struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, last, bx, by, bz; unsigned lastmask; };
+// lanes (columns) of the short last row are given by a bit mask chosen at sort time (the columns whose bank group has particles
+// left over after R - 1 full rows), not by a prefix: its particles are stored compacted in lane order
+DD_DEV bool lane_on(const ChunkGeom &c, int j, int lane) { return j < c.R - 1 || (c.lastmask >> lane & 1u); }
+DD_DEV int row_pos(const ChunkGeom &c, int j, int lane) {  // storage position of (row j, lane), or the chunk's first particle for an idle lane
+  if (j < c.R - 1) return c.start + 32 * j + lane;
+  return (c.lastmask >> lane & 1u) ? c.start + 32 * j + __popc(c.lastmask & ((1u << lane) - 1u)) : c.start;
+}
 DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
   ChunkGeom c;
   int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
@@ -611,6 +617,7 @@ DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
   c.start = ch.y; c.cnt = ch.z;
   c.R = (c.cnt + 31) >> 5;
   c.last = c.cnt - 32 * (c.R - 1);
+  c.lastmask = (unsigned)ch.w;
   return c;
 }
 // Which of the 27 bricks around the chunk's home brick are active (bit (dx+1)*9 + (dy+1)*3 + (dz+1)); whole warp calls.
@@ -930,17 +937,16 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
   };
   // (no look-ahead across chunks: a warp that holds a chunk in reserve lengthens the tail of the launch -- measured)
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
-  int4 ch = chunks[ci];
-  stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
-  ChunkGeom cg = chunk_geom(ch, kp);
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  stage_row(row_pos(cg, 0, lane));
   unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   float4 *g = grid + (size_t)cg.env * kp.G;
   for (int j = 0; j < cg.R; ++j) {
-    bool act = lane < row_lanes(cg, j);
-    int p = act ? cg.start + 32 * j + lane : cg.start;  // idle lanes shadow a valid particle, contribute nothing
+    bool act = lane_on(cg, j, lane);
+    int p = row_pos(cg, j, lane);  // idle lanes shadow a valid particle, contribute nothing
     cp_async_wait_all();
     float4 r0 = stage[0], r1 = stage[32], r2 = stage[64], r3 = stage[96], r4 = stage[128], r5 = stage[160], q = stage[192], m0 = stage[224], r8 = stage[256], qu;
-    if (j + 1 < cg.R) stage_row(lane < row_lanes(cg, j + 1) ? cg.start + 32 * (j + 1) + lane : cg.start);
+    if (j + 1 < cg.R) stage_row(row_pos(cg, j + 1, lane));
     XVC s;
     s.x = v3(r0.x, r0.y, r0.z);
     s.v = v3(r0.w, r1.x, r1.y);
@@ -1043,20 +1049,19 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
   };
   // (no look-ahead across chunks: a warp that holds a chunk in reserve lengthens the tail of the launch -- measured)
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
-  int4 ch = chunks[ci];
-  stage_row(ch.y + (lane < min(ch.z, 32) ? lane : 0));
-  ChunkGeom cg = chunk_geom(ch, kp);
+  ChunkGeom cg = chunk_geom(chunks[ci], kp);
+  stage_row(row_pos(cg, 0, lane));
   unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   size_t goff = (size_t)cg.env * kp.G;
   if (GATHER) fill_tile(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
   else for (int n = lane; n < kTileN; n += 32) tg[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
-    bool act = lane < row_lanes(cg, j);
-    int p = act ? cg.start + 32 * j + lane : cg.start;
+    bool act = lane_on(cg, j, lane);
+    int p = row_pos(cg, j, lane);
     cp_async_wait_all();
     float4 a = stage[0], n0 = stage[32], n1 = stage[64], g0_ = stage[96], g1_ = stage[128], g2_ = stage[160], g3_ = stage[192];
-    if (j + 1 < cg.R) stage_row(lane < row_lanes(cg, j + 1) ? cg.start + 32 * (j + 1) + lane : cg.start);
+    if (j + 1 < cg.R) stage_row(row_pos(cg, j + 1, lane));
     V3 x = v3(a.x, a.y, a.z);
     XVC g;
     g.x = v3(g0_.x, g0_.y, g0_.z);
@@ -1201,21 +1206,21 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
   P2ggStager stager{kp, cur, nxt, gin, yield, mat0, gout, tile + kTileN + lane, -1};
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
     ChunkGeom cg = chunk_geom(chunks[ci], kp);
-    if (STAGED) { int p0 = cg.start + (lane < row_lanes(cg, 0) ? lane : 0); stager.stage1(p0); stager.stage2(p0); }
+    if (STAGED) { int p0 = row_pos(cg, 0, lane); stager.stage1(p0); stager.stage2(p0); }
     fill_tile(tile, ggrid + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
     if (G2PG) fill_tile(tile_v, grid_v + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
     __syncwarp();
     for (int j = 0; j < cg.R; ++j) {
       if (STAGED) {
         // every lane takes part (idle lanes of a short last row shadow the chunk's first particle and write nothing)
-        bool act = lane < row_lanes(cg, j);
-        stager.p_next = j + 1 < cg.R ? cg.start + (lane < row_lanes(cg, j + 1) ? 32 * (j + 1) + lane : 0) : -1;
+        bool act = lane_on(cg, j, lane);
+        stager.p_next = j + 1 < cg.R ? row_pos(cg, j + 1, lane) : -1;
         cp_async_wait_all();
-        if (act) p2g_grad_particle<SVD, true, G2PG, P2ggStager>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v, stager.stg, stager);
+        if (act) p2g_grad_particle<SVD, true, G2PG, P2ggStager>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v, stager.stg, stager);
         else { stager.phase1_done(); stager.phase2_done(); }
       } else {
-        if (lane >= row_lanes(cg, j)) continue;
-        p2g_grad_particle<SVD, true, G2PG>(kp, cg.start + 32 * j + lane, cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v);
+        if (!lane_on(cg, j, lane)) continue;
+        p2g_grad_particle<SVD, true, G2PG>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v);
       }
     }
     __syncwarp();
@@ -1237,8 +1242,8 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
   fill_tile(tile, genv, kp, cg.ox, cg.oy, cg.oz, lane);
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
-    if (lane >= row_lanes(cg, j)) continue;
-    int p = cg.start + 32 * j + lane;
+    if (!lane_on(cg, j, lane)) continue;
+    int p = row_pos(cg, j, lane);
     float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
     V3 x = v3(a.x, a.y, a.z);
     Stencil st = make_stencil_safe(x, kp);
@@ -1469,7 +1474,7 @@ __global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_p
 // cell-sorted list, so the lanes of a round also sit in different cells (no read-modify-write collisions).  Groups are
 // not equally populated: what does not fit into a group's own columns spills into the free slots of the others (a few
 // percent of the particles, costing at most one extra wavefront where they sit).  One warp per chunk.
-__global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src, const unsigned *__restrict__ keys_sorted,
+__global__ void k_interleave(KP kp, int nchunks, int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src, const unsigned *__restrict__ keys_sorted,
                              const int *__restrict__ perm_in, int *__restrict__ perm_out, int *__restrict__ spos) {
   int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (ci >= nchunks) return;
@@ -1488,7 +1493,21 @@ __global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks
     gs = lo;
   }
   int g_cnt = __shfl_down_sync(full, gs, 1) - gs;                        // valid on lanes 0..7
-  int cap = lane < cg.last ? R : R - 1;                                  // capacity of column `lane`
+  // The short last row: its `last` slots go to the columns whose group still has particles after R - 1 full rows (one more per
+  // quarter-warp, up to four per group), so that the idle lanes of that row absorb the imbalance between the groups instead of
+  // spills into foreign columns; what is left goes to the lowest free columns.
+  int need = __shfl_sync(full, g_cnt, lane & 7) - 4 * (R - 1);           // of this column's group
+  int want = need > (lane >> 3) ? 1 : 0, pre = want;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(full, pre, o); if (lane >= o) pre += t; }
+  bool bit = want && pre - want < cg.last;
+  int given = __popc(__ballot_sync(full, bit)), nb2 = bit ? 0 : 1, pre2 = nb2;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(full, pre2, o); if (lane >= o) pre2 += t; }
+  bit = bit || (nb2 && pre2 - nb2 < cg.last - given);
+  unsigned lastmask = __ballot_sync(full, bit);
+  if (lane == 0) chunks[ci].w = (int)lastmask;
+  int cap = R - 1 + (bit ? 1 : 0);                                       // capacity of column `lane`
   int cap1 = __shfl_sync(full, cap, (lane & 7) + 8), cap2 = __shfl_sync(full, cap, (lane & 7) + 16), cap3 = __shfl_sync(full, cap, (lane & 7) + 24);
   int cap0 = __shfl_sync(full, cap, lane & 7);
   int capg = cap0 + cap1 + cap2 + cap3;                                  // capacity of group (lane & 7)
@@ -1525,7 +1544,7 @@ __global__ void k_interleave(KP kp, int nchunks, const int4 *__restrict__ chunks
       if (spilled && sidx >= fb && sidx < fb + ff) { col = l; row = uu + sidx - fb; }
     }
     if (live) {
-      int pos = cg.start + 32 * row + col;
+      int pos = cg.start + 32 * row + (row < R - 1 ? col : __popc(lastmask & ((1u << col) - 1u)));
       perm_out[pos] = perm_in[from];
       spos[from] = pos;  // sorted rank -> storage position, for the flat gather kernels
     }
