@@ -8,7 +8,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libmaniskill_mpm.so")
 SOURCES = ["abi1_kernels.cu", "engine.cu", "fk.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--use_fast_math=false",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-deprecated-declarations", "-shared"]
 
 
 def _stale():

@@ -70,6 +70,13 @@ struct KP {            // kernel parameters shared by all kernels
   float g0, g1, g2;    // gravity (already scaled as the caller wants it)
 };
 
+struct SegView {       // device-resident description of one particle ordering (a "segment" of the rollout, see dd_sim)
+  const int4 *chunks;  // (brick, start, count, last-row lane mask), largest first
+  int *cnt;            // [0] chunks  [1] active bricks  [2] occupied bricks
+  int *active;         // active brick list; grows when a particle's stencil reaches a new brick (activate_bricks)
+  int *flags;          // per brick: 0 inactive, 1 active, 2 being activated
+};
+
 // ---- particle planes ----------------------------------------------------------------------------------------
 // slot layout (floats): [0,4EN) P0=(x.x,x.y,x.z,v.x)  [4EN,8EN) P1=(v.y,v.z,C00,C01)  [8EN,12EN) P2=(C02,C10,C11,C12)
 //                       [12EN,16EN) P3=(C20,C21,C22,0) [16EN,20EN) F0=(F00..F10) [20EN,24EN) F1=(F11..F21) [24EN,25EN) F2=F22
@@ -621,13 +628,13 @@ DD_DEV ChunkGeom chunk_geom(int4 ch, const KP &kp) {
   return c;
 }
 // Which of the 27 bricks around the chunk's home brick are active (bit (dx+1)*9 + (dy+1)*3 + (dz+1)); whole warp calls.
-DD_DEV unsigned chunk_active_mask(const char *__restrict__ active_flag, const ChunkGeom &cg, const KP &kp, int lane) {
+DD_DEV unsigned chunk_active_mask(const int *active_flag, const ChunkGeom &cg, const KP &kp, int lane) {
   int nbx = kp.gx >> 2, nby = kp.gy >> 2, nbz = kp.gz >> 2;
   bool on = false;
   if (lane < 27) {
     int x = cg.bx + lane / 9 - 1, y = cg.by + (lane / 3) % 3 - 1, z = cg.bz + lane % 3 - 1;
     if ((unsigned)x < (unsigned)nbx && (unsigned)y < (unsigned)nby && (unsigned)z < (unsigned)nbz)
-      on = active_flag[(size_t)cg.env * nbx * nby * nbz + (x * nby + y) * nbz + z] != 0;
+      on = *(const volatile int *)(active_flag + (size_t)cg.env * nbx * nby * nbz + (x * nby + y) * nbz + z) == 1;
   }
   return __ballot_sync(0xffffffffu, on);
 }
@@ -665,19 +672,56 @@ DD_DEV int next_chunk(int *sched, int lane) {
 DD_DEV void chunks_done(int *sched, int lane) {
   if (lane == 0 && atomicAdd(sched + 1, 1) == (int)(gridDim.x * (blockDim.x >> 5)) - 1) { sched[0] = 0; sched[1] = 0; }
 }
-// The active region is exactly the set of bricks some particle's stencil (+1 node of slack) touched at the last sort.  A
-// particle whose stencil now reaches a brick outside it has out-run the region: its mass would land on nodes no grid
-// kernel processes, so the step is flagged invalid (reported at the next sync).  (tx,ty,tz) = stencil base in tile coordinates.
-DD_DEV void check_active(unsigned amask, int tx, int ty, int tz, int *overflow) {
-  bool ok = (unsigned)(tx + 3) <= 9u && (unsigned)(ty + 3) <= 9u && (unsigned)(tz + 3) <= 9u;  // inside the 3x3x3 brick neighbourhood
-  if (ok && amask != 0x7ffffffu) {  // (warp-uniform) some neighbour brick is inactive: test the bricks this stencil needs
-    int ax = (tx + 3) >> 2, bx = (tx + 5) >> 2, ay = (ty + 3) >> 2, by = (ty + 5) >> 2, az = (tz + 3) >> 2, bz = (tz + 5) >> 2;
-    unsigned need = 0u;
-    need |= 1u << (ax * 9 + ay * 3 + az); need |= 1u << (ax * 9 + ay * 3 + bz); need |= 1u << (ax * 9 + by * 3 + az); need |= 1u << (ax * 9 + by * 3 + bz);
-    need |= 1u << (bx * 9 + ay * 3 + az); need |= 1u << (bx * 9 + ay * 3 + bz); need |= 1u << (bx * 9 + by * 3 + az); need |= 1u << (bx * 9 + by * 3 + bz);
-    ok = (need & ~amask) == 0u;
+// The active region starts as the set of bricks some particle's stencil (+1 node of slack) touched at the last sort and GROWS
+// while a segment runs: a particle whose stencil reaches a brick outside it activates that brick (k_p2g_tile is the first
+// kernel of a substep to see a new position).  Activation = claim the brick's flag (0 -> 2), zero its nodes in this substep's
+// scatter target (stale data of an earlier rollout may sit there), append it to the active list the grid kernels walk, publish
+// (flag = 1).  The list only grows, so every later kernel of the segment -- forward or adjoint -- covers the brick.
+// (tx,ty,tz) = stencil base in tile coordinates; returns true if this lane's stencil needs a brick the chunk's mask lacks.
+DD_DEV bool stencil_misses(unsigned amask, int tx, int ty, int tz) {
+  bool near = (unsigned)(tx + 3) <= 9u && (unsigned)(ty + 3) <= 9u && (unsigned)(tz + 3) <= 9u;  // inside the 3x3x3 brick neighbourhood
+  if (!near) return true;
+  if (amask == 0x7ffffffu) return false;
+  int ax = (tx + 3) >> 2, bx = (tx + 5) >> 2, ay = (ty + 3) >> 2, by = (ty + 5) >> 2, az = (tz + 3) >> 2, bz = (tz + 5) >> 2;
+  unsigned need = 0u;
+  need |= 1u << (ax * 9 + ay * 3 + az); need |= 1u << (ax * 9 + ay * 3 + bz); need |= 1u << (ax * 9 + by * 3 + az); need |= 1u << (ax * 9 + by * 3 + bz);
+  need |= 1u << (bx * 9 + ay * 3 + az); need |= 1u << (bx * 9 + ay * 3 + bz); need |= 1u << (bx * 9 + by * 3 + az); need |= 1u << (bx * 9 + by * 3 + bz);
+  return (need & ~amask) != 0u;
+}
+// whole warp calls; `miss` marks the lanes whose stencil (base node sbx,sby,sbz, already clamped into the grid) needs activation
+DD_DEV void activate_bricks(const KP &kp, int env, bool miss, int sbx, int sby, int sbz, int *flags, int *active, int *cnt, float4 *grid_env, int lane) {
+  const unsigned full = 0xffffffffu;
+  int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
+  unsigned todo = __ballot_sync(full, miss);
+  while (todo) {
+    int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    int sx = __shfl_sync(full, sbx, src), sy = __shfl_sync(full, sby, src), sz = __shfl_sync(full, sbz, src);
+    for (int c = 0; c < 8; ++c) {
+      int X = (sx + ((c & 1) ? 2 : 0)) >> 2, Y = (sy + ((c & 2) ? 2 : 0)) >> 2, Z = (sz + ((c & 4) ? 2 : 0)) >> 2;
+      int b = env * NB + (X * nby + Y) * nbz + Z;
+      int state = 1;
+      if (lane == 0) {
+        state = *(volatile int *)(flags + b);
+        if (state != 1) state = atomicCAS(flags + b, 0, 2);
+      }
+      state = __shfl_sync(full, state, 0);
+      if (state == 0) {  // ours to activate
+        for (int n = lane; n < 64; n += 32)
+          grid_env[((X * 4 + (n >> 4)) * kp.gy + Y * 4 + ((n >> 2) & 3)) * kp.gz + Z * 4 + (n & 3)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          active[atomicAdd(cnt + 1, 1)] = b;
+          __threadfence();
+          atomicExch(flags + b, 1);
+        }
+      } else if (state == 2) {  // another warp is zeroing it right now
+        if (lane == 0) while (atomicAdd(flags + b, 0) == 2) {}
+      }
+      __syncwarp();
+    }
   }
-  if (!ok) atomicOr(overflow, 1);
 }
 
 // TILE = true: node adjoints are read from a swizzled shared-memory tile at (tx,ty,tz); otherwise from the dense grid
@@ -692,7 +736,7 @@ constexpr int kStageP2GG = 16;  // 0 x|v  1 v|C  2 material  3-5 affine, sigma |
 template <int SVD, bool TILE, bool G2PG = false, class Hook = NoHook>
 DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur, const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                               const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *tile, int ox, int oy, int oz,
-                              const float *__restrict__ gin, float *__restrict__ gout, int *overflow, const float4 *tile_v = nullptr,
+                              const float *__restrict__ gin, float *__restrict__ gout, const float4 *tile_v = nullptr,
                               const float4 *__restrict__ grid_v = nullptr, const float4 *stg = nullptr, const Hook &hook = Hook()) {
   // svd_mode 1: the gather needs only x, v, the mass and the affine matrix the forward pass left in the next slot; everything
   // else (F, C, the SVD factors, the incoming F gradient) is loaded after the gather so that it does not sit in registers
@@ -904,7 +948,7 @@ __global__ void __launch_bounds__(kT, DD_LB_P2G_GRAD) k_p2g_grad(KP kp, const in
   int p = blockIdx.x * kT + threadIdx.x;
   if (p >= kp.EN) return;
   (void)spos;  // measured: strided state loads cost this kernel more than the gather locality gains
-  p2g_grad_particle<SVD, false>(kp, p, cur, nxt, mat0, yield, ggrid, nullptr, 0, 0, 0, gin, gout, nullptr);
+  p2g_grad_particle<SVD, false>(kp, p, cur, nxt, mat0, yield, ggrid, nullptr, 0, 0, 0, gin, gout);
 }
 
 // ================================================================================================ tiled kernels
@@ -917,13 +961,15 @@ __global__ void __launch_bounds__(kT, DD_LB_P2G_GRAD) k_p2g_grad(KP kp, const in
 // touched node instead of one per (particle, node).
 
 template <int SVD, bool WRITE_F>
-__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP kp, SegView sg, const float *__restrict__ cur,
                                                                  float *__restrict__ nxt, const float4 *__restrict__ mat0,
-                                                                 const float *__restrict__ yield, float4 *__restrict__ grid, const char *__restrict__ active_flag, int *overflow, int *sched) {
+                                                                 const float *__restrict__ yield, float4 *__restrict__ grid, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 *tile = dd_smem + warp * (kTileN + kStageP2G * 32), *stage = tile + kTileN + lane;
   unsigned tbase = smem_u32(tile);
+  const int nchunks = sg.cnt[0];
+  const int4 *__restrict__ chunks = sg.chunks;
   for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   auto stage_row = [&](int p) {  // x,v,C | 8 of F | quaternion | material: 8 float4; then F22 and the yield stress
@@ -939,7 +985,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   stage_row(row_pos(cg, 0, lane));
-  unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
+  unsigned amask = chunk_active_mask(sg.flags, cg, kp, lane);
   float4 *g = grid + (size_t)cg.env * kp.G;
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane_on(cg, j, lane);
@@ -962,7 +1008,13 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     V3 base = m * s.v - (c0 * st.fx.x + c1 * st.fx.y + c2 * st.fx.z);  // value at node offset (0,0,0); +c_a per step along axis a
     float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
     int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
-    if (act) check_active(amask, tx, ty, tz, overflow);
+    {  // (rare) the stencil reaches a brick outside the active region: activate it before anything lands there
+      bool miss = act && stencil_misses(amask, tx, ty, tz);
+      if (__any_sync(0xffffffffu, miss)) {
+        activate_bricks(kp, cg.env, miss, st.bx, st.by, st.bz, sg.flags, sg.active, sg.cnt, g, lane);
+        amask = chunk_active_mask(sg.flags, cg, kp, lane);
+      }
+    }
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -1028,15 +1080,17 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
 //   d/d v_n  = w_n h_n ;  dL/dx = -(4/dx^2) gC'^T (sum w_n v_n) + sum gradN_n (v_n . h_n)
 // GATHER = false: scatter only (one tile); the gather half then runs inside k_p2g_grad_tile<.., true>
 template <bool GATHER>
-__global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD_LB_G2PG_SCATTER) k_g2p_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+__global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD_LB_G2PG_SCATTER) k_g2p_grad_tile(KP kp, SegView sg, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout,
-                                                                      float4 *__restrict__ ggrid_v, const char *__restrict__ active_flag, int *overflow, int *sched) {
+                                                                      float4 *__restrict__ ggrid_v, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kStage = kStageG2PG;  // staged float4s per particle: x | next (x,v) | incoming (gx, gv, gC)
   float4 *tv = dd_smem + warp * ((GATHER ? 2 : 1) * kTileN + kStage * 32), *tg = GATHER ? tv + kTileN : tv, *stage = tg + kTileN + lane;
   unsigned vbase = smem_u32(tv), gbase = smem_u32(tg);
+  const int nchunks = sg.cnt[0];
+  const int4 *__restrict__ chunks = sg.chunks;
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
   auto stage_row = [&](int p) {
@@ -1051,7 +1105,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   stage_row(row_pos(cg, 0, lane));
-  unsigned amask = chunk_active_mask(active_flag, cg, kp, lane);
   size_t goff = (size_t)cg.env * kp.G;
   if (GATHER) fill_tile(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
   else for (int n = lane; n < kTileN; n += 32) tg[n] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1081,8 +1134,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
     V3 H0 = v3(g.C.a00, g.C.a10, g.C.a20) * s4, H1 = v3(g.C.a01, g.C.a11, g.C.a21) * s4, H2 = v3(g.C.a02, g.C.a12, g.C.a22) * s4;
     V3 h0 = gnv - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
     int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
-    if (act) check_active(amask, tx, ty, tz, overflow);
-    bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
+    bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;  // (every brick this stencil needs was activated by the forward pass)
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
     int rank = __popc(peers & ((1u << lane) - 1u));
@@ -1195,15 +1247,17 @@ struct P2ggStager {
 };
 
 template <int SVD, bool G2PG>
-__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
+__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_tile(KP kp, SegView sg, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                                                                       const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *__restrict__ grid_v,
-                                                                      const float *__restrict__ gin, float *__restrict__ gout, int *overflow, int *sched) {
+                                                                      const float *__restrict__ gin, float *__restrict__ gout, int *sched) {
   extern __shared__ float4 dd_smem[];
   constexpr bool STAGED = SVD == 1 && !G2PG;
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 *tile = dd_smem + warp * ((G2PG ? 2 : 1) * kTileN + (STAGED ? kStageP2GG * 32 : 0)), *tile_v = tile + kTileN;
   P2ggStager stager{kp, cur, nxt, gin, yield, mat0, gout, tile + kTileN + lane, -1};
+  const int nchunks = sg.cnt[0];
+  const int4 *__restrict__ chunks = sg.chunks;
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
     ChunkGeom cg = chunk_geom(chunks[ci], kp);
     if (STAGED) { int p0 = row_pos(cg, 0, lane); stager.stage1(p0); stager.stage2(p0); }
@@ -1216,11 +1270,11 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
         bool act = lane_on(cg, j, lane);
         stager.p_next = j + 1 < cg.R ? row_pos(cg, j + 1, lane) : -1;
         cp_async_wait_all();
-        if (act) p2g_grad_particle<SVD, true, G2PG, P2ggStager>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v, stager.stg, stager);
+        if (act) p2g_grad_particle<SVD, true, G2PG, P2ggStager>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, tile_v, grid_v, stager.stg, stager);
         else { stager.phase1_done(); stager.phase2_done(); }
       } else {
         if (!lane_on(cg, j, lane)) continue;
-        p2g_grad_particle<SVD, true, G2PG>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, overflow, tile_v, grid_v);
+        p2g_grad_particle<SVD, true, G2PG>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, tile_v, grid_v);
       }
     }
     __syncwarp();
@@ -1229,11 +1283,13 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
 }
 
 // g2p on tiles: the 27 node velocities come from a shared-memory copy of the brick's neighbourhood
-__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP kp, int nchunks, const int4 *__restrict__ chunks, const float *__restrict__ cur,
-                                                                 float *__restrict__ nxt, const float4 *__restrict__ grid_v, int *overflow, int *sched) {
+__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP kp, SegView sg, const float *__restrict__ cur,
+                                                                 float *__restrict__ nxt, const float4 *__restrict__ grid_v, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 *tile = dd_smem + warp * kTileN;
+  const int nchunks = sg.cnt[0];
+  const int4 *__restrict__ chunks = sg.chunks;
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx;
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
@@ -1276,13 +1332,15 @@ DD_DEV int brick_node(int brick, int local, const KP &kp, int &env, int &gx_, in
   gx_ = (b / (nby * nbz)) * 4 + (local >> 4); gy_ = ((b / nbz) % nby) * 4 + ((local >> 2) & 3); gz_ = (b % nbz) * 4 + (local & 3);
   return env * kp.G + (gx_ * kp.gy + gy_) * kp.gz + gz_;
 }
-__global__ void __launch_bounds__(kT) k_zero_bricks(KP kp, int nactive, const int *__restrict__ active, float4 *a, float4 *b) {
-  int t = blockIdx.x * kT + threadIdx.x;
-  if (t >= nactive * 64) return;
-  int env, x, y, z;
-  int node = brick_node(active[t >> 6], t & 63, kp, env, x, y, z);
-  a[node] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (b) b[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+// (the active-brick count lives in device memory, cnt[1]: launches use a fixed upper-bound grid and stride over the list)
+__global__ void __launch_bounds__(kT) k_zero_bricks(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *a, float4 *b) {
+  int total = cnt[1] * 64;
+  for (int t = blockIdx.x * kT + threadIdx.x; t < total; t += gridDim.x * kT) {
+    int env, x, y, z;
+    int node = brick_node(active[t >> 6], t & 63, kp, env, x, y, z);
+    a[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b) b[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 // Four bricks (64 nodes each) per block.  Each 64-thread group first copies its environment's body poses into shared
 // memory and builds a 64-bit mask of the bodies whose activation sphere reaches the brick's bounding box at all; the
@@ -1292,9 +1350,11 @@ struct GridSm {
   float cull[64];
   unsigned long long cand[4];
 };
+DD_DEV void stage_shapes(GridSm &sm, const KP &kp, const BodyTables &bt) {
+  if ((int)threadIdx.x < kp.nb) { sm.tfsr[threadIdx.x] = bt.tfsr[threadIdx.x]; sm.args[threadIdx.x] = bt.args[threadIdx.x]; sm.cull[threadIdx.x] = bt.cull[threadIdx.x]; }
+}
 DD_DEV unsigned long long stage_bodies(GridSm &sm, const KP &kp, const BodyTables &bt, bool valid, int brick, int grp, int g, BodyTables &view) {
   if (threadIdx.x < 4) sm.cand[threadIdx.x] = 0ull;
-  if ((int)threadIdx.x < kp.nb) { sm.tfsr[threadIdx.x] = bt.tfsr[threadIdx.x]; sm.args[threadIdx.x] = bt.args[threadIdx.x]; sm.cull[threadIdx.x] = bt.cull[threadIdx.x]; }
   __syncthreads();
   int nby = kp.gy >> 2, nbz = kp.gz >> 2, NB = (kp.gx >> 2) * nby * nbz;
   int env = valid ? brick / NB : 0, bb = valid ? brick - env * NB : 0;
@@ -1319,49 +1379,59 @@ DD_DEV unsigned long long stage_bodies(GridSm &sm, const KP &kp, const BodyTable
 
 // zero_next: the (distinct) scatter target of the NEXT substep, cleared here so that no separate zeroing pass is needed;
 // zero_self: clear this substep's (m, mv) after use (forward-only mode with a single grid buffer)
-__global__ void __launch_bounds__(kT, 4) k_grid_b(KP kp, int nactive, const int *__restrict__ active, float4 *__restrict__ grid,
+__global__ void __launch_bounds__(kT, 4) k_grid_b(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *__restrict__ grid,
                                                float4 *__restrict__ grid_v, BodyTables bt, float4 *__restrict__ zero_next, int zero_self) {
   __shared__ GridSm sm;
-  int t = blockIdx.x * kT + threadIdx.x, grp = threadIdx.x >> 6, g = threadIdx.x & 63;
-  bool valid = t < nactive * 64;
-  int brick = valid ? active[t >> 6] : 0;
-  BodyTables view;
-  unsigned long long cand = stage_bodies(sm, kp, bt, valid, brick, grp, g, view);
-  if (!valid) return;
-  int env, gx_, gy_, gz_;
-  int node = brick_node(brick, g, kp, env, gx_, gy_, gz_);
-  float4 mm = grid[node];
-  if (zero_next) zero_next[node] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (zero_self) grid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!(mm.w > 1e-12)) {
-    grid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
+  const int nactive = cnt[1], grp = threadIdx.x >> 6, g = threadIdx.x & 63;
+  stage_shapes(sm, kp, bt);
+  for (int blk = blockIdx.x; blk * 4 < nactive; blk += gridDim.x) {
+    if (blk != (int)blockIdx.x) __syncthreads();  // the previous iteration is done with the staged poses
+    int t = blk * kT + threadIdx.x;
+    bool valid = t < nactive * 64;
+    int brick = valid ? active[t >> 6] : 0;
+    BodyTables view;
+    unsigned long long cand = stage_bodies(sm, kp, bt, valid, brick, grp, g, view);
+    if (!valid) continue;
+    int env, gx_, gy_, gz_;
+    int node = brick_node(brick, g, kp, env, gx_, gy_, gz_);
+    float4 mm = grid[node];
+    if (zero_next) zero_next[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (zero_self) grid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(mm.w > 1e-12)) {
+      grid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    V3 v = v3(mm.x, mm.y, mm.z) * (1.f / mm.w) + kp.dt * v3(kp.g0, kp.g1, kp.g2);
+    V3 gx = v3((float)gx_, (float)gy_, (float)gz_) * kp.dx;
+    for (unsigned long long c = cand; c; c &= c - 1ull) {
+      int b = __ffsll((long long)c) - 1, pb = env * kp.nb + b;
+      Hit h;
+      Q4 bq = q4f(view.rot[pb]), tfsr = q4f(view.tfsr[b]), sargs = q4f(view.args[b]);
+      if (contact_geom(gx, v3f(view.pos[pb]), bq, tfsr, sargs, view.cull[b], h))
+        v = contact_apply(gx, v, bq, v3f(view.npos[pb]), q4f(view.nrot[pb]), tfsr, sargs, kp.dt, h);
+    }
+    v = apply_bc(v, gx_, gy_, gz_, kp);
+    grid_v[node] = make_float4(v.x, v.y, v.z, 0.f);
   }
-  V3 v = v3(mm.x, mm.y, mm.z) * (1.f / mm.w) + kp.dt * v3(kp.g0, kp.g1, kp.g2);
-  V3 gx = v3((float)gx_, (float)gy_, (float)gz_) * kp.dx;
-  for (unsigned long long c = cand; c; c &= c - 1ull) {
-    int b = __ffsll((long long)c) - 1, pb = env * kp.nb + b;
-    Hit h;
-    Q4 bq = q4f(view.rot[pb]), tfsr = q4f(view.tfsr[b]), sargs = q4f(view.args[b]);
-    if (contact_geom(gx, v3f(view.pos[pb]), bq, tfsr, sargs, view.cull[b], h))
-      v = contact_apply(gx, v, bq, v3f(view.npos[pb]), q4f(view.nrot[pb]), tfsr, sargs, kp.dt, h);
-  }
-  v = apply_bc(v, gx_, gy_, gz_, kp);
-  grid_v[node] = make_float4(v.x, v.y, v.z, 0.f);
 }
 
-__global__ void __launch_bounds__(kT, 4) k_grid_grad_b(KP kp, int nactive, const int *__restrict__ active, float4 *__restrict__ grid,
+__global__ void __launch_bounds__(kT, 4) k_grid_grad_b(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *__restrict__ grid,
                                                     float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos,
                                                     float4 *grot, float4 *gnpos, float4 *gnrot, int zero_m) {
   __shared__ GridSm sm;
-  int t = blockIdx.x * kT + threadIdx.x, grp = threadIdx.x >> 6, g = threadIdx.x & 63;
-  bool inr = t < nactive * 64;
-  int brick = inr ? active[t >> 6] : 0;
-  BodyTables view;
-  unsigned long long cand = stage_bodies(sm, kp, bt, inr, brick, grp, g, view);
-  int env = 0, x = 0, y = 0, z = 0, node = 0;
-  if (inr) node = brick_node(brick, g, kp, env, x, y, z);
-  grid_grad_body(kp, node, inr, env, x, y, z, grid, ggrid_v, ggrid, view, gpos, grot, gnpos, gnrot, cand, true, zero_m != 0);
+  const int nactive = cnt[1], grp = threadIdx.x >> 6, g = threadIdx.x & 63;
+  stage_shapes(sm, kp, bt);
+  for (int blk = blockIdx.x; blk * 4 < nactive; blk += gridDim.x) {
+    if (blk != (int)blockIdx.x) __syncthreads();
+    int t = blk * kT + threadIdx.x;
+    bool inr = t < nactive * 64;
+    int brick = inr ? active[t >> 6] : 0;
+    BodyTables view;
+    unsigned long long cand = stage_bodies(sm, kp, bt, inr, brick, grp, g, view);
+    int env = 0, x = 0, y = 0, z = 0, node = 0;
+    if (inr) node = brick_node(brick, g, kp, env, x, y, z);
+    grid_grad_body(kp, node, inr, env, x, y, z, grid, ggrid_v, ggrid, view, gpos, grot, gnpos, gnrot, cand, true, zero_m != 0);
+  }
 }
 
 // ---- layout conversion (original AoS order <-> sorted planes) --------------------------------------------------------
@@ -1410,10 +1480,13 @@ __global__ void k_pack_mat(int EN, const int *__restrict__ perm, const float *__
   yield[i] = mly[3 * s + 2];
 }
 // sort key of a particle: environment-major, then 4x4x4-cell brick (x-major like the grid), then cell inside the brick
-__global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__restrict__ keys, int *__restrict__ idx) {
+// x_aos: positions in the caller's order (dd_sim_set_state), or x_plane: plane 0 of a checkpoint slot (device re-sort)
+__global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, const float4 *__restrict__ x_plane, unsigned *__restrict__ keys, int *__restrict__ idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kp.EN) return;
-  V3 x = ld_v3(x_aos, i);
+  V3 x;
+  if (x_aos) x = ld_v3(x_aos, i);
+  else { float4 a = x_plane[i]; x = v3(a.x, a.y, a.z); }
   int cx = clampi((int)floorf(x.x * kp.inv_dx - 0.5f), 0, kp.gx - 1), cy = clampi((int)floorf(x.y * kp.inv_dx - 0.5f), 0, kp.gy - 1),
       cz = clampi((int)floorf(x.z * kp.inv_dx - 0.5f), 0, kp.gz - 1);
   int nby = (kp.gy + 3) >> 2, nbz = (kp.gz + 3) >> 2;
@@ -1427,7 +1500,7 @@ __global__ void k_sort_keys(KP kp, const float *__restrict__ x_aos, unsigned *__
 
 // On the sorted keys: flags the first particle of every brick, and -- once per occupied cell, the active region depends on the
 // cell only -- marks the bricks reached by that cell's stencil [base, base + 2] padded by one node on each side.
-__global__ void k_mark_heads(KP kp, const unsigned *__restrict__ keys, char *__restrict__ flags, char *__restrict__ active_flag) {
+__global__ void k_mark_heads(KP kp, const unsigned *__restrict__ keys, char *__restrict__ flags, int *__restrict__ active_flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kp.EN) return;
   unsigned key = keys[i], prev = i ? keys[i - 1] : ~key;
@@ -1444,16 +1517,18 @@ __global__ void k_mark_heads(KP kp, const unsigned *__restrict__ keys, char *__r
   for (int x_ = x0; x_ <= x1; ++x_)
     for (int y_ = y0; y_ <= y1; ++y_)
       for (int z_ = z0; z_ <= z1; ++z_) {
-        char *fl = active_flag + (size_t)env * NB + (x_ * nby + y_) * nbz + z_;
+        int *fl = active_flag + (size_t)env * NB + (x_ * nby + y_) * nbz + z_;
         if (!*fl) *fl = 1;
       }
 }
 // one thread per occupied brick: split its particles into `nsub` chunks.
 // Chunk c takes the cell-sorted ranks r = c (mod nsub) of the brick -- a thinned copy of the whole brick, so that the
 // lanes of a round still sit in different cells -- and owns the storage range after chunks 0..c-1.
-__global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_pos, const unsigned *__restrict__ keys, int chunk_max,
+// (launched over an upper bound of threads; the number of occupied bricks is counters[2], written by the stream compaction)
+__global__ void k_make_chunks(KP kp, const int *__restrict__ head_pos, const unsigned *__restrict__ keys, int chunk_max,
                               int4 *__restrict__ chunks, int4 *__restrict__ chunk_src, int *__restrict__ counters) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nbricks = counters[2];
   if (k >= nbricks) return;
   int start = head_pos[k], end = k + 1 < nbricks ? head_pos[k + 1] : kp.EN, cnt = end - start;
   int brick = (int)(keys[start] >> 6);
@@ -1474,10 +1549,10 @@ __global__ void k_make_chunks(KP kp, int nbricks, const int *__restrict__ head_p
 // cell-sorted list, so the lanes of a round also sit in different cells (no read-modify-write collisions).  Groups are
 // not equally populated: what does not fit into a group's own columns spills into the free slots of the others (a few
 // percent of the particles, costing at most one extra wavefront where they sit).  One warp per chunk.
-__global__ void k_interleave(KP kp, int nchunks, int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src, const unsigned *__restrict__ keys_sorted,
+__global__ void k_interleave(KP kp, const int *__restrict__ counters, int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src, const unsigned *__restrict__ keys_sorted,
                              const int *__restrict__ perm_in, int *__restrict__ perm_out, int *__restrict__ spos) {
   int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (ci >= nchunks) return;
+  if (ci >= counters[0]) return;
   const unsigned full = 0xffffffffu;
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   int4 src = chunk_src[ci];  // (brick start, brick count, c, nsub): item r of the chunk is sorted rank src.x + src.z + r * src.w
@@ -1552,16 +1627,17 @@ __global__ void k_interleave(KP kp, int nchunks, int4 *__restrict__ chunks, cons
 }
 
 // largest chunks first: the persistent tiled kernels hand chunks out in list order, so the launch ends on the small ones
-__global__ void k_chunk_keys(int nchunks, const int4 *__restrict__ chunks, int *__restrict__ keys, int *__restrict__ idx) {
+// (the sort runs over the whole capacity of the list: entries past the live count get size 0 and sort to the end)
+__global__ void k_chunk_keys(int cap, const int *__restrict__ counters, const int4 *__restrict__ chunks, int *__restrict__ keys, int *__restrict__ idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nchunks) return;
-  keys[i] = chunks[i].z;
+  if (i >= cap) return;
+  keys[i] = i < counters[0] ? chunks[i].z : 0;
   idx[i] = i;
 }
-__global__ void k_chunk_permute(int nchunks, const int *__restrict__ order, const int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src,
+__global__ void k_chunk_permute(int cap, const int *__restrict__ counters, const int *__restrict__ order, const int4 *__restrict__ chunks, const int4 *__restrict__ chunk_src,
                                 int4 *__restrict__ chunks_out, int4 *__restrict__ chunk_src_out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nchunks) return;
+  if (i >= cap || i >= counters[0]) return;
   chunks_out[i] = chunks[order[i]];
   chunk_src_out[i] = chunk_src[order[i]];
 }
@@ -1586,6 +1662,35 @@ __global__ void k_add4(int n, const float *__restrict__ src, int w, float4 *dst)
   for (int k = 0; k < w; ++k) t[k] = src[(size_t)i * w + k];
   float4 d = dst[i];
   dst[i] = make_float4(d.x + t[0], d.y + t[1], d.z + t[2], d.w + t[3]);
+}
+
+// ---- device-side re-sort at a segment boundary ---------------------------------------------------------------------------
+// dst[i] = src[from[i]] for the state planes (x, v, C | F | quaternion of V): the head copy of a boundary slot in the new order
+__global__ void k_gather_planes(int EN, const int *__restrict__ from, const float *__restrict__ src, float *__restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= EN) return;
+  int j = from[i];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) plane4(dst, EN, k)[i] = plane4(src, EN, k)[j];
+  dst[(size_t)24 * EN + i] = src[(size_t)24 * EN + j];
+  store_q(dst, EN, i, reinterpret_cast<const float4 *>(src + (size_t)25 * EN)[j]);
+}
+// gradient planes of a boundary state from the new order back into the previous one: dst[from[i]] = src[i]
+__global__ void k_scatter_grad(int EN, const int *__restrict__ from, const float *__restrict__ src, float *__restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= EN) return;
+  int j = from[i];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) plane4(dst, EN, k)[j] = plane4(src, EN, k)[i];
+  dst[(size_t)24 * EN + j] = src[(size_t)24 * EN + i];
+}
+__global__ void k_compose_perm(int EN, const int *__restrict__ from, const int *__restrict__ perm_prev, int *__restrict__ perm_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < EN) perm_out[i] = perm_prev[from[i]];
+}
+__global__ void k_copy_poses(int n, const float4 *__restrict__ ps, const float4 *__restrict__ rs, float4 *__restrict__ pd, float4 *__restrict__ rd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { pd[i] = ps[i]; rd[i] = rs[i]; }
 }
 
 // compute_dist (integrator.cu:188-237) on the engine layout; dist is (E*N, nb) in ORIGINAL particle order
@@ -1672,55 +1777,94 @@ inline int nblk(long long n) { return (int)((n + kT - 1) / kT); }
 }  // namespace
 
 // ======================================================================================================= host side
+// Storage model.  A rollout of max_steps substeps is cut into SEGMENTS of `resort_interval` substeps (one segment when 0).
+// All states of a segment are stored in one particle order -- the cell order of the segment's first state -- described by
+// device-resident tables (Segment).  The first state of segments 1.. is therefore stored twice: as the last slot of the previous
+// segment (old order, "tail" copy) and, re-sorted on the device, as the first slot of its own segment ("head" copy); the
+// adjoint permutes the gradient of that state back once per boundary.  Every count the kernels need (chunks, active bricks)
+// lives in device memory, so building a segment never synchronises with the host and cached CUDA graphs stay valid across
+// re-sorts.  Host-side bookkeeping only tracks which physical slots hold data written under the current ordering of their
+// segment (epochs): reading anything else is an error instead of silently permuted data.
+struct Segment {
+  int *perm = nullptr;       // storage position -> particle index in the caller's order
+  int *from_prev = nullptr;  // storage position -> storage position in the previous segment (valid when linked)
+  float4 *mat0 = nullptr;    // (mass, vol, mu, lambda) in storage order
+  float *yield = nullptr;
+  int4 *chunks = nullptr;
+  int *active = nullptr, *flags = nullptr, *cnt = nullptr;
+  int epoch = 0;             // 0: never built
+  bool linked = false;       // built by re-sorting the previous segment's last state: gradients may flow across the boundary
+  SegView view() const { SegView v; v.chunks = chunks; v.cnt = cnt; v.active = active; v.flags = flags; return v; }
+};
+
 struct dd_sim {
   dd_sim_config cfg;
   KP kp;
-  int slots;                 // max_steps + 1
-  size_t slot_floats;        // kPlaneFloats * ENp
-  float *ckpt = nullptr;     // slots * slot_floats
+  int slots = 0;             // logical states: max_steps + 1
+  int L = 0, nseg = 1;       // substeps per segment (0: the whole rollout is one segment), number of segments
+  int pslots = 0;            // physical slots = slots + nseg - 1
+  size_t slot_floats = 0;    // kPlaneFloats * EN
+  float *ckpt = nullptr;     // pslots * slot_floats
   float *grad[2] = {nullptr, nullptr};
-  int grad_holds[2] = {-1, -1};
-  float4 *mat0 = nullptr;
-  float *yield = nullptr;
+  int grad_holds[2] = {-1, -1};   // logical state whose gradient the slot holds
+  int grad_order[2] = {-1, -1};   // segment whose particle order it is stored in (-1: all zeros, any order)
+  float *gtmp = nullptr;     // 25 * EN floats, gradient planes in flight at a segment boundary
   float4 *grid = nullptr, *grid_v = nullptr, *ggrid_v = nullptr, *ggrid = nullptr;
   float4 *pos = nullptr, *rot = nullptr, *gpos = nullptr, *grot = nullptr;  // slots * E * nb
   float4 *tfsr = nullptr, *args = nullptr;
   float *cull = nullptr;
-  int *perm = nullptr;       // sorted index -> original particle index
+  // scratch of the sort pipeline (shared by all segments; builds are serialised on the caller's stream)
   unsigned *keys = nullptr, *keys_alt = nullptr;
-  int *idx_alt = nullptr;
+  int *iota = nullptr, *sorted_idx = nullptr, *stor_idx = nullptr, *perm_tmp = nullptr;
   void *cub_tmp = nullptr;
   size_t cub_bytes = 0;
-  // tiled mode: chunk list, active bricks, per-substep grid checkpoints
-  int4 *chunks = nullptr, *chunk_src = nullptr, *chunks_alt = nullptr, *chunk_src_alt = nullptr;
+  int4 *chunks_tmp = nullptr, *chunk_src_tmp = nullptr, *chunk_src = nullptr;
   int *chunk_sort = nullptr;  // 4 * chunk_cap ints: sizes, sorted sizes, indices, sorted indices
   void *csort_tmp = nullptr;
   size_t csort_bytes = 0;
-  int chunk_cap = 0, nchunks = 0, chunk_max = 512;
+  int chunk_cap = 0, chunk_max = 512;
   int *head_pos = nullptr, *spos = nullptr;
-  char *head_flags = nullptr, *active_flag = nullptr;
-  int *active = nullptr;
-  int nactive = 0, NBtot = 0;
-  int *counters = nullptr;   // [0] chunks, [1] active bricks, [2] occupied bricks, [3] overflow flag
+  char *head_flags = nullptr;
+  int NBtot = 0, occ_cap = 0;
+  int *counters = nullptr;   // [4],[5] chunk tickets of the persistent tile kernels
   void *sel_tmp = nullptr;
   size_t sel_bytes = 0;
-  float4 *gridck = nullptr, *gridvck = nullptr;  // (slots-1) * E * G each when grid checkpoints are on
+  // per-segment tables, pooled
+  std::vector<Segment> segs;
+  std::vector<int> slot_epoch;  // per physical slot: epoch of its segment when it was written (-1: nothing)
+  int epoch_counter = 0;
+  int *perm_pool = nullptr, *from_pool = nullptr, *active_pool = nullptr, *flags_pool = nullptr, *cnt_pool = nullptr;
+  float4 *mat0_pool = nullptr;
+  float *yield_pool = nullptr;
+  int4 *chunks_pool = nullptr;
+  float4 *gridck = nullptr, *gridvck = nullptr;  // max_steps * E * G each when grid checkpoints are on
   bool grid_ckpt = false;
-  float *mat_aos = nullptr;  // (mass | vol | mu_lam_yield) in original order, re-packed after every sort
+  float *mat_aos = nullptr;  // (mass | vol | mu_lam_yield) in the caller's order, re-packed for every new ordering
   bool have_material = false;
   float *stage = nullptr;    // 24 * EN floats (x|v|F|C in original AoS order) or E*N*nb for dist
   size_t stage_floats = 0;
-  std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;
+  std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
+  std::map<std::tuple<int, int, int, int>, long long> graph_launches;  // kernels per replay of each cached graph
   long long launches = 0;    // kernels launched (or replayed through graphs) since creation
   cudaStream_t side = nullptr;  // uploads that may overlap the sort in dd_sim_set_state
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // persistent launch geometry of the tiled kernels (resident blocks per SM x SMs) and which gather variants run
+  int sms = 1;
   int pb_p2g = 0, pb_g2pg = 0, pb_g2p = 0, pb_p2gg = 0;
   bool g2p_tiled = false, p2gg_tiled = false, fuse_gather = false;  // fuse_gather: gather half of the g2p adjoint inside k_p2g_grad_tile
   int w_p2g = 4, w_g2pg = 1, w_g2p = 4, w_p2gg = 4;  // warps per block (the warps of a block are independent; this only sets the shared-memory granularity)
-  int tile_blocks(int per_device, int wpb) const { return std::max(1, std::min((nchunks + wpb - 1) / wpb, per_device)); }
+  // upper-bound grids: the live counts are read on the device
+  int tile_blocks(int per_device, int wpb) const { return std::max(1, std::min((chunk_cap + wpb - 1) / wpb, per_device)); }
+  int brick_blocks() const { return std::max(1, std::min((NBtot + 3) / 4, sms * 16)); }
 
-  float *slot(int f) const { return ckpt + (size_t)f * slot_floats; }
+  // ---- logical state f <-> segment and physical slot
+  int seg_of(int f) const { return L > 0 ? std::min(f / L, nseg - 1) : 0; }          // segment in which state f is the INPUT of a substep
+  bool is_boundary(int f) const { return L > 0 && f > 0 && f % L == 0 && f / L < nseg; }  // stored twice
+  int phys_cur(int f) const { return f + seg_of(f); }                                 // head copy (or the only copy)
+  int phys_tail(int f) const { return f >= 1 ? phys_cur(f - 1) + 1 : phys_cur(0); }   // the copy written by substep f-1
+  int seg_of_phys(int p) const { return L > 0 ? std::min(p / (L + 1), nseg - 1) : 0; }
+  bool valid(int p) const { int e = slot_epoch[p]; return e > 0 && e == segs[seg_of_phys(p)].epoch; }
+  float *pslot(int p) const { return ckpt + (size_t)p * slot_floats; }
   float4 *G(int f) const { return grid_ckpt ? gridck + (size_t)f * kp.E * kp.G : grid; }
   float4 *GV(int f) const { return grid_ckpt ? gridvck + (size_t)f * kp.E * kp.G : grid_v; }
   BodyTables tables(int f) const {
@@ -1738,86 +1882,142 @@ using Mark = std::function<void(const char *)>;
 inline void mark(const Mark *m, const char *name) { if (m) (*m)(name); }
 int fwd_launches(const dd_sim *s) { return 3; }
 int bwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? (s->grid_ckpt ? 3 : 5) : 5; }
+constexpr int kBuildLaunches = 16;  // kernels of one segment build (sort, compaction, chunk tables, gather)
 
 template <int SVD>
 void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk = nullptr) {
   const KP &kp = s->kp;
+  const Segment &sg = s->segs[s->seg_of(f)];
+  float *cur = s->pslot(s->phys_cur(f)), *nxt = s->pslot(s->phys_cur(f) + 1);
   if (s->cfg.tile_mode) {
-    int nb64 = nblk((long long)s->nactive * 64);
     // invariant: the scatter target of substep f is already zero on the active bricks (cleared by the previous grid
-    // kernel, or by dd_sim_forward for the first substep of a range)
-    k_p2g_tile<SVD, true><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->G(f), s->active_flag, s->counters + 3, s->counters + 4);
+    // kernel, or by dd_sim_forward for the first substep of a range; bricks activated on the fly clear themselves)
+    k_p2g_tile<SVD, true><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->G(f), s->counters + 4);
     mark(mk, "p2g_tile (svd+return map+scatter)");
     float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
-    k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
+    k_grid_b<<<s->brick_blocks(), kT, 0, st>>>(kp, sg.cnt, sg.active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_b (grid update + contact)");
-    if (s->g2p_tiled) k_g2p_tile<<<s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), s->counters + 3, s->counters + 4);
-    else k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->GV(f));
+    if (s->g2p_tiled) k_g2p_tile<<<s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * kTileN * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), s->counters + 4);
+    else k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, cur, nxt, s->GV(f));
     mark(mk, "g2p");
   } else {
     cudaMemsetAsync(s->grid, 0, sizeof(float4) * (size_t)kp.E * kp.G, st);
-    k_p2g<SVD, true><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
+    k_p2g<SVD, true><<<nblk(kp.EN), kT, 0, st>>>(kp, cur, nxt, sg.mat0, sg.yield, s->grid);
     k_grid<<<nblk((long long)kp.E * kp.G), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
-    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, nullptr, s->slot(f), s->slot(f + 1), s->grid_v);
+    k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, nullptr, cur, nxt, s->grid_v);
   }
   s->launches += fwd_launches(s);
 }
 template <int SVD>
 void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk = nullptr) {
   const KP &kp = s->kp;
+  const Segment &sg = s->segs[s->seg_of(f)];
+  float *cur = s->pslot(s->phys_cur(f)), *nxt = s->pslot(s->phys_cur(f) + 1);
   float *gin = s->grad[(f + 1) & 1], *gout = s->grad[f & 1];
   size_t eg = (size_t)kp.E * kp.G, ep = (size_t)kp.E * kp.nb;
   float4 *gp = s->gpos + (size_t)f * ep, *gr = s->grot + (size_t)f * ep, *gnp = s->gpos + (size_t)(f + 1) * ep, *gnr = s->grot + (size_t)(f + 1) * ep;
   if (s->cfg.tile_mode) {
-    int nb64 = nblk((long long)s->nactive * 64);
     // invariant: ggrid_v is zero on the active bricks (k_grid_grad_b clears what it consumes)
     if (!s->grid_ckpt) {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
-      k_p2g_tile<SVD, false><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid, s->active_flag, s->counters + 3, s->counters + 4);
-      k_grid_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
+      k_p2g_tile<SVD, false><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->grid, s->counters + 4);
+      k_grid_b<<<s->brick_blocks(), kT, 0, st>>>(kp, sg.cnt, sg.active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
-    if (s->fuse_gather) k_g2p_grad_tile<false><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3, s->counters + 4);
-    else k_g2p_grad_tile<true><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->GV(f), gin, gout, s->ggrid_v, s->active_flag, s->counters + 3, s->counters + 4);
+    if (s->fuse_gather) k_g2p_grad_tile<false><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
+    else k_g2p_grad_tile<true><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
     mark(mk, "g2p_grad_tile");
-    k_grid_grad_b<<<nb64, kT, 0, st>>>(kp, s->nactive, s->active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
+    k_grid_grad_b<<<s->brick_blocks(), kT, 0, st>>>(kp, sg.cnt, sg.active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
-    if (s->fuse_gather) k_p2g_grad_tile<SVD, true><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * 2 * kTileN * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, s->GV(f), gin, gout, s->counters + 3, s->counters + 4);
-    else if (s->p2gg_tiled) k_p2g_grad_tile<SVD, false><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * (kTileN + (SVD == 1 ? kStageP2GG * 32 : 0)) * sizeof(float4), st>>>(kp, s->nchunks, s->chunks, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, nullptr, gin, gout, s->counters + 3, s->counters + 4);
-    else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
+    if (s->fuse_gather) k_p2g_grad_tile<SVD, true><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * 2 * kTileN * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, s->GV(f), gin, gout, s->counters + 4);
+    else if (s->p2gg_tiled) k_p2g_grad_tile<SVD, false><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * (kTileN + (SVD == 1 ? kStageP2GG * 32 : 0)) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, nullptr, gin, gout, s->counters + 4);
+    else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, cur, nxt, sg.mat0, sg.yield, s->ggrid, gin, gout);
     mark(mk, "p2g_grad (+svd adjoint)");
   } else {
     cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st);
     cudaMemsetAsync(s->ggrid_v, 0, sizeof(float4) * eg, st);
-    k_p2g<SVD, false><<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->grid);
+    k_p2g<SVD, false><<<nblk(kp.EN), kT, 0, st>>>(kp, cur, nxt, sg.mat0, sg.yield, s->grid);
     k_grid<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->grid_v, s->tables(f));
-    k_g2p_grad<<<nblk(kp.EN), kT, 0, st>>>(kp, s->slot(f), s->slot(f + 1), s->grid_v, gin, gout, s->ggrid_v);
+    k_g2p_grad<<<nblk(kp.EN), kT, 0, st>>>(kp, cur, nxt, s->grid_v, gin, gout, s->ggrid_v);
     k_grid_grad<<<nblk((long long)eg), kT, 0, st>>>(kp, s->grid, s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr);
-    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, nullptr, s->slot(f), s->slot(f + 1), s->mat0, s->yield, s->ggrid, gin, gout);
+    k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, nullptr, cur, nxt, sg.mat0, sg.yield, s->ggrid, gin, gout);
   }
   s->launches += bwd_launches(s);
 }
 
-int check_overflow(dd_sim *s) {
-  if (!s->cfg.tile_mode) return 0;
-  int flag = 0;
-  DD_CUDA(cudaMemcpy(&flag, s->counters + 3, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) {
-    cudaMemset(s->counters + 3, 0, sizeof(int));
-    return fail("a particle moved more than two cells away from the brick it was sorted into; results since the last dd_sim_set_state are invalid -- "
-                "re-sort more often (call dd_sim_set_state at environment-step boundaries)");
+// Enqueue the construction of segment k's ordering from positions: `x_aos` (caller's order, dd_sim_set_state) or plane 0 of
+// physical slot `src` stored in segment kprev's order (device re-sort).  Afterwards stor_idx[i] = source index of storage
+// position i, seg.perm is final and, for a device re-sort, seg.from_prev = stor_idx and the state planes of `src` have been
+// gathered into physical slot `dst`.  Nothing here waits for the device.
+int enqueue_build(dd_sim *s, int k, const float *x_aos, int src, int kprev, int dst, cudaStream_t st) {
+  const KP &kp = s->kp;
+  Segment &sg = s->segs[k];
+  const int EN = kp.EN;
+  const int *order = s->iota;  // storage position -> source index
+  if (s->cfg.sort_particles) {
+    k_sort_keys<<<nblk(EN), kT, 0, st>>>(kp, x_aos, x_aos ? nullptr : reinterpret_cast<const float4 *>(s->pslot(src)), s->keys, s->iota);
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)kp.E * kp.G) ++bits;
+    DD_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_tmp, s->cub_bytes, s->keys, s->keys_alt, s->iota, s->sorted_idx, EN, 0, bits, st));
+    order = s->sorted_idx;
+    if (s->cfg.tile_mode) {
+      DD_CUDA(cudaMemsetAsync(sg.flags, 0, sizeof(int) * s->NBtot, st));
+      DD_CUDA(cudaMemsetAsync(sg.cnt, 0, sizeof(int) * 4, st));
+      k_mark_heads<<<nblk(EN), kT, 0, st>>>(kp, s->keys_alt, s->head_flags, sg.flags);
+      DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, sg.cnt + 2, EN, st));
+      k_make_chunks<<<nblk(s->occ_cap), kT, 0, st>>>(kp, s->head_pos, s->keys_alt, s->chunk_max, s->chunks_tmp, s->chunk_src_tmp, sg.cnt);
+      DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), sg.flags, sg.active, sg.cnt + 1, s->NBtot, st));
+      int cap = s->chunk_cap;
+      int *ck = s->chunk_sort, *cks = ck + cap, *ci = ck + 2 * cap, *cis = ck + 3 * cap;
+      k_chunk_keys<<<nblk(cap), kT, 0, st>>>(cap, sg.cnt, s->chunks_tmp, ck, ci);
+      DD_CUDA(cub::DeviceRadixSort::SortPairsDescending(s->csort_tmp, s->csort_bytes, ck, cks, ci, cis, cap, 0, 32, st));
+      k_chunk_permute<<<nblk(cap), kT, 0, st>>>(cap, sg.cnt, cis, s->chunks_tmp, s->chunk_src_tmp, sg.chunks, s->chunk_src);
+      k_interleave<<<nblk((long long)cap * 32), kT, 0, st>>>(kp, sg.cnt, sg.chunks, s->chunk_src, s->keys_alt, s->sorted_idx, s->stor_idx, s->spos);
+      order = s->stor_idx;
+    }
   }
+  if (x_aos) {
+    DD_CUDA(cudaMemcpyAsync(sg.perm, order, sizeof(int) * EN, cudaMemcpyDeviceToDevice, st));
+  } else {
+    k_compose_perm<<<nblk(EN), kT, 0, st>>>(EN, order, s->segs[kprev].perm, s->perm_tmp);  // (kprev may be k: compose out of place)
+    DD_CUDA(cudaMemcpyAsync(sg.from_prev, order, sizeof(int) * EN, cudaMemcpyDeviceToDevice, st));
+    DD_CUDA(cudaMemcpyAsync(sg.perm, s->perm_tmp, sizeof(int) * EN, cudaMemcpyDeviceToDevice, st));
+    k_gather_planes<<<nblk(EN), kT, 0, st>>>(EN, sg.from_prev, s->pslot(src), s->pslot(dst));
+  }
+  if (s->have_material) {
+    float *a = s->mat_aos;
+    k_pack_mat<<<nblk(EN), kT, 0, st>>>(EN, sg.perm, a, a + EN, a + 2 * (size_t)EN, sg.mat0, sg.yield);
+  }
+  DD_CUDA(cudaGetLastError());
+  s->launches += kBuildLaunches;
   return 0;
 }
+// host bookkeeping that goes with enqueue_build: a new ordering invalidates everything stored under the old one
+void segment_rebuilt(dd_sim *s, int k, bool linked, int first_phys) {
+  Segment &sg = s->segs[k];
+  sg.epoch = ++s->epoch_counter;
+  sg.linked = linked;
+  s->slot_epoch[first_phys] = sg.epoch;
+  for (int i = 0; i < 2; ++i)
+    if (s->grad_order[i] == k) { s->grad_holds[i] = -1; s->grad_order[i] = -1; }
+}
+// gradient of boundary state (held in grad slot `gi`, order of segment k) back into the order of segment k-1
+void enqueue_grad_permute(dd_sim *s, int k, int gi, cudaStream_t st) {
+  const int EN = s->kp.EN;
+  k_scatter_grad<<<nblk(EN), kT, 0, st>>>(EN, s->segs[k].from_prev, s->grad[gi], s->gtmp);
+  cudaMemcpyAsync(s->grad[gi], s->gtmp, sizeof(float) * 25 * (size_t)EN, cudaMemcpyDeviceToDevice, st);
+  s->launches += 2;
+}
 
-// run `body` either directly or as a cached CUDA graph keyed by (kind, f0, n)
+// run `body` either directly or as a cached CUDA graph keyed by (kind, f0, n, variant)
 template <class Fn>
-int run_graphed(dd_sim *s, int kind, int f0, int n, cudaStream_t st, long long launches_per_call, Fn body) {
+int run_graphed(dd_sim *s, int kind, int f0, int n, int variant, cudaStream_t st, Fn body) {
   if (!s->cfg.use_graphs) {
     body(st);
     DD_CUDA(cudaGetLastError());
     return 0;
   }
-  auto key = std::make_tuple(kind, f0, n);
+  auto key = std::make_tuple(kind, f0, n, variant);
   auto it = s->graphs.find(key);
+  long long before = s->launches;
   if (it == s->graphs.end()) {
     cudaStream_t cap = st;
     cudaStream_t tmp = nullptr;
@@ -1825,26 +2025,57 @@ int run_graphed(dd_sim *s, int kind, int f0, int n, cudaStream_t st, long long l
       DD_CUDA(cudaStreamCreateWithFlags(&tmp, cudaStreamNonBlocking));
       cap = tmp;
     }
-    long long before = s->launches;
     DD_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     body(cap);
     cudaGraph_t graph = nullptr;
     DD_CUDA(cudaStreamEndCapture(cap, &graph));
-    s->launches = before;
     cudaGraphExec_t exec = nullptr;
     DD_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     DD_CUDA(cudaGraphDestroy(graph));
     if (tmp) DD_CUDA(cudaStreamDestroy(tmp));
     it = s->graphs.emplace(key, exec).first;
+    s->graph_launches[key] = s->launches - before;
   }
   DD_CUDA(cudaGraphLaunch(it->second, st));
-  s->launches += launches_per_call;
+  s->launches = before + s->graph_launches[key];
+  return 0;
+}
+
+// results written to device memory are ordered by the stream: only host destinations make a getter wait
+bool on_device(const void *p) {
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice;
+}
+int finish_readback(cudaStream_t st, std::initializer_list<const void *> outs) {
+  for (const void *p : outs)
+    if (!on_device(p)) { DD_CUDA(cudaStreamSynchronize(st)); break; }
   return 0;
 }
 
 int check_range(dd_sim *s, int f0, int n, const char *what) {
   if (!s) return fail(std::string(what) + ": null simulator");
   if (f0 < 0 || n < 0 || f0 + n >= s->slots) return fail(std::string(what) + ": substep range [" + std::to_string(f0) + ", " + std::to_string(f0 + n) + "] exceeds max_steps=" + std::to_string(s->slots - 1));
+  return 0;
+}
+// which stored copy of state f to read: the head copy if it is current, else the copy the previous substep wrote
+int pick_copy(dd_sim *s, int f, int *phys, int *seg, const char *what) {
+  if (s->valid(s->phys_cur(f))) { *phys = s->phys_cur(f); *seg = s->seg_of(f); return 0; }
+  if (f >= 1 && s->valid(s->phys_tail(f))) { *phys = s->phys_tail(f); *seg = s->seg_of(f - 1); return 0; }
+  return fail(std::string(what) + ": state " + std::to_string(f) + " is not available (never computed, or stored under a particle order that a later "
+              "dd_sim_set_state / re-sort replaced)");
+}
+// the copy of state f that is stored in the same order as its gradient slot; fixes the order of an all-zero slot
+int grad_copy(dd_sim *s, int f, int *phys, int *seg, const char *what) {
+  int gi = f & 1;
+  if (s->grad_holds[gi] != f) return fail(std::string(what) + ": gradient slot does not hold state " + std::to_string(f) + " (call dd_sim_zero_grad or run the backward pass down to it first)");
+  if (s->grad_order[gi] < 0) {  // zeros: take the order the backward pass will consume it in (the substep that produced the state)
+    if (f >= 1 && s->valid(s->phys_tail(f))) s->grad_order[gi] = s->seg_of(f - 1);
+    else s->grad_order[gi] = s->seg_of(f);
+  }
+  *seg = s->grad_order[gi];
+  *phys = *seg == s->seg_of(f) ? s->phys_cur(f) : s->phys_tail(f);
   return 0;
 }
 
@@ -1866,6 +2097,12 @@ int dd_sim_pose_table(dd_sim *s, float **pos, float **rot, int *slots, int *n_en
   if (n_bodies) *n_bodies = s->kp.nb;
   return 0;
 }
+int dd_sim_pose_grad_table(dd_sim *s, float **gpos, float **grot) {
+  if (!s) return fail("dd_sim_pose_grad_table: null simulator");
+  if (gpos) *gpos = reinterpret_cast<float *>(s->gpos);
+  if (grot) *grot = reinterpret_cast<float *>(s->grot);
+  return 0;
+}
 
 int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
   if (!cfg || !out) return fail("dd_sim_create: null argument");
@@ -1873,6 +2110,9 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
   if (cfg->n_bodies < 0 || cfg->n_bodies > 64) return fail("dd_sim_create: n_bodies must be in [0, 64]");
   if (cfg->grid_x < 8 || cfg->grid_y < 8 || cfg->grid_z < 8) return fail("dd_sim_create: grid must be at least 8^3");
   if (((long long)cfg->grid_x * cfg->grid_y * cfg->grid_z) % 32 != 0) return fail("dd_sim_create: grid size must be a multiple of 32 nodes");
+  if ((long long)cfg->n_envs * cfg->grid_x * cfg->grid_y * cfg->grid_z >= (1ll << 32)) return fail("dd_sim_create: n_envs * grid nodes must stay below 2^32 (32-bit sort keys)");
+  if ((long long)cfg->n_envs * cfg->n_particles >= (1ll << 31)) return fail("dd_sim_create: n_envs * n_particles must stay below 2^31");
+  if (cfg->resort_interval < 0) return fail("dd_sim_create: resort_interval must be >= 0");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail("dd_sim_create: no CUDA device (dexdeform_b200 has no CPU fallback)");
   dd_sim *s = new dd_sim();
@@ -1886,21 +2126,25 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
   kp.dx = cfg->dx; kp.inv_dx = 1.0f / cfg->dx; kp.dt = cfg->dt; kp.gf = cfg->ground_friction; kp.gh = cfg->ground_height;
   kp.g0 = cfg->gravity[0]; kp.g1 = cfg->gravity[1]; kp.g2 = cfg->gravity[2];
   s->slots = cfg->max_steps + 1;
+  // segments: re-sorting needs the sorted, tiled layout
+  s->L = (cfg->tile_mode && cfg->sort_particles && cfg->resort_interval < cfg->max_steps) ? cfg->resort_interval : 0;
+  s->nseg = s->L > 0 ? (cfg->max_steps + s->L - 1) / s->L : 1;
+  s->pslots = s->slots + s->nseg - 1;
   size_t ENp = ((size_t)kp.EN + 3) / 4 * 4;
-  if (ENp != (size_t)kp.EN) { delete s; return fail("dd_sim_create: n_envs * n_particles must be a multiple of 4"); }
+  if (ENp != (size_t)kp.EN) { delete s; return fail("dd_sim_create: n_envs * n_particles must be a multiple of 4 (float4 planes)"); }
   s->slot_floats = kPlaneFloats * ENp;
   size_t eg = (size_t)kp.E * kp.G, ep = (size_t)kp.E * (kp.nb > 0 ? kp.nb : 1) * s->slots;
+  const int nseg = s->nseg;
 #define DD_ALLOC(ptr, bytes)                                                                                   \
   do {                                                                                                         \
     cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                                                     \
     if (e_ != cudaSuccess) { dd_sim_destroy(s); return fail(std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); } \
     cudaMemset((ptr), 0, (bytes));                                                                             \
   } while (0)
-  DD_ALLOC(s->ckpt, sizeof(float) * s->slot_floats * s->slots);
-  DD_ALLOC(s->grad[0], sizeof(float) * s->slot_floats);
-  DD_ALLOC(s->grad[1], sizeof(float) * s->slot_floats);
-  DD_ALLOC(s->mat0, sizeof(float4) * ENp);
-  DD_ALLOC(s->yield, sizeof(float) * ENp);
+  DD_ALLOC(s->ckpt, sizeof(float) * s->slot_floats * s->pslots);
+  DD_ALLOC(s->grad[0], sizeof(float) * 28 * ENp);  // 25 floats per particle: the gradient of (x, v, C | F)
+  DD_ALLOC(s->grad[1], sizeof(float) * 28 * ENp);
+  DD_ALLOC(s->gtmp, sizeof(float) * 25 * ENp);
   DD_ALLOC(s->grid, sizeof(float4) * eg);
   DD_ALLOC(s->grid_v, sizeof(float4) * eg);
   DD_ALLOC(s->ggrid_v, sizeof(float4) * eg);
@@ -1912,13 +2156,23 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
   DD_ALLOC(s->tfsr, sizeof(float4) * 64);
   DD_ALLOC(s->args, sizeof(float4) * 64);
   DD_ALLOC(s->cull, sizeof(float) * 64);
-  DD_ALLOC(s->perm, sizeof(int) * ENp);
   DD_ALLOC(s->keys, sizeof(unsigned) * ENp);
   DD_ALLOC(s->keys_alt, sizeof(unsigned) * ENp);
-  DD_ALLOC(s->idx_alt, sizeof(int) * ENp);
+  DD_ALLOC(s->iota, sizeof(int) * ENp);
+  DD_ALLOC(s->sorted_idx, sizeof(int) * ENp);
+  DD_ALLOC(s->stor_idx, sizeof(int) * ENp);
+  DD_ALLOC(s->perm_tmp, sizeof(int) * ENp);
   DD_ALLOC(s->mat_aos, sizeof(float) * 5 * ENp);
-  cub::DeviceRadixSort::SortPairs(nullptr, s->cub_bytes, s->keys, s->keys_alt, s->idx_alt, s->perm, kp.EN);
+  DD_ALLOC(s->perm_pool, sizeof(int) * ENp * nseg);
+  DD_ALLOC(s->from_pool, sizeof(int) * ENp * nseg);
+  DD_ALLOC(s->mat0_pool, sizeof(float4) * ENp * nseg);
+  DD_ALLOC(s->yield_pool, sizeof(float) * ENp * nseg);
+  DD_ALLOC(s->cnt_pool, sizeof(int) * 8 * nseg);
+  DD_ALLOC(s->counters, sizeof(int) * 8);
+  cub::DeviceRadixSort::SortPairs(nullptr, s->cub_bytes, s->keys, s->keys_alt, s->iota, s->sorted_idx, kp.EN);
   DD_ALLOC(s->cub_tmp, s->cub_bytes + 16);
+  s->segs.resize(nseg);
+  s->slot_epoch.assign(s->pslots, -1);
   if (cfg->tile_mode) {
     if (!cfg->sort_particles) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode requires sort_particles"); }
     if ((kp.gx | kp.gy | kp.gz) & 3) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode needs grid dimensions that are multiples of 4"); }
@@ -1938,9 +2192,10 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       cudaFuncSetAttribute(k_p2g_grad_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * big);
     }
     {
-      int dev = 0, sms = 1, occ = 1;
+      int dev = 0, occ = 1;
       cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, dev);
+      const int sms = s->sms;
       auto knob = [](const char *name, int dflt) { const char *e = getenv(name); int v = e ? atoi(e) : dflt; return v >= 1 && v <= 8 ? v : dflt; };
       s->w_p2g = knob("DD_WPB_P2G", s->w_p2g); s->w_g2pg = knob("DD_WPB_G2PG", s->w_g2pg); s->w_g2p = knob("DD_WPB_G2P", s->w_g2p); s->w_p2gg = knob("DD_WPB_P2GG", s->w_p2gg);
       size_t one = kTileN * sizeof(float4), two = (2 * kTileN + kStageG2PG * 32) * sizeof(float4), one_p2g = (kTileN + kStageP2G * 32) * sizeof(float4), one_g2p = kTileN * sizeof(float4);
@@ -1968,24 +2223,23 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       int warps = std::max(1, s->pb_p2g * s->w_p2g), per_warp = kp.EN / warps;
       s->chunk_max = per_warp >= 256 ? 256 : std::min(256, std::max(64, (per_warp / 2 + 31) / 32 * 32));
     }
-    int occ_cap = std::min(kp.EN, s->NBtot);
-    s->chunk_cap = kp.EN / s->chunk_max + occ_cap + 1;
-    DD_ALLOC(s->chunks, sizeof(int4) * s->chunk_cap);
+    s->occ_cap = std::min(kp.EN, s->NBtot);
+    s->chunk_cap = kp.EN / s->chunk_max + s->occ_cap + 1;  // every occupied brick adds at most one partly filled chunk
+    DD_ALLOC(s->chunks_tmp, sizeof(int4) * s->chunk_cap);
+    DD_ALLOC(s->chunk_src_tmp, sizeof(int4) * s->chunk_cap);
     DD_ALLOC(s->chunk_src, sizeof(int4) * s->chunk_cap);
-    DD_ALLOC(s->chunks_alt, sizeof(int4) * s->chunk_cap);
-    DD_ALLOC(s->chunk_src_alt, sizeof(int4) * s->chunk_cap);
     DD_ALLOC(s->chunk_sort, sizeof(int) * 4 * s->chunk_cap);
     cub::DeviceRadixSort::SortPairsDescending(nullptr, s->csort_bytes, s->chunk_sort, s->chunk_sort, s->chunk_sort, s->chunk_sort, s->chunk_cap);
     DD_ALLOC(s->csort_tmp, s->csort_bytes + 16);
-    DD_ALLOC(s->head_pos, sizeof(int) * (occ_cap + 1));
+    DD_ALLOC(s->head_pos, sizeof(int) * (s->occ_cap + 1));
     DD_ALLOC(s->spos, sizeof(int) * ENp);
     DD_ALLOC(s->head_flags, ENp);
-    DD_ALLOC(s->active_flag, s->NBtot);
-    DD_ALLOC(s->active, sizeof(int) * s->NBtot);
-    DD_ALLOC(s->counters, sizeof(int) * 8);
+    DD_ALLOC(s->chunks_pool, sizeof(int4) * (size_t)s->chunk_cap * nseg);
+    DD_ALLOC(s->active_pool, sizeof(int) * (size_t)s->NBtot * nseg);
+    DD_ALLOC(s->flags_pool, sizeof(int) * (size_t)s->NBtot * nseg);
     size_t b1 = 0, b2 = 0;
-    cub::DeviceSelect::Flagged(nullptr, b1, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, s->counters, kp.EN);
-    cub::DeviceSelect::Flagged(nullptr, b2, cub::CountingInputIterator<int>(0), s->active_flag, s->active, s->counters, s->NBtot);
+    cub::DeviceSelect::Flagged(nullptr, b1, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, s->cnt_pool, kp.EN);
+    cub::DeviceSelect::Flagged(nullptr, b2, cub::CountingInputIterator<int>(0), s->flags_pool, s->active_pool, s->cnt_pool, s->NBtot);
     s->sel_bytes = std::max(b1, b2);
     DD_ALLOC(s->sel_tmp, s->sel_bytes + 16);
     // per-substep grid checkpoints (no scatter / grid-update replay in the backward pass) if they fit
@@ -1998,12 +2252,23 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       DD_ALLOC(s->gridvck, sizeof(float4) * eg * (size_t)cfg->max_steps);
     }
   }
+  for (int k = 0; k < nseg; ++k) {
+    Segment &sg = s->segs[k];
+    sg.perm = s->perm_pool + (size_t)k * ENp; sg.from_prev = s->from_pool + (size_t)k * ENp;
+    sg.mat0 = s->mat0_pool + (size_t)k * ENp; sg.yield = s->yield_pool + (size_t)k * ENp;
+    sg.cnt = s->cnt_pool + 8 * k;
+    if (cfg->tile_mode) {
+      sg.chunks = s->chunks_pool + (size_t)k * s->chunk_cap;
+      sg.active = s->active_pool + (size_t)k * s->NBtot; sg.flags = s->flags_pool + (size_t)k * s->NBtot;
+    }
+  }
   s->stage_floats = std::max((size_t)kp.EN * (24 > kp.nb ? 24 : kp.nb), (size_t)7 * s->slots * kp.E * kp.nb);  // states / distances, or every pose of every slot
   DD_ALLOC(s->stage, sizeof(float) * s->stage_floats);
 #undef DD_ALLOC
   std::vector<int> ident(kp.EN);
   for (int i = 0; i < kp.EN; ++i) ident[i] = i;
-  cudaMemcpy(s->perm, ident.data(), sizeof(int) * kp.EN, cudaMemcpyHostToDevice);
+  cudaMemcpy(s->iota, ident.data(), sizeof(int) * kp.EN, cudaMemcpyHostToDevice);
+  cudaMemcpy(s->segs[0].perm, ident.data(), sizeof(int) * kp.EN, cudaMemcpyHostToDevice);
   *out = s;
   return 0;
 }
@@ -2014,9 +2279,10 @@ void dd_sim_destroy(dd_sim *s) {
   if (s->side) cudaStreamDestroy(s->side);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_join) cudaEventDestroy(s->ev_join);
-  void *ptrs[] = {s->ckpt, s->grad[0], s->grad[1], s->mat0, s->yield, s->grid, s->grid_v, s->ggrid_v, s->ggrid, s->pos, s->rot, s->gpos, s->grot,
-                  s->tfsr, s->args, s->cull, s->perm, s->stage, s->keys, s->keys_alt, s->idx_alt, s->cub_tmp, s->mat_aos,
-                  s->chunks, s->chunk_src, s->chunks_alt, s->chunk_src_alt, s->chunk_sort, s->csort_tmp, s->head_pos, s->spos, s->head_flags, s->active_flag, s->active, s->counters, s->sel_tmp, s->gridck, s->gridvck};
+  void *ptrs[] = {s->ckpt, s->grad[0], s->grad[1], s->gtmp, s->grid, s->grid_v, s->ggrid_v, s->ggrid, s->pos, s->rot, s->gpos, s->grot,
+                  s->tfsr, s->args, s->cull, s->stage, s->keys, s->keys_alt, s->iota, s->sorted_idx, s->stor_idx, s->perm_tmp, s->cub_tmp, s->mat_aos,
+                  s->chunks_tmp, s->chunk_src_tmp, s->chunk_src, s->chunk_sort, s->csort_tmp, s->head_pos, s->spos, s->head_flags, s->counters, s->sel_tmp,
+                  s->perm_pool, s->from_pool, s->mat0_pool, s->yield_pool, s->cnt_pool, s->chunks_pool, s->active_pool, s->flags_pool, s->gridck, s->gridvck};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -2032,7 +2298,8 @@ int dd_sim_set_material(dd_sim *s, const float *mass, const float *vol, const fl
   DD_CUDA(cudaMemcpyAsync(a, mass, sizeof(float) * EN, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemcpyAsync(b, vol, sizeof(float) * EN, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemcpyAsync(c, mu_lam_yield, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
-  k_pack_mat<<<nblk(EN), kT, 0, st>>>(EN, s->perm, a, b, c, s->mat0, s->yield);
+  for (auto &sg : s->segs)
+    if (sg.epoch > 0 || &sg == &s->segs[0]) k_pack_mat<<<nblk(EN), kT, 0, st>>>(EN, sg.perm, a, b, c, sg.mat0, sg.yield);
   DD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -2058,6 +2325,8 @@ int dd_sim_set_bodies(dd_sim *s, const float *tfsr, const float *args) {
   return 0;
 }
 
+// State f from the caller's arrays (host or device).  Starts a new particle order for f's segment; nothing here waits for
+// the device (the caller synchronises before releasing host buffers).
 int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const float *F, const float *C, cudaStream_t st) {
   if (check_range(s, f, 0, "dd_sim_set_state")) return 1;
   if (!x || !v || !F || !C) return fail("dd_sim_set_state: x, v, F, C are all required");
@@ -2071,73 +2340,52 @@ int dd_sim_set_state(dd_sim *s, int f, const float *x, const float *v, const flo
   DD_CUDA(cudaMemcpyAsync(sF, F, sizeof(float) * 9 * EN, cudaMemcpyDefault, s->side));
   DD_CUDA(cudaMemcpyAsync(sC, C, sizeof(float) * 9 * EN, cudaMemcpyDefault, s->side));
   DD_CUDA(cudaEventRecord(s->ev_join, s->side));
-  if (s->cfg.sort_particles) {
-    // cell-sorted particle order: environment, 4^3-cell brick, cell.  perm maps sorted -> original index.
-    if (s->cfg.tile_mode) DD_CUDA(cudaMemsetAsync(s->active_flag, 0, s->NBtot, st));
-    k_sort_keys<<<nblk(EN), kT, 0, st>>>(s->kp, sx, s->keys, s->idx_alt);
-    int bits = 1;
-    while (bits < 32 && (1ull << bits) < (unsigned long long)s->kp.E * s->kp.G) ++bits;
-    DD_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_tmp, s->cub_bytes, s->keys, s->keys_alt, s->idx_alt, s->perm, EN, 0, bits, st));
-    if (s->cfg.tile_mode) {
-      const KP &kp = s->kp;
-      int host[4] = {0, 0, 0, 0};
-      k_mark_heads<<<nblk(EN), kT, 0, st>>>(kp, s->keys_alt, s->head_flags, s->active_flag);
-      DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->head_flags, s->head_pos, s->counters + 2, EN, st));
-      DD_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(int) * 2, st));
-      DD_CUDA(cudaMemsetAsync(s->counters + 4, 0, sizeof(int) * 2, st));  // chunk tickets: start clean even after an aborted launch
-      DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-      DD_CUDA(cudaStreamSynchronize(st));
-      int nbricks = host[2];
-      k_make_chunks<<<nblk(nbricks), kT, 0, st>>>(kp, nbricks, s->head_pos, s->keys_alt, s->chunk_max, s->chunks, s->chunk_src, s->counters);
-      DD_CUDA(cub::DeviceSelect::Flagged(s->sel_tmp, s->sel_bytes, cub::CountingInputIterator<int>(0), s->active_flag, s->active, s->counters + 1, s->NBtot, st));
-      DD_CUDA(cudaMemcpyAsync(host, s->counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-      DD_CUDA(cudaStreamSynchronize(st));
-      s->nchunks = host[0];
-      s->nactive = host[1];
-      if (s->nchunks > s->chunk_cap) return fail("dd_sim_set_state: chunk list overflow");
-      {
-        int nc = s->nchunks, cap = s->chunk_cap;
-        int *ck = s->chunk_sort, *cks = ck + cap, *ci = ck + 2 * cap, *cis = ck + 3 * cap;
-        k_chunk_keys<<<nblk(nc), kT, 0, st>>>(nc, s->chunks, ck, ci);
-        DD_CUDA(cub::DeviceRadixSort::SortPairsDescending(s->csort_tmp, s->csort_bytes, ck, cks, ci, cis, nc, 0, 32, st));
-        k_chunk_permute<<<nblk(nc), kT, 0, st>>>(nc, cis, s->chunks, s->chunk_src, s->chunks_alt, s->chunk_src_alt);
-        std::swap(s->chunks, s->chunks_alt);
-        std::swap(s->chunk_src, s->chunk_src_alt);
-      }
-      k_interleave<<<nblk((long long)s->nchunks * 32), kT, 0, st>>>(kp, s->nchunks, s->chunks, s->chunk_src, s->keys_alt, s->perm, s->idx_alt, s->spos);
-      std::swap(s->perm, s->idx_alt);
-      // the active region changed: drop stale graphs (they captured the old launch geometry) and stale grid contents
-      for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
-      s->graphs.clear();
-      size_t eg = (size_t)kp.E * kp.G;
-      DD_CUDA(cudaMemsetAsync(s->grid, 0, sizeof(float4) * eg, st));
-      DD_CUDA(cudaMemsetAsync(s->grid_v, 0, sizeof(float4) * eg, st));
-      DD_CUDA(cudaMemsetAsync(s->ggrid_v, 0, sizeof(float4) * eg, st));
-      DD_CUDA(cudaMemsetAsync(s->ggrid, 0, sizeof(float4) * eg, st));
-    }
-    if (s->have_material) {
-      float *a = s->mat_aos;
-      k_pack_mat<<<nblk(EN), kT, 0, st>>>(EN, s->perm, a, a + EN, a + 2 * (size_t)EN, s->mat0, s->yield);
-    }
-    for (int k = 0; k < 2; ++k) s->grad_holds[k] = -1;  // gradient slots refer to the previous ordering
+  int k = s->seg_of(f), p = s->phys_cur(f);
+  if (s->cfg.sort_particles || s->segs[k].epoch == 0) {
+    if (s->cfg.tile_mode) DD_CUDA(cudaMemsetAsync(s->counters + 4, 0, sizeof(int) * 2, st));  // chunk tickets: start clean even after an aborted launch
+    if (enqueue_build(s, k, sx, -1, -1, p, st)) return 1;
+    segment_rebuilt(s, k, false, p);
+  } else {
+    s->slot_epoch[p] = s->segs[k].epoch;
   }
   DD_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
-  k_pack<<<nblk(EN), kT, 0, st>>>(EN, s->perm, sx, sv, sF, sC, s->slot(f));
+  k_pack<<<nblk(EN), kT, 0, st>>>(EN, s->segs[k].perm, sx, sv, sF, sC, s->pslot(p));
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Rolling window (mpm/simulator.py:626-634): state f_src becomes state 0, re-sorted on the device, poses included.
+int dd_sim_roll(dd_sim *s, int f_src, cudaStream_t st) {
+  if (check_range(s, f_src, 0, "dd_sim_roll")) return 1;
+  if (f_src == 0) return 0;
+  int src = 0, kprev = 0;
+  if (pick_copy(s, f_src, &src, &kprev, "dd_sim_roll")) return 1;
+  if (s->cfg.sort_particles) {
+    if (enqueue_build(s, 0, nullptr, src, kprev, 0, st)) return 1;
+  } else {
+    DD_CUDA(cudaMemcpyAsync(s->pslot(0), s->pslot(src), sizeof(float) * 29 * (size_t)s->kp.EN, cudaMemcpyDeviceToDevice, st));
+  }
+  segment_rebuilt(s, 0, false, 0);
+  if (!s->cfg.sort_particles) s->slot_epoch[0] = s->segs[0].epoch;
+  size_t ep = (size_t)s->kp.E * s->kp.nb;
+  if (ep) k_copy_poses<<<nblk((long long)ep), kT, 0, st>>>((int)ep, s->pos + (size_t)f_src * ep, s->rot + (size_t)f_src * ep, s->pos, s->rot);
   DD_CUDA(cudaGetLastError());
   return 0;
 }
 
 int dd_sim_get_state(dd_sim *s, int f, float *x, float *v, float *F, float *C, cudaStream_t st) {
   if (check_range(s, f, 0, "dd_sim_get_state")) return 1;
+  int p = 0, k = 0;
+  if (pick_copy(s, f, &p, &k, "dd_sim_get_state")) return 1;
   int EN = s->kp.EN;
   float *sx = s->stage, *sv = sx + 3 * (size_t)EN, *sF = sv + 3 * (size_t)EN, *sC = sF + 9 * (size_t)EN;
-  k_unpack<<<nblk(EN), kT, 0, st>>>(EN, s->perm, s->slot(f), x ? sx : nullptr, v ? sv : nullptr, F ? sF : nullptr, C ? sC : nullptr);
+  k_unpack<<<nblk(EN), kT, 0, st>>>(EN, s->segs[k].perm, s->pslot(p), x ? sx : nullptr, v ? sv : nullptr, F ? sF : nullptr, C ? sC : nullptr);
   DD_CUDA(cudaGetLastError());
   if (x) DD_CUDA(cudaMemcpyAsync(x, sx, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
   if (v) DD_CUDA(cudaMemcpyAsync(v, sv, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
   if (F) DD_CUDA(cudaMemcpyAsync(F, sF, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
   if (C) DD_CUDA(cudaMemcpyAsync(C, sC, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
-  DD_CUDA(cudaStreamSynchronize(st));
+  if (finish_readback(st, {x, v, F, C})) return 1;
   return 0;
 }
 
@@ -2157,10 +2405,39 @@ int dd_sim_set_poses(dd_sim *s, int f0, int count, const float *pos, const float
   DD_CUDA(cudaGetLastError());
   return 0;
 }
+int dd_sim_get_poses(dd_sim *s, int f0, int count, float *pos, float *rot, cudaStream_t st) {
+  if (!s) return fail("dd_sim_get_poses: null simulator");
+  if (s->kp.nb == 0 || count == 0) return 0;
+  if (f0 < 0 || count < 0 || f0 + count > s->slots) return fail("dd_sim_get_poses: slot range out of bounds");
+  size_t n = (size_t)count * s->kp.E * s->kp.nb, o = (size_t)f0 * s->kp.E * s->kp.nb;
+  if (7 * n > s->stage_floats) return fail("dd_sim_get_poses: too many poses for the staging buffer; download in smaller chunks");
+  float *sp = s->stage, *sr = sp + 3 * n;
+  k_unpad4<<<nblk((long long)n), kT, 0, st>>>((int)n, s->pos + o, 3, sp, 0);
+  k_unpad4<<<nblk((long long)n), kT, 0, st>>>((int)n, s->rot + o, 4, sr, 0);
+  DD_CUDA(cudaGetLastError());
+  if (pos) DD_CUDA(cudaMemcpyAsync(pos, sp, sizeof(float) * 3 * n, cudaMemcpyDefault, st));
+  if (rot) DD_CUDA(cudaMemcpyAsync(rot, sr, sizeof(float) * 4 * n, cudaMemcpyDefault, st));
+  if (finish_readback(st, {pos, rot})) return 1;
+  return 0;
+}
 
 int dd_sim_forward(dd_sim *s, int f0, int n, cudaStream_t st) {
   if (check_range(s, f0, n, "dd_sim_forward")) return 1;
   if (n == 0) return 0;
+  // ---- plan: the first state must exist; a range that starts on a segment boundary re-sorts there unless the head copy is current
+  bool rebuild0 = false;
+  if (s->is_boundary(f0) && !s->valid(s->phys_cur(f0))) {
+    if (!s->valid(s->phys_tail(f0))) return fail("dd_sim_forward: state " + std::to_string(f0) + " is not available");
+    rebuild0 = true;
+  } else if (!s->valid(s->phys_cur(f0))) {
+    return fail("dd_sim_forward: state " + std::to_string(f0) + " is not available (dd_sim_set_state it, or run the substeps before it)");
+  }
+  for (int f = f0; f < f0 + n; ++f) {
+    int k = s->seg_of(f);
+    if (s->is_boundary(f) && (f > f0 || rebuild0)) segment_rebuilt(s, k, true, s->phys_cur(f));
+    s->slot_epoch[s->phys_cur(f) + 1] = s->segs[k].epoch;
+    if (s->is_boundary(f + 1)) s->slot_epoch[s->phys_cur(f + 1)] = -1;  // the head copy of the next segment is out of date now
+  }
   size_t ep = (size_t)s->kp.E * s->kp.nb;
   auto body = [&](cudaStream_t q) {
     // reference: states[f+i+1].clear_grad in the forward pass (mpm/simulator.py:570-571) -- pose gradients only here,
@@ -2169,71 +2446,105 @@ int dd_sim_forward(dd_sim *s, int f0, int n, cudaStream_t st) {
       cudaMemsetAsync(s->gpos + (size_t)(f0 + 1) * ep, 0, sizeof(float4) * ep * n, q);
       cudaMemsetAsync(s->grot + (size_t)(f0 + 1) * ep, 0, sizeof(float4) * ep * n, q);
     }
-    if (s->cfg.tile_mode) {
-      k_zero_bricks<<<nblk((long long)s->nactive * 64), kT, 0, q>>>(s->kp, s->nactive, s->active, s->G(f0), nullptr);
-      s->launches += 1;
-    }
     for (int f = f0; f < f0 + n; ++f) {
+      bool resort = s->is_boundary(f) && (f > f0 || rebuild0);
+      if (resort) enqueue_build(s, s->seg_of(f), nullptr, s->phys_tail(f), s->seg_of(f - 1), s->phys_cur(f), q);
+      if (s->cfg.tile_mode && (f == f0 || resort)) {  // scatter target of the first substep under this active list
+        const Segment &sg = s->segs[s->seg_of(f)];
+        k_zero_bricks<<<s->brick_blocks(), kT, 0, q>>>(s->kp, sg.cnt, sg.active, s->G(f), nullptr);
+        s->launches += 1;
+      }
       if (s->cfg.svd_mode == 0) enqueue_forward_substep<0>(s, f, q); else enqueue_forward_substep<1>(s, f, q);
     }
   };
-  return run_graphed(s, 0, f0, n, st, (long long)fwd_launches(s) * n + (s->cfg.tile_mode ? 1 : 0), body);
+  return run_graphed(s, 0, f0, n, rebuild0 ? 1 : 0, st, body);
 }
 
 int dd_sim_zero_grad(dd_sim *s, int f, cudaStream_t st) {
   if (check_range(s, f, 0, "dd_sim_zero_grad")) return 1;
   size_t ep = (size_t)s->kp.E * s->kp.nb;
-  DD_CUDA(cudaMemsetAsync(s->grad[f & 1], 0, sizeof(float) * s->slot_floats, st));
+  DD_CUDA(cudaMemsetAsync(s->grad[f & 1], 0, sizeof(float) * 25 * (size_t)s->kp.EN, st));
   s->grad_holds[f & 1] = f;
+  s->grad_order[f & 1] = -1;
   if (ep) {
     DD_CUDA(cudaMemsetAsync(s->gpos + (size_t)f * ep, 0, sizeof(float4) * ep, st));
     DD_CUDA(cudaMemsetAsync(s->grot + (size_t)f * ep, 0, sizeof(float4) * ep, st));
   }
   return 0;
 }
+// pose gradients of state f only (GradModel.zero_grad clears states[0]'s gradients, mpm/torch_wrapper.py:26)
+int dd_sim_zero_pose_grads(dd_sim *s, int f0, int count, cudaStream_t st) {
+  if (!s) return fail("dd_sim_zero_pose_grads: null simulator");
+  if (f0 < 0 || count < 0 || f0 + count > s->slots) return fail("dd_sim_zero_pose_grads: slot range out of bounds");
+  size_t ep = (size_t)s->kp.E * s->kp.nb;
+  if (ep && count) {
+    DD_CUDA(cudaMemsetAsync(s->gpos + (size_t)f0 * ep, 0, sizeof(float4) * ep * count, st));
+    DD_CUDA(cudaMemsetAsync(s->grot + (size_t)f0 * ep, 0, sizeof(float4) * ep * count, st));
+  }
+  return 0;
+}
 
 int dd_sim_add_state_grad(dd_sim *s, int f, const float *gx, const float *gv, const float *gF, const float *gC, cudaStream_t st) {
   if (check_range(s, f, 0, "dd_sim_add_state_grad")) return 1;
-  if (s->grad_holds[f & 1] != f) return fail("dd_sim_add_state_grad: gradient slot does not hold state " + std::to_string(f) + " (call dd_sim_zero_grad or run the backward pass down to it first)");
+  int p = 0, k = 0;
+  if (grad_copy(s, f, &p, &k, "dd_sim_add_state_grad")) return 1;
   int EN = s->kp.EN;
   float *sx = s->stage, *sv = sx + 3 * (size_t)EN, *sF = sv + 3 * (size_t)EN, *sC = sF + 9 * (size_t)EN;
   if (gx) DD_CUDA(cudaMemcpyAsync(sx, gx, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
   if (gv) DD_CUDA(cudaMemcpyAsync(sv, gv, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
   if (gF) DD_CUDA(cudaMemcpyAsync(sF, gF, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
   if (gC) DD_CUDA(cudaMemcpyAsync(sC, gC, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
-  k_add_grad<<<nblk(EN), kT, 0, st>>>(EN, s->perm, gx ? sx : nullptr, gv ? sv : nullptr, gF ? sF : nullptr, gC ? sC : nullptr, s->grad[f & 1]);
+  k_add_grad<<<nblk(EN), kT, 0, st>>>(EN, s->segs[k].perm, gx ? sx : nullptr, gv ? sv : nullptr, gF ? sF : nullptr, gC ? sC : nullptr, s->grad[f & 1]);
   DD_CUDA(cudaGetLastError());
   return 0;
 }
 
 int dd_sim_get_state_grad(dd_sim *s, int f, float *gx, float *gv, float *gF, float *gC, cudaStream_t st) {
   if (check_range(s, f, 0, "dd_sim_get_state_grad")) return 1;
-  if (s->grad_holds[f & 1] != f) return fail("dd_sim_get_state_grad: gradient slot does not hold state " + std::to_string(f));
+  int p = 0, k = 0;
+  if (grad_copy(s, f, &p, &k, "dd_sim_get_state_grad")) return 1;
   int EN = s->kp.EN;
   float *sx = s->stage, *sv = sx + 3 * (size_t)EN, *sF = sv + 3 * (size_t)EN, *sC = sF + 9 * (size_t)EN;
-  k_unpack<<<nblk(EN), kT, 0, st>>>(EN, s->perm, s->grad[f & 1], gx ? sx : nullptr, gv ? sv : nullptr, gF ? sF : nullptr, gC ? sC : nullptr);
+  k_unpack<<<nblk(EN), kT, 0, st>>>(EN, s->segs[k].perm, s->grad[f & 1], gx ? sx : nullptr, gv ? sv : nullptr, gF ? sF : nullptr, gC ? sC : nullptr);
   DD_CUDA(cudaGetLastError());
   if (gx) DD_CUDA(cudaMemcpyAsync(gx, sx, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
   if (gv) DD_CUDA(cudaMemcpyAsync(gv, sv, sizeof(float) * 3 * EN, cudaMemcpyDefault, st));
   if (gF) DD_CUDA(cudaMemcpyAsync(gF, sF, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
   if (gC) DD_CUDA(cudaMemcpyAsync(gC, sC, sizeof(float) * 9 * EN, cudaMemcpyDefault, st));
-  DD_CUDA(cudaStreamSynchronize(st));
+  if (finish_readback(st, {gx, gv, gF, gC})) return 1;
   return 0;
 }
 
 int dd_sim_backward(dd_sim *s, int f0, int n, cudaStream_t st) {
   if (check_range(s, f0, n, "dd_sim_backward")) return 1;
   if (n == 0) return 0;
-  if (s->grad_holds[(f0 + n) & 1] != f0 + n) return fail("dd_sim_backward: no gradient seeded for state " + std::to_string(f0 + n) + " (dd_sim_zero_grad + dd_sim_add_state_grad)");
+  const int ft = f0 + n, gi = ft & 1;
+  if (s->grad_holds[gi] != ft) return fail("dd_sim_backward: no gradient seeded for state " + std::to_string(ft) + " (dd_sim_zero_grad + dd_sim_add_state_grad)");
+  // ---- plan: the seed must be (or be brought) in the order of the segment that produced state ft
+  const int want = s->seg_of(ft - 1);
+  bool permute_top = false;
+  if (s->grad_order[gi] >= 0 && s->grad_order[gi] != want) {
+    if (s->is_boundary(ft) && s->grad_order[gi] == s->seg_of(ft)) permute_top = true;
+    else return fail("dd_sim_backward: the gradient of state " + std::to_string(ft) + " is stored in the particle order of another segment");
+  }
+  for (int f = f0; f < ft; ++f) {
+    if (!s->valid(s->phys_cur(f)) || !s->valid(s->phys_cur(f) + 1))
+      return fail("dd_sim_backward: the checkpoints of substep " + std::to_string(f) + " are not available (run dd_sim_forward over it first; dd_sim_set_state or a re-sort replaced them)");
+    if (s->is_boundary(f + 1) && (f + 1 < ft || permute_top) && !s->segs[s->seg_of(f + 1)].linked)
+      return fail("dd_sim_backward: cannot back-propagate across state " + std::to_string(f + 1) + ": it was set with dd_sim_set_state, not computed");
+  }
   auto body = [&](cudaStream_t q) {
-    for (int f = f0 + n - 1; f >= f0; --f) {
+    for (int f = ft - 1; f >= f0; --f) {
+      if (s->is_boundary(f + 1) && (f + 1 < ft || permute_top)) enqueue_grad_permute(s, s->seg_of(f + 1), (f + 1) & 1, q);
       if (s->cfg.svd_mode == 0) enqueue_backward_substep<0>(s, f, q); else enqueue_backward_substep<1>(s, f, q);
     }
   };
-  int rc = run_graphed(s, 1, f0, n, st, (long long)bwd_launches(s) * n, body);
+  int rc = run_graphed(s, 1, f0, n, permute_top ? 1 : 0, st, body);
   if (rc) return rc;
   s->grad_holds[f0 & 1] = f0;
-  s->grad_holds[(f0 + 1) & 1] = n >= 1 ? f0 + 1 : s->grad_holds[(f0 + 1) & 1];
+  s->grad_order[f0 & 1] = s->seg_of(f0);
+  s->grad_holds[(f0 + 1) & 1] = f0 + 1;
+  s->grad_order[(f0 + 1) & 1] = s->seg_of(f0);
   return 0;
 }
 
@@ -2249,7 +2560,7 @@ int dd_sim_get_pose_grads(dd_sim *s, int f0, int count, float *gpos, float *grot
   DD_CUDA(cudaGetLastError());
   if (gpos) DD_CUDA(cudaMemcpyAsync(gpos, sp, sizeof(float) * 3 * n, cudaMemcpyDefault, st));
   if (grot) DD_CUDA(cudaMemcpyAsync(grot, sr, sizeof(float) * 4 * n, cudaMemcpyDefault, st));
-  DD_CUDA(cudaStreamSynchronize(st));
+  if (finish_readback(st, {gpos, grot})) return 1;
   return 0;
 }
 
@@ -2274,11 +2585,13 @@ int dd_sim_compute_dist(dd_sim *s, int f, float *dist, cudaStream_t st) {
   if (check_range(s, f, 0, "dd_sim_compute_dist")) return 1;
   if (s->kp.nb == 0) return 0;
   if (!dist) return fail("dd_sim_compute_dist: null output");
+  int p = 0, k = 0;
+  if (pick_copy(s, f, &p, &k, "dd_sim_compute_dist")) return 1;
   size_t n = (size_t)s->kp.EN * s->kp.nb;
-  k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->tables(f), s->stage, nullptr, nullptr, nullptr, nullptr, 0);
+  k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->tables(f), s->stage, nullptr, nullptr, nullptr, nullptr, 0);
   DD_CUDA(cudaGetLastError());
   DD_CUDA(cudaMemcpyAsync(dist, s->stage, sizeof(float) * n, cudaMemcpyDefault, st));
-  DD_CUDA(cudaStreamSynchronize(st));
+  if (finish_readback(st, {dist})) return 1;
   return 0;
 }
 
@@ -2286,10 +2599,12 @@ int dd_sim_compute_dist_grad(dd_sim *s, int f, const float *dist_grad, cudaStrea
   if (check_range(s, f, 0, "dd_sim_compute_dist_grad")) return 1;
   if (s->kp.nb == 0) return 0;
   if (!dist_grad) return fail("dd_sim_compute_dist_grad: null argument");
-  if (s->grad_holds[f & 1] != f) return fail("dd_sim_compute_dist_grad: gradient slot does not hold state " + std::to_string(f));
+  int p = 0, k = 0;
+  if (grad_copy(s, f, &p, &k, "dd_sim_compute_dist_grad")) return 1;
+  if (!s->valid(p)) return fail("dd_sim_compute_dist_grad: state " + std::to_string(f) + " is not available");
   size_t n = (size_t)s->kp.EN * s->kp.nb, ep = (size_t)s->kp.E * s->kp.nb;
   DD_CUDA(cudaMemcpyAsync(s->stage, dist_grad, sizeof(float) * n, cudaMemcpyDefault, st));
-  k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->tables(f), nullptr, s->stage, s->grad[f & 1], s->gpos + (size_t)f * ep,
+  k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->tables(f), nullptr, s->stage, s->grad[f & 1], s->gpos + (size_t)f * ep,
                                         s->grot + (size_t)f * ep, 1);
   DD_CUDA(cudaGetLastError());
   return 0;
@@ -2301,16 +2616,18 @@ int dd_sim_profile_substep(dd_sim *s, int f, int reps, float *ms_out, char *name
   if (check_range(s, f, 1, "dd_sim_profile_substep")) return 1;
   if (!s->cfg.tile_mode || !s->grid_ckpt) return fail("dd_sim_profile_substep: needs tile_mode with grid checkpoints");
   if (s->grad_holds[(f + 1) & 1] != f + 1) return fail("dd_sim_profile_substep: seed a gradient for state f+1 first");
+  if (!s->valid(s->phys_cur(f))) return fail("dd_sim_profile_substep: state f is not available");
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> names;
   std::vector<double> acc;
+  const Segment &sg = s->segs[s->seg_of(f)];
   for (int r = 0; r < reps; ++r) {
     size_t k = 0;
     auto new_event = [&]() {
       if (k >= ev.size()) { cudaEvent_t e_; cudaEventCreate(&e_); ev.push_back(e_); }
       cudaEventRecord(ev[k++], st);
     };
-    k_zero_bricks<<<nblk((long long)s->nactive * 64), kT, 0, st>>>(s->kp, s->nactive, s->active, s->G(f), nullptr);  // untimed: scatter target of this substep
+    k_zero_bricks<<<s->brick_blocks(), kT, 0, st>>>(s->kp, sg.cnt, sg.active, s->G(f), nullptr);  // untimed: scatter target of this substep
     new_event();
     Mark mk = [&](const char *name) { if (r == 0) names.push_back(name); new_event(); };
     if (s->cfg.svd_mode == 0) { enqueue_forward_substep<0>(s, f, st, &mk); enqueue_backward_substep<0>(s, f, st, &mk); }
@@ -2325,7 +2642,9 @@ int dd_sim_profile_substep(dd_sim *s, int f, int reps, float *ms_out, char *name
   if ((int)joined.size() + 1 > names_cap) return fail("dd_sim_profile_substep: names buffer too small");
   std::memcpy(names_out, joined.c_str(), joined.size() + 1);
   *n_out = (int)names.size();
+  s->slot_epoch[s->phys_cur(f) + 1] = sg.epoch;
   s->grad_holds[f & 1] = f;
+  s->grad_order[f & 1] = s->seg_of(f);
   return 0;
 }
 
@@ -2334,38 +2653,56 @@ int dd_sim_compute_grid_mass(dd_sim *s, int f, const int *ids, int id, float *ou
   if (check_range(s, f, 0, "dd_sim_compute_grid_mass")) return 1;
   if (!out) return fail("dd_sim_compute_grid_mass: null output");
   if (id != -1 && !ids) return fail("dd_sim_compute_grid_mass: object ids required when id != -1");
+  int p = 0, k = 0;
+  if (pick_copy(s, f, &p, &k, "dd_sim_compute_grid_mass")) return 1;
   size_t eg = (size_t)s->kp.E * s->kp.G;
   float *buf = reinterpret_cast<float *>(s->ggrid);  // scratch: E*G floats fit in the float4 adjoint grid
   int *dids = reinterpret_cast<int *>(s->keys);
   if (ids) DD_CUDA(cudaMemcpyAsync(dids, ids, sizeof(int) * s->kp.EN, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemsetAsync(buf, 0, sizeof(float) * eg, st));
-  k_grid_mass<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->mat0, ids ? dids : nullptr, id, buf, nullptr, nullptr, 0);
+  k_grid_mass<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->segs[k].mat0, ids ? dids : nullptr, id, buf, nullptr, nullptr, 0);
   DD_CUDA(cudaGetLastError());
   DD_CUDA(cudaMemcpyAsync(out, buf, sizeof(float) * eg, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemsetAsync(buf, 0, sizeof(float) * eg, st));  // ggrid must stay zero outside the active bricks
-  DD_CUDA(cudaStreamSynchronize(st));
+  if (finish_readback(st, {out})) return 1;
   return 0;
 }
 int dd_sim_compute_grid_mass_grad(dd_sim *s, int f, const int *ids, int id, const float *grid_m_grad, cudaStream_t st) {
   if (check_range(s, f, 0, "dd_sim_compute_grid_mass_grad")) return 1;
   if (!grid_m_grad) return fail("dd_sim_compute_grid_mass_grad: null argument");
   if (id != -1 && !ids) return fail("dd_sim_compute_grid_mass_grad: object ids required when id != -1");
-  if (s->grad_holds[f & 1] != f) return fail("dd_sim_compute_grid_mass_grad: gradient slot does not hold state " + std::to_string(f));
+  int p = 0, k = 0;
+  if (grad_copy(s, f, &p, &k, "dd_sim_compute_grid_mass_grad")) return 1;
+  if (!s->valid(p)) return fail("dd_sim_compute_grid_mass_grad: state " + std::to_string(f) + " is not available");
   size_t eg = (size_t)s->kp.E * s->kp.G;
   float *buf = reinterpret_cast<float *>(s->ggrid);
   int *dids = reinterpret_cast<int *>(s->keys);
   if (ids) DD_CUDA(cudaMemcpyAsync(dids, ids, sizeof(int) * s->kp.EN, cudaMemcpyDefault, st));
   DD_CUDA(cudaMemcpyAsync(buf, grid_m_grad, sizeof(float) * eg, cudaMemcpyDefault, st));
-  k_grid_mass<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->perm, s->slot(f), s->mat0, ids ? dids : nullptr, id, nullptr, buf, s->grad[f & 1], 1);
+  k_grid_mass<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->segs[k].mat0, ids ? dids : nullptr, id, nullptr, buf, s->grad[f & 1], 1);
   DD_CUDA(cudaGetLastError());
   DD_CUDA(cudaMemsetAsync(buf, 0, sizeof(float) * eg, st));
+  return 0;
+}
+
+// diagnostics: out = {segment of state f, chunks, active bricks, occupied bricks, epoch, linked} (synchronises)
+int dd_sim_segment_info(dd_sim *s, int f, int *out, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_segment_info")) return 1;
+  if (!out) return fail("dd_sim_segment_info: null output");
+  int k = s->seg_of(f), host[4] = {0, 0, 0, 0};
+  if (s->cfg.tile_mode) {
+    DD_CUDA(cudaMemcpyAsync(host, s->segs[k].cnt, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    DD_CUDA(cudaStreamSynchronize(st));
+  }
+  out[0] = k; out[1] = host[0]; out[2] = host[1]; out[3] = host[2]; out[4] = s->segs[k].epoch; out[5] = s->segs[k].linked ? 1 : 0;
+  out[6] = s->nseg; out[7] = s->L;
   return 0;
 }
 
 int dd_sim_sync(dd_sim *s, cudaStream_t st) {
   if (!s) return fail("dd_sim_sync: null simulator");
   DD_CUDA(cudaStreamSynchronize(st));
-  return check_overflow(s);
+  return 0;
 }
 
 }  // extern "C"

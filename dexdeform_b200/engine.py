@@ -1,5 +1,7 @@
 """``FusedSim`` -- thin Python handle on the fused engine (ABI-2).  No arithmetic happens here: every method is one
-C-ABI call.  Arrays may be numpy arrays (host) or torch CUDA tensors (device); both are passed as raw pointers."""
+C-ABI call.  Arrays may be numpy arrays (host) or torch CUDA tensors (device); both are passed as raw pointers.  Getters
+return numpy by default and torch CUDA tensors with ``device=True`` -- in that case nothing waits for the GPU (the engine
+enqueues on ``stream``; give it the stream torch is using, or leave both on the legacy default stream)."""
 import ctypes
 
 import numpy as np
@@ -19,13 +21,18 @@ def _ptr(a):
     return a.data_ptr()
 
 
+def _is_host(*arrays):
+    return any(isinstance(a, np.ndarray) or (a is not None and hasattr(a, "is_cuda") and not a.is_cuda) for a in arrays)
+
+
 class EngineError(RuntimeError):
     pass
 
 
 class FusedSim:
     def __init__(self, n_envs, n_particles, n_bodies, grid_dim, dx, dt, max_steps, ground_friction=0.0, ground_height=3.0,
-                 gravity=(0.0, -30.0, 0.0), svd_mode=1, use_graphs=True, sort_particles=True, tile_mode=True, grid_ckpt=True, chunk_max=0, library=None, stream=None):
+                 gravity=(0.0, -30.0, 0.0), svd_mode=1, use_graphs=True, sort_particles=True, tile_mode=True, grid_ckpt=True, chunk_max=0,
+                 resort_interval=0, library=None, stream=None):
         self.lib = library if library is not None else _default_lib
         self.E, self.N, self.nb = int(n_envs), int(n_particles), int(n_bodies)
         self.grid_dim = tuple(int(g) for g in grid_dim)
@@ -33,7 +40,8 @@ class FusedSim:
         self.dx, self.dt = float(dx), float(dt)
         self.stream = stream  # raw cudaStream_t (int) or None for the legacy default stream
         cfg = dd_sim_config(self.E, self.N, self.nb, *self.grid_dim, self.max_steps, self.dx, self.dt, float(ground_friction),
-                            float(ground_height), (ctypes.c_float * 3)(*[float(g) for g in gravity]), int(svd_mode), int(bool(use_graphs)), int(bool(sort_particles)), int(bool(tile_mode)), int(bool(grid_ckpt)), int(chunk_max))
+                            float(ground_height), (ctypes.c_float * 3)(*[float(g) for g in gravity]), int(svd_mode), int(bool(use_graphs)),
+                            int(bool(sort_particles)), int(bool(tile_mode)), int(bool(grid_ckpt)), int(chunk_max), int(resort_interval))
         handle = ctypes.c_void_p()
         self._h = None
         self._check(self.lib.dd_sim_create(ctypes.byref(cfg), ctypes.byref(handle)))
@@ -71,6 +79,12 @@ class FusedSim:
         except Exception:
             pass
 
+    def _empty(self, shape, device):
+        if device:
+            import torch
+            return torch.empty(shape, dtype=torch.float32, device="cuda")
+        return np.empty(shape, np.float32)
+
     # ---- setup
     def set_material(self, mass, vol, mu_lam_yield):
         self._check(self.lib.dd_sim_set_material(self._h, _ptr(mass), _ptr(vol), _ptr(mu_lam_yield), self.stream))
@@ -81,8 +95,14 @@ class FusedSim:
         self._check(self.lib.dd_sim_set_bodies(self._h, _ptr(tfsr), _ptr(args)))
 
     def set_state(self, f, x, v, F, C):
+        """(E, N, 3|9) arrays in the caller's particle order.  Starts a new particle order (cell sort) for f's segment."""
         self._check(self.lib.dd_sim_set_state(self._h, f, _ptr(x), _ptr(v), _ptr(F), _ptr(C), self.stream))
-        self.sync()  # host arrays may be released by the caller
+        if _is_host(x, v, F, C):
+            self.sync()  # host arrays may be released by the caller
+
+    def roll(self, f_src):
+        """State f_src (particles and poses) becomes state 0, re-sorted, without leaving the device (mpm/simulator.py:634)."""
+        self._check(self.lib.dd_sim_roll(self._h, int(f_src), self.stream))
 
     def set_poses(self, f0, pos, rot):
         """pos (count, E, nb, 3), rot (count, E, nb, 4 wxyz) for slots f0 .. f0+count-1."""
@@ -94,8 +114,14 @@ class FusedSim:
             if isinstance(p, np.ndarray):
                 p, r = np.ascontiguousarray(p, np.float32), np.ascontiguousarray(r, np.float32)
             self._check(self.lib.dd_sim_set_poses(self._h, f0 + c0, c1 - c0, _ptr(p), _ptr(r), self.stream))
-            if isinstance(p, np.ndarray):
+            if _is_host(p, r):
                 self.sync()
+
+    def get_poses(self, f0, count, device=False):
+        pos, rot = self._empty((count, self.E, self.nb, 3), device), self._empty((count, self.E, self.nb, 4), device)
+        if self.nb:
+            self._check(self.lib.dd_sim_get_poses(self._h, f0, count, _ptr(pos), _ptr(rot), self.stream))
+        return pos, rot
 
     # ---- simulation
     def forward(self, f0, n):
@@ -107,9 +133,13 @@ class FusedSim:
     def zero_grad(self, f):
         self._check(self.lib.dd_sim_zero_grad(self._h, f, self.stream))
 
+    def zero_pose_grads(self, f0, count=1):
+        self._check(self.lib.dd_sim_zero_pose_grads(self._h, f0, count, self.stream))
+
     def add_state_grad(self, f, gx=None, gv=None, gF=None, gC=None):
         self._check(self.lib.dd_sim_add_state_grad(self._h, f, _ptr(gx), _ptr(gv), _ptr(gF), _ptr(gC), self.stream))
-        self.sync()
+        if _is_host(gx, gv, gF, gC):
+            self.sync()
 
     def sync(self):
         self._check(self.lib.dd_sim_sync(self._h, self.stream))
@@ -117,39 +147,49 @@ class FusedSim:
     def launch_count(self):
         return int(self.lib.dd_sim_launch_count(self._h))
 
-    # ---- readback (numpy, original particle order)
-    def get_state(self, f, names=("x", "v", "F", "C")):
+    def segment_info(self, f=0):
+        """dict(segment, chunks, active_bricks, occupied_bricks, epoch, linked, n_segments, interval) of state f's segment."""
+        out = (ctypes.c_int * 8)()
+        self._check(self.lib.dd_sim_segment_info(self._h, int(f), out, self.stream))
+        keys = ("segment", "chunks", "active_bricks", "occupied_bricks", "epoch", "linked", "n_segments", "interval")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    # ---- readback (original particle order)
+    def get_state(self, f, names=("x", "v", "F", "C"), device=False):
         shp = dict(x=3, v=3, F=9, C=9)
-        out = {k: np.empty((self.E, self.N, shp[k]), np.float32) for k in names}
+        out = {k: self._empty((self.E, self.N, shp[k]), device) for k in names}
         self._check(self.lib.dd_sim_get_state(self._h, f, _ptr(out.get("x")), _ptr(out.get("v")), _ptr(out.get("F")), _ptr(out.get("C")), self.stream))
         return out
 
-    def get_state_grad(self, f, names=("x", "v", "F", "C")):
+    def get_state_grad(self, f, names=("x", "v", "F", "C"), device=False):
         shp = dict(x=3, v=3, F=9, C=9)
-        out = {k: np.empty((self.E, self.N, shp[k]), np.float32) for k in names}
+        out = {k: self._empty((self.E, self.N, shp[k]), device) for k in names}
         self._check(self.lib.dd_sim_get_state_grad(self._h, f, _ptr(out.get("x")), _ptr(out.get("v")), _ptr(out.get("F")), _ptr(out.get("C")), self.stream))
         return out
 
-    def get_pose_grads(self, f0, count):
-        gp = np.empty((count, self.E, self.nb, 3), np.float32)
-        gr = np.empty((count, self.E, self.nb, 4), np.float32)
+    def get_pose_grads(self, f0, count, device=False):
+        gp, gr = self._empty((count, self.E, self.nb, 3), device), self._empty((count, self.E, self.nb, 4), device)
         if self.nb:
             self._check(self.lib.dd_sim_get_pose_grads(self._h, f0, count, _ptr(gp), _ptr(gr), self.stream))
         return gp, gr
 
     def add_pose_grads(self, f, gpos=None, grot=None):
         self._check(self.lib.dd_sim_add_pose_grads(self._h, f, _ptr(gpos), _ptr(grot), self.stream))
-        self.sync()
+        if _is_host(gpos, grot):
+            self.sync()
 
-    def compute_dist(self, f):
-        d = np.empty((self.E, self.N, self.nb), np.float32)
+    def compute_dist(self, f, device=False):
+        d = self._empty((self.E, self.N, self.nb), device)
         if self.nb:
             self._check(self.lib.dd_sim_compute_dist(self._h, f, _ptr(d), self.stream))
         return d
 
     def compute_dist_grad(self, f, dist_grad):
-        self._check(self.lib.dd_sim_compute_dist_grad(self._h, f, _ptr(np.ascontiguousarray(dist_grad, np.float32)), self.stream))
-        self.sync()
+        if isinstance(dist_grad, np.ndarray):
+            dist_grad = np.ascontiguousarray(dist_grad, np.float32)
+        self._check(self.lib.dd_sim_compute_dist_grad(self._h, f, _ptr(dist_grad), self.stream))
+        if _is_host(dist_grad):
+            self.sync()
 
     def profile_substep(self, f, reps=5):
         """[(kernel label, ms)] for one forward + backward substep (needs a gradient seeded for state f+1)."""
@@ -160,14 +200,14 @@ class FusedSim:
         labels = names.value.decode().strip().split("\n")
         return [(labels[i], float(ms[i])) for i in range(n.value)]
 
-    def compute_grid_mass(self, f, ids=None, id=-1):
-        out = np.empty((self.E,) + self.grid_dim, np.float32)
-        ids_p = None if ids is None else np.ascontiguousarray(ids, np.int32).ctypes.data
-        self._check(self.lib.dd_sim_compute_grid_mass(self._h, f, ids_p, int(id), _ptr(out), self.stream))
+    def compute_grid_mass(self, f, ids=None, id=-1, device=False):
+        out = self._empty((self.E,) + self.grid_dim, device)
+        ids_a = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        self._check(self.lib.dd_sim_compute_grid_mass(self._h, f, None if ids_a is None else ids_a.ctypes.data, int(id), _ptr(out), self.stream))
         return out
 
     def compute_grid_mass_grad(self, f, grid_m_grad, ids=None, id=-1):
-        g = np.ascontiguousarray(grid_m_grad, np.float32)
+        g = np.ascontiguousarray(grid_m_grad, np.float32) if isinstance(grid_m_grad, np.ndarray) else grid_m_grad
         ids_a = None if ids is None else np.ascontiguousarray(ids, np.int32)
         self._check(self.lib.dd_sim_compute_grid_mass_grad(self._h, f, None if ids_a is None else ids_a.ctypes.data, int(id), _ptr(g), self.stream))
         self.sync()

@@ -9,7 +9,8 @@ S = c_void_p  # cudaStream_t
 class dd_sim_config(ctypes.Structure):
     _fields_ = [("n_envs", c_int), ("n_particles", c_int), ("n_bodies", c_int), ("grid_x", c_int), ("grid_y", c_int),
                 ("grid_z", c_int), ("max_steps", c_int), ("dx", c_float), ("dt", c_float), ("ground_friction", c_float),
-                ("ground_height", c_float), ("gravity", c_float * 3), ("svd_mode", c_int), ("use_graphs", c_int), ("sort_particles", c_int), ("tile_mode", c_int), ("grid_ckpt", c_int), ("chunk_max", c_int)]
+                ("ground_height", c_float), ("gravity", c_float * 3), ("svd_mode", c_int), ("use_graphs", c_int), ("sort_particles", c_int), ("tile_mode", c_int), ("grid_ckpt", c_int), ("chunk_max", c_int),
+                ("resort_interval", c_int)]
 
 
 ABI2 = {
@@ -22,8 +23,11 @@ ABI2 = {
     "dd_sim_set_state": (c_int, [P, c_int, P, P, P, P, S]),
     "dd_sim_get_state": (c_int, [P, c_int, P, P, P, P, S]),
     "dd_sim_set_poses": (c_int, [P, c_int, c_int, P, P, S]),
+    "dd_sim_get_poses": (c_int, [P, c_int, c_int, P, P, S]),
+    "dd_sim_roll": (c_int, [P, c_int, S]),
     "dd_sim_forward": (c_int, [P, c_int, c_int, S]),
     "dd_sim_zero_grad": (c_int, [P, c_int, S]),
+    "dd_sim_zero_pose_grads": (c_int, [P, c_int, c_int, S]),
     "dd_sim_add_state_grad": (c_int, [P, c_int, P, P, P, P, S]),
     "dd_sim_get_state_grad": (c_int, [P, c_int, P, P, P, P, S]),
     "dd_sim_backward": (c_int, [P, c_int, c_int, S]),
@@ -34,7 +38,9 @@ ABI2 = {
     "dd_sim_compute_grid_mass": (c_int, [P, c_int, P, c_int, P, S]),
     "dd_sim_compute_grid_mass_grad": (c_int, [P, c_int, P, c_int, P, S]),
     "dd_sim_sync": (c_int, [P, S]),
+    "dd_sim_segment_info": (c_int, [P, c_int, P, S]),
     "dd_sim_pose_table": (c_int, [P, P, P, P, P, P]),
+    "dd_sim_pose_grad_table": (c_int, [P, P, P]),
     "dd_hand_create": (c_int, [c_int, c_int, P, P, P, c_int, P, P, P, c_int, P, P, P, P, P, P, P]),
     "dd_hand_destroy": (None, [P]),
     "dd_hand_fk": (c_int, [P, P, c_int, c_int, P, P, P, P, P, c_int, S]),

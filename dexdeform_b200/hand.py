@@ -24,10 +24,11 @@ SUPPORTED_ENVS = ["folding", "rope", "bun", "dumpling", "wrap", "flip", "lift_bo
 
 
 def rigid_body_motion_hand(state, actions, T):
-    """hand.py:20-65: wrist pose (nh,4,4) ramped linearly by `actions` (nh,6) over T substeps -> (T, nh, 4, 4)."""
-    state = state[None, :].expand(T, -1, -1, -1).clone()
-    ramp = (torch.arange(T, device=actions.device)[:, None, None] + 1) / T
-    actions = actions[None, :].expand(T, -1, -1) * ramp
+    """hand.py:20-65: wrist pose (..., nh, 4, 4) ramped linearly by `actions` (..., nh, 6) over T substeps -> (T, ..., nh, 4, 4).
+    Leading batch axes (environments) are carried along."""
+    state = state[None].expand(T, *state.shape).clone()
+    ramp = ((torch.arange(T, device=actions.device) + 1) / T).reshape((T,) + (1,) * actions.dim())
+    actions = actions[None].expand(T, *actions.shape) * ramp
     trans = state[..., :3, 3] + actions[..., :3]
     q = matrix_to_quaternion(state[..., :3, :3])
     rot = actions[..., 3:]
@@ -60,10 +61,9 @@ class HandKinematics:
         self.action_map = g(actuator_of_joint(), torch.long)
 
     def forward(self, base_pose, q):
-        """hand.py:347-381.  base_pose (S, nh, 4, 4), q (S, nh, 24) -> pos (S, nb, 3), quat (S, nb, 4 wxyz)."""
-        S = base_pose.shape[0]
-        T = torch.zeros((S, self.n_hands, N_JOINTS, 4, 4), device=q.device, dtype=q.dtype)
-        T[..., :3, :3] = axis_angle_to_matrix(self.joint_axis[None] * q[..., None])
+        """hand.py:347-381.  base_pose (S, [E,] nh, 4, 4), q (S, [E,] nh, 24) -> pos (S, [E,] nb, 3), quat (S, [E,] nb, 4 wxyz)."""
+        T = torch.zeros(q.shape + (4, 4), device=q.device, dtype=q.dtype)
+        T[..., :3, :3] = axis_angle_to_matrix(self.joint_axis * q[..., None])
         T[..., :3, 3] = self.joint_pos
         T[..., 3, 3] = 1
         joint_pose = [None] * N_JOINTS
@@ -76,8 +76,8 @@ class HandKinematics:
             else:
                 base = base @ T[..., idx, :, :]
                 joint_pose[idx] = base
-        jp = torch.stack([joint_pose[j] for j in self.geom_index.tolist()], 2)  # (S, nh, n_geoms, 4, 4)
-        geom = (jp @ self.geom_local).reshape(S, -1, 4, 4)
+        jp = torch.stack([joint_pose[j] for j in self.geom_index.tolist()], -3)  # (S, [E,] nh, n_geoms, 4, 4)
+        geom = (jp @ self.geom_local).flatten(-4, -3)                            # hands side by side: primitive = hand * n_geoms + geom
         return geom[..., :3, 3], matrix_to_quaternion(geom[..., :3, :3])
 
 
@@ -192,20 +192,22 @@ class HandSimulator(MPMSimulator):
         super().set_state(index, tuple(state[:4]) + tuple(pose))
 
     def JointVel_Fk(self, f, actions, pos_rot=None):
-        """hand.py:383-428: action (nh, 26) -> poses of the S substeps + the end-of-step kinematic state."""
+        """hand.py:383-428: action ([E,] nh, 26) -> poses of the S substeps + the end-of-step kinematic state."""
         curr_base, curr_q = (self.base_pose[f], self.joint_rot[f]) if pos_rot is None else pos_rot
         if not isinstance(actions, torch.Tensor):
             actions = torch.tensor(np.asarray(actions), device=self.device, dtype=torch.float32)
         actions = actions.to(self.device)
         S, na = self.substeps, N_ACTUATORS
-        if actions.shape[1] == na + 6:
-            next_base = rigid_body_motion_hand(curr_base, actions[:, -6:] * self.torch_action_scale[None, -6:], S)
+        assert actions.shape[-2] == self.n_hands
+        if actions.dim() == 3 and curr_base.dim() == 3:  # one kinematic state shared by all environments so far
+            curr_base, curr_q = curr_base[None].expand(actions.shape[0], -1, -1, -1), curr_q[None].expand(actions.shape[0], -1, -1)
+        if actions.shape[-1] == na + 6:
+            next_base = rigid_body_motion_hand(curr_base, actions[..., -6:] * self.torch_action_scale[-6:], S)
         else:
-            next_base = curr_base[None, ...].expand(S, -1, -1, -1)
-        assert actions.shape[0] == self.n_hands
-        a = (actions[..., :na].clamp(-1.0, 1.0) * self.torch_action_scale[None, :na])[:, self.action_map]
-        next_q = curr_q[None, :] + a[None, :] * (torch.arange(S, device=self.device)[:, None, None] + 1)
-        next_q = next_q.clamp(self.q_lower, self.q_upper)
+            next_base = curr_base[None].expand(S, *curr_base.shape)
+        a = (actions[..., :na].clamp(-1.0, 1.0) * self.torch_action_scale[:na])[..., self.action_map]
+        ramp = (torch.arange(S, device=self.device) + 1).reshape((S,) + (1,) * a.dim())
+        next_q = (curr_q[None] + a[None] * ramp).clamp(self.q_lower, self.q_upper)
         geom_pos, geom_rot = self.hand_forward_kinematics(next_base, next_q)
         nb_, nq_ = next_base[-1], next_q[-1]
         if f + S < len(self.base_pose):
@@ -213,28 +215,23 @@ class HandSimulator(MPMSimulator):
         return geom_pos, geom_rot, (nb_, nq_)
 
     def step(self, action, q_state=None):
+        """hand.py:430-433 + mpm/simulator.py:626-634.  Kinematics, the S substeps and the rolling window (state S -> state 0,
+        re-sorted) all stay on the device."""
         S = self.substeps
         if self.device_fk is not None and self.n_envs == 1:
-            # forward-only env step: kinematics, pose upload and the S substeps all stay on the device
             if not isinstance(action, torch.Tensor):
                 action = torch.tensor(np.asarray(action), dtype=torch.float32)
             base, q = (self.base_pose[0], self.joint_rot[0]) if q_state is None else q_state
             nb_, nq_ = self.device_fk.run(self.engine, 0, S, base[None].to(self.device), q[None].to(self.device), action[None].to(self.device),
                                           has_base_action=action.shape[1] == N_ACTUATORS + 6)
-            self.base_pose[S], self.joint_rot[S] = nb_[0], nq_[0]
-            p, r = read_poses(self.engine, S, 1)
-            self._pos[S], self._rot[S] = p[0].cpu().numpy(), r[0].cpu().numpy()
+            nb_, nq_ = nb_[0], nq_[0]
         else:
-            pos, rot, _ = self.JointVel_Fk(self.cur if self.cur % self.substeps == 0 else 0, action, q_state)
+            pos, rot, (nb_, nq_) = self.JointVel_Fk(self.cur if self.cur % self.substeps == 0 else 0, action, q_state)
             self.set_poses(1, pos, rot)
         self.engine.forward(0, S)
-        st = self.engine.get_state(S)
-        self.engine.set_state(0, st["x"], st["v"], st["F"], st["C"])
-        self._pos[0], self._rot[0] = self._pos[S], self._rot[S]
-        self.engine.set_poses(0, self._pos[0:1], self._rot[0:1])
-        self.base_pose[0], self.joint_rot[0] = self.base_pose[S].detach(), self.joint_rot[S].detach()
+        self.engine.roll(S)
+        self.base_pose[0], self.joint_rot[0] = nb_.detach(), nq_.detach()
         self.cur = 0
-        self.sync()
 
 
 def _parse_tuple(v):

@@ -41,7 +41,8 @@ def rigid_body_motion(states, actions):
 
 class _Field:
     """One member of a state (``states[f].x`` ...): upload / download / cuda_add / zero in the reference's vocabulary
-    (mpm/types.py:294-400), forwarded to the engine."""
+    (mpm/types.py:294-400), forwarded to the engine.  ``device`` other than "numpy" returns torch CUDA tensors without a
+    host round trip."""
 
     def __init__(self, sim, f, name, grad):
         self.sim, self.f, self.name, self.grad = sim, f, name, grad
@@ -51,36 +52,38 @@ class _Field:
 
     def download(self, n=None, device="numpy", stream=None):
         s, eng = self.sim, self.sim.engine
+        dev = device != "numpy" and str(device).startswith("cuda")
         if self.name in ("body_pos", "body_rot"):
-            if self.grad:
-                gp, gr = eng.get_pose_grads(self.f, 1)
-                out = (gp if self.name == "body_pos" else gr)[0]
-            else:
-                out = (s._pos if self.name == "body_pos" else s._rot)[self.f]
+            gp, gr = (eng.get_pose_grads if self.grad else eng.get_poses)(self.f, 1, device=dev)
+            out = (gp if self.name == "body_pos" else gr)[0]
         else:
-            out = (eng.get_state_grad if self.grad else eng.get_state)(self.f, (self.name,))[self.name]
+            out = (eng.get_state_grad if self.grad else eng.get_state)(self.f, (self.name,), device=dev)[self.name]
         out = self._squeeze(out)
         if n is not None and self.name not in ("body_pos", "body_rot"):
             out = out[..., :n, :]
-        if device != "numpy":
+        if device != "numpy" and not dev:
             import torch
             return torch.tensor(out, device=device)
         return out
 
     def upload(self, arr, strict=False):
         s = self.sim
-        arr = np.ascontiguousarray(arr, np.float32)
-        if self.name in ("body_pos", "body_rot") and not self.grad:
-            buf = s._pos if self.name == "body_pos" else s._rot
-            buf[self.f] = arr.reshape(buf[self.f].shape)
-            s.engine.set_poses(self.f, s._pos[self.f:self.f + 1], s._rot[self.f:self.f + 1])
+        if self.grad:
+            raise NotImplementedError(f"upload of states[{self.f}].{self.name}_grad: gradients are accumulated, use cuda_add (after State.clear_grad)")
+        if self.name in ("body_pos", "body_rot"):
+            pos, rot = s.engine.get_poses(self.f, 1)
+            (pos if self.name == "body_pos" else rot)[0] = np.float32(arr).reshape((pos if self.name == "body_pos" else rot)[0].shape)
+            s.engine.set_poses(self.f, pos, rot)
             return
-        raise NotImplementedError(f"upload of states[{self.f}].{self.name}{'_grad' if self.grad else ''}: use set_state / cuda_add")
+        # one particle field of state f: read the others back, replace this one, store (re-sorts, like any set_state)
+        st = s.engine.get_state(self.f)
+        st[self.name] = np.ascontiguousarray(np.broadcast_to(np.float32(arr).reshape((-1, s.n_particles, st[self.name].shape[-1])), st[self.name].shape))
+        s.engine.set_state(self.f, st["x"], st["v"], st["F"], st["C"])
 
     def cuda_add(self, values, stream=None):
         s, eng = self.sim, self.sim.engine
-        v = np.ascontiguousarray(values, np.float32)
         assert self.grad, "cuda_add is only meaningful on gradient buffers"
+        v = values if hasattr(values, "is_cuda") and values.is_cuda else np.ascontiguousarray(values, np.float32)
         if self.name in ("body_pos", "body_rot"):
             v = v.reshape(s.n_envs, s.n_bodies, -1)
             eng.add_pose_grads(self.f, gpos=v if self.name == "body_pos" else None, grot=v if self.name == "body_rot" else None)
@@ -89,8 +92,14 @@ class _Field:
             eng.add_state_grad(self.f, **{"g" + self.name: v})
 
     def zero(self, stream=None):
-        if self.grad:
-            self.sim._zero_grad_pending.add(self.f)
+        """Gradient members only.  Particle gradients of a state live in one ping-pong slot and are cleared together
+        (the reference clears them together too, mpm/simulator.py:136-145)."""
+        if not self.grad:
+            raise NotImplementedError("zero() of a state member: use set_state")
+        if self.name in ("body_pos", "body_rot"):
+            self.sim.engine.zero_pose_grads(self.f, 1)
+        else:
+            self.sim.engine.zero_grad(self.f)
 
     zero_async = zero
 
@@ -128,13 +137,16 @@ class MPMSimulator:
         self.n_grid = self.grid_dim[0]
         self._ground_friction = float(ground_friction)
         self.gravity = np.float32(np.array(gravity) * 30)  # mpm/simulator.py:385
+        # particles are re-sorted on the device at every env-step boundary of a longer rollout (GradModel chains env steps
+        # without set_state, mpm/torch_wrapper.py:110-118)
+        engine_kwargs.setdefault("resort_interval", self.substeps if max_steps > self.substeps else 0)
         self.engine = FusedSim(self.n_envs, n_particles, self.n_bodies, self.grid_dim, self.dx, self.dt, max_steps, self._ground_friction,
                                self.get_ground_height(), self.gravity, **engine_kwargs)
         self.states = [State(self, f) for f in range(max_steps + 1)]
-        self._pos = np.zeros((max_steps + 1, self.n_envs, max(self.n_bodies, 1), 3), np.float32)
-        self._rot = np.zeros((max_steps + 1, self.n_envs, max(self.n_bodies, 1), 4), np.float32)
-        self._rot[..., 0] = 1.0
-        self._zero_grad_pending = set()
+        if self.n_bodies:  # identity quaternions until poses are set
+            rot = np.zeros((max_steps + 1, self.n_envs, self.n_bodies, 4), np.float32)
+            rot[..., 0] = 1.0
+            self.engine.set_poses(0, np.zeros((max_steps + 1, self.n_envs, self.n_bodies, 3), np.float32), rot)
         mu = E / (2 * (1 + nu))
         lam = E * nu / ((1 + nu) * (1 - 2 * nu))
         self.init_particles(np.zeros(n_particles) + vol, np.zeros(n_particles) + mass, np.zeros((n_particles, 3)) + np.array([mu, lam, yield_stress]))
@@ -163,12 +175,17 @@ class MPMSimulator:
         """mpm/simulator.py:323-354 for an integer state index."""
         ids = None if id == -1 else np.ascontiguousarray(np.broadcast_to(self.object_id, (self.n_envs, self.n_particles)), np.int32)
         if backward_grad is not None:
-            g = backward_grad.detach().cpu().numpy() if hasattr(backward_grad, "detach") else np.asarray(backward_grad)
-            self.engine.compute_grid_mass_grad(f, np.float32(g).reshape((self.n_envs,) + self.grid_dim), ids, id)
+            g = backward_grad
+            if hasattr(g, "is_cuda") and g.is_cuda:
+                g = g.detach().float().reshape((self.n_envs,) + self.grid_dim).contiguous()
+            else:
+                g = np.float32(g.detach().cpu().numpy() if hasattr(g, "detach") else g).reshape((self.n_envs,) + self.grid_dim)
+            self.engine.compute_grid_mass_grad(f, g, ids, id)
             return None
-        out = self.engine.compute_grid_mass(f, ids, id)
+        dev = str(device).startswith("cuda")
+        out = self.engine.compute_grid_mass(f, ids, id, device=dev)
         out = out[0] if self.n_envs == 1 else out
-        if device == "numpy":
+        if device == "numpy" or dev:
             return out
         import torch
         return torch.tensor(out, device=device)
@@ -181,9 +198,18 @@ class MPMSimulator:
         self.engine.set_bodies(self._tfsr, self._args)
         self.action_scales = action_scales
         if pos is not None and rot is not None:
-            self._pos[0] = np.float32(pos).reshape(1, self.n_bodies, 3)
-            self._rot[0] = np.float32(rot).reshape(1, self.n_bodies, 4)
-            self.engine.set_poses(0, self._pos[0:1], self._rot[0:1])
+            self._upload_pose(0, np.float32(pos), np.float32(rot))
+
+    def _upload_pose(self, f, pos, rot):
+        """pos (nb, 3) / rot (nb, 4) shared by all environments, or with a leading environment axis."""
+        E, nb = self.n_envs, self.n_bodies
+        full = lambda a, d: np.ascontiguousarray(np.broadcast_to(np.float32(a).reshape((-1, nb, d)), (E, nb, d)))[None]
+        self.engine.set_poses(f, full(pos, 3), full(rot, 4))
+
+    def _pose7(self, f):
+        """(E, nb, 7) numpy: position | quaternion of every primitive at state f."""
+        pos, rot = self.engine.get_poses(f, 1)
+        return np.concatenate((pos[0], rot[0]), -1)
 
     def set_softness(self, softness):
         self._tfsr[:, 2] = softness
@@ -200,7 +226,7 @@ class MPMSimulator:
             x, v, F, C = st["x"][0], st["v"][0], st["F"][0].reshape(n, 3, 3), st["C"][0].reshape(n, 3, 3)
         else:
             x, v, F, C = st["x"], st["v"], st["F"].reshape(E, n, 3, 3), st["C"].reshape(E, n, 3, 3)
-        tools = [np.r_[a, b] for a, b in zip(self._pos[index][0], self._rot[index][0])] if self.n_bodies else []
+        tools = list(self._pose7(index)[0]) if self.n_bodies else []
         return (x, v, F, C) + tuple(tools)
 
     def set_state(self, index, state):
@@ -210,9 +236,7 @@ class MPMSimulator:
         self.engine.set_state(index, x, v, F, C)
         if self.n_bodies and len(state) > 4:
             pose = np.float32(state[4:4 + self.n_bodies])
-            self._pos[index] = pose[None, :, :3]
-            self._rot[index] = pose[None, :, 3:7]
-            self.engine.set_poses(index, self._pos[index:index + 1], self._rot[index:index + 1])
+            self._upload_pose(index, pose[:, :3], pose[:, 3:7])
         self.cur = index
 
     def get_x(self, index, device="numpy"):
@@ -222,7 +246,7 @@ class MPMSimulator:
         return self.states[index].v.download(self.n_particles, device=device)
 
     def get_tool_state(self, index=0, device=None):
-        state = [np.r_[a, b] for a, b in zip(self._pos[index][0], self._rot[index][0])]
+        state = list(self._pose7(index)[0])
         if device == "numpy" or device is None:
             return state
         import torch
@@ -231,45 +255,52 @@ class MPMSimulator:
     def set_tool_state(self, index, pose):
         pose = np.float32(pose)
         assert pose.shape == (self.n_bodies, 7), f"{pose.shape}, {self.n_bodies}"
-        self._pos[index] = pose[None, :, :3]
-        self._rot[index] = pose[None, :, 3:7]
-        self.engine.set_poses(index, self._pos[index:index + 1], self._rot[index:index + 1])
+        self._upload_pose(index, pose[:, :3], pose[:, 3:7])
 
     def get_dists(self, f, grad=None, device="cuda:0"):
         """mpm/simulator.py:294-321: (N, n_bodies) signed distances; with ``grad`` given, their adjoint is accumulated into
-        states[f].x_grad and the body pose gradients instead."""
+        states[f].x_grad and the body pose gradients instead.  CUDA tensors in and out stay on the device."""
         if grad is None:
-            d = self.engine.compute_dist(f)
+            dev = str(device).startswith("cuda")
+            d = self.engine.compute_dist(f, device=dev)
             d = d[0] if self.n_envs == 1 else d
-            if device == "numpy":
+            if device == "numpy" or dev:
                 return d
             import torch
             return torch.tensor(d, device=device)
-        g = grad.detach().cpu().numpy() if hasattr(grad, "detach") else np.asarray(grad)
-        self.engine.compute_dist_grad(f, np.float32(g).reshape(self.n_envs, self.n_particles, self.n_bodies))
+        if hasattr(grad, "is_cuda") and grad.is_cuda:
+            g = grad.detach().float().reshape(self.n_envs, self.n_particles, self.n_bodies).contiguous()
+        else:
+            g = np.float32(grad.detach().cpu().numpy() if hasattr(grad, "detach") else grad).reshape(self.n_envs, self.n_particles, self.n_bodies)
+        self.engine.compute_dist_grad(f, g)
 
     # ---- stepping
     def set_pose(self, state, pos, rot, stream=None):
         """mpm/simulator.py:553-559.  ``state`` is a State (or its index); pos (nb,3) / rot (nb,4) numpy or torch."""
         f = state.f if isinstance(state, State) else int(state)
+        if hasattr(pos, "is_cuda") and pos.is_cuda:
+            E, nb = self.n_envs, self.n_bodies
+            p = pos.detach().float().reshape(-1, nb, 3).expand(E, nb, 3).contiguous()[None]
+            r = rot.detach().float().reshape(-1, nb, 4).expand(E, nb, 4).contiguous()[None]
+            self.engine.set_poses(f, p, r)
+            return
         if hasattr(pos, "detach"):
             pos, rot = pos.detach().cpu().numpy(), rot.detach().cpu().numpy()
-        self._pos[f] = np.float32(pos).reshape(self._pos[f].shape)
-        self._rot[f] = np.float32(rot).reshape(self._rot[f].shape)
-        self.engine.set_poses(f, self._pos[f:f + 1], self._rot[f:f + 1])
+        self._upload_pose(f, pos, rot)
 
     def set_poses(self, f0, pos, rot):
-        """All poses of an env step at once: pos (S, nb, 3) / rot (S, nb, 4) for states f0 .. f0+S-1 (device tensors stay on device)."""
+        """All poses of an env step at once: pos (S, [E,] nb, 3) / rot (S, [E,] nb, 4) for states f0 .. f0+S-1 (device tensors
+        stay on the device)."""
+        E, nb = self.n_envs, self.n_bodies
         if hasattr(pos, "detach"):
-            p = pos.detach().reshape(pos.shape[0], self.n_envs, self.n_bodies, 3).contiguous()
-            r = rot.detach().reshape(rot.shape[0], self.n_envs, self.n_bodies, 4).contiguous()
-            self.engine.set_poses(f0, p, r)
-            self._pos[f0:f0 + len(p)] = p.cpu().numpy()
-            self._rot[f0:f0 + len(r)] = r.cpu().numpy()
+            S = pos.shape[0]
+            p = pos.detach().float().reshape(S, -1, nb, 3).expand(S, E, nb, 3).contiguous()
+            r = rot.detach().float().reshape(S, -1, nb, 4).expand(S, E, nb, 4).contiguous()
         else:
-            self._pos[f0:f0 + len(pos)] = np.float32(pos).reshape((-1,) + self._pos.shape[1:])
-            self._rot[f0:f0 + len(rot)] = np.float32(rot).reshape((-1,) + self._rot.shape[1:])
-            self.engine.set_poses(f0, self._pos[f0:f0 + len(pos)], self._rot[f0:f0 + len(rot)])
+            S = len(pos)
+            p = np.ascontiguousarray(np.broadcast_to(np.float32(pos).reshape(S, -1, nb, 3), (S, E, nb, 3)))
+            r = np.ascontiguousarray(np.broadcast_to(np.float32(rot).reshape(S, -1, nb, 4), (S, E, nb, 4)))
+        self.engine.set_poses(f0, p, r)
 
     def substep(self, f, clear_grad=False):
         self.engine.forward(f, 1)
@@ -288,10 +319,17 @@ class MPMSimulator:
 
     def download_pos_rot(self, cur, device):
         import torch
-        return (torch.tensor(self._pos[cur][0], device=device, dtype=torch.float32), torch.tensor(self._rot[cur][0], device=device, dtype=torch.float32))
+        dev = str(device).startswith("cuda")
+        pos, rot = self.engine.get_poses(cur, 1, device=dev)
+        pos, rot = pos[0], rot[0]
+        if self.n_envs == 1:
+            pos, rot = pos[0], rot[0]
+        if dev:
+            return pos, rot
+        return torch.tensor(pos, device=device, dtype=torch.float32), torch.tensor(rot, device=device, dtype=torch.float32)
 
     def compute_forward_kinematics(self, f, action, pos_rot=None):
-        """mpm/simulator.py:597-624: free tools driven by (translation, axis-angle) velocity actions."""
+        """mpm/simulator.py:597-624: free tools driven by (translation, axis-angle) velocity actions.  action ([E,] nb, 6)."""
         import torch
         device = "cpu" if not isinstance(action, torch.Tensor) else action.device
         pos, rot = self.download_pos_rot(f, device) if pos_rot is None else pos_rot
@@ -299,19 +337,24 @@ class MPMSimulator:
             action = torch.tensor(np.array(action, np.float32), device=device)
         if self.torch_scale is None:
             self.torch_scale = torch.tensor(np.array(self.action_scales), device=device, dtype=torch.float32)
-        action = action.reshape(-1, 6).clamp(-1.0, 1.0) * self.torch_scale.to(device)
-        S = self.substeps
-        pos, rot = rigid_body_motion((pos, rot), action[None, :].expand(S, -1, -1) * (torch.arange(S, device=device)[:, None, None] + 1) / S)
+        nb, S = self.n_bodies, self.substeps
+        batched = action.dim() == 3 or pos.dim() == 3
+        a = action.reshape(-1, nb, 6).clamp(-1.0, 1.0) * self.torch_scale.to(device)
+        B = max(a.shape[0], pos.reshape(-1, nb, 3).shape[0])
+        a = a.expand(B, nb, 6).reshape(B * nb, 6)
+        pos, rot = pos.reshape(-1, nb, 3).expand(B, nb, 3).reshape(B * nb, 3), rot.reshape(-1, nb, 4).expand(B, nb, 4).reshape(B * nb, 4)
+        ramp = (torch.arange(S, device=device)[:, None, None] + 1) / S
+        pos, rot = rigid_body_motion((pos, rot), a[None].expand(S, -1, -1) * ramp)
+        if batched:
+            pos, rot = pos.reshape(S, B, nb, 3), rot.reshape(S, B, nb, 4)
         return pos, rot, (pos[-1], rot[-1])
 
     def step(self, action, pos_rot=None):
-        """mpm/simulator.py:626-634: one env step from states[0]; the result becomes the new states[0]."""
+        """mpm/simulator.py:626-634: one env step from states[0]; the result becomes the new states[0].  The rolling window
+        (state and poses of states[S] -> states[0], re-sorted) never leaves the device."""
         pos, rot, _ = self.compute_forward_kinematics(self.cur, action, pos_rot=pos_rot)
         S = self.substeps
         self.set_poses(1, pos, rot)
         self.engine.forward(0, S)
-        st = self.engine.get_state(S)
-        self.engine.set_state(0, st["x"], st["v"], st["F"], st["C"])  # rolling window + re-sort at the env-step boundary
-        self._pos[0], self._rot[0] = self._pos[S], self._rot[S]
-        self.engine.set_poses(0, self._pos[0:1], self._rot[0:1])
-        self.sync()
+        self.engine.roll(S)
+        self.cur = 0

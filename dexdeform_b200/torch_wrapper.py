@@ -6,11 +6,16 @@ Contract kept: ``get_obs(s, device) -> (cat[x, v, dist] (N, 6+nb), tool (nb, 7)[
 ``(None, pos_grad (S,nb,3), rot_grad (S,nb,4), zeros_like(past_obs)...)``; state-to-state gradients never pass through
 torch -- they live in the simulator and observation gradients are *added* to them at step boundaries.
 
-What changed: the S poses of a step go to the device in one call and the S substeps (and their reverse) are one
-CUDA-graph launch each; the reference performs a device->host->device pose round trip, ~10 library calls and one
-synchronous gradient download per substep (mpm/torch_wrapper.py:115-134).
+What changed:
+* the S poses of a step go to the device in one call and the S substeps (and their reverse) are one CUDA-graph launch each;
+  the reference performs a device->host->device pose round trip, ~10 library calls and one synchronous gradient download
+  per substep (mpm/torch_wrapper.py:115-134);
+* nothing crosses PCIe: observations, observation gradients and pose gradients are torch CUDA tensors handed to / filled by
+  the engine through raw device pointers (the reference downloads to numpy and re-uploads, mpm/torch_wrapper.py:54-105);
+* particles are re-sorted on the device at every env-step boundary, so a rollout may be as long as ``max_steps`` allows;
+* ``n_envs > 1``: every tensor gains a leading environment axis -- obs ``(E, N, 6+nb)``, tool ``(E, nb, 7)``, poses
+  ``(S, E, nb, 3|4)``, actions ``(E, n_hands, 26)``.
 """
-import numpy as np
 import torch
 from torch.autograd import Function
 
@@ -35,14 +40,17 @@ class GradModel:
         return self.sim.substeps
 
     def zero_grad(self, return_grid=None, return_svd=None, **kwargs):
+        """mpm/torch_wrapper.py:24-30: a new optimisation iteration starts -- states[0]'s gradients are cleared (the forward
+        pass clears those of every later state, mpm/simulator.py:570-571)."""
         self._frontier = None
+        self.sim.engine.zero_pose_grads(0, 1)
         if return_grid is not None:
             self.return_grid = tuple(return_grid)
         if return_svd is not None:
             self.return_svd = return_svd or self.return_svd
 
     def wrap_obs(self, obs):
-        output = {"pos": obs[0][:, :3], "vel": obs[0][:, 3:6], "tool": obs[1], "dist": obs[0][:, 6:]}
+        output = {"pos": obs[0][..., :3], "vel": obs[0][..., 3:6], "tool": obs[1], "dist": obs[0][..., 6:]}
         obs = obs[2:]
         if len(self.return_grid) > 0:
             ng = len(self.return_grid)
@@ -51,16 +59,23 @@ class GradModel:
         assert len(obs) == 0
         return output
 
+    def _squeeze(self, t):
+        return t[0] if self.sim.n_envs == 1 else t
+
     def get_obs(self, s, device):
-        f = s * self.sim.substeps
-        st = self.sim.engine.get_state(f, ("x", "v"))
-        x = torch.tensor(st["x"][0], device=device)
-        v = torch.tensor(st["v"][0], device=device)
-        c = torch.tensor(np.concatenate((self.sim._pos[f][0], self.sim._rot[f][0]), 1), device=device)
-        dists = self.sim.get_dists(f, device=device) if self.sim.n_bodies else torch.zeros((self.sim.n_particles, 0), device=device)
-        outputs = [torch.cat((x, v, dists), 1), c]
+        sim, eng = self.sim, self.sim.engine
+        f = s * sim.substeps
+        st = eng.get_state(f, ("x", "v"), device=True)
+        parts = [st["x"], st["v"]]
+        if sim.n_bodies:
+            parts.append(eng.compute_dist(f, device=True))
+            pos, rot = eng.get_poses(f, 1, device=True)
+            tool = torch.cat((pos[0], rot[0]), -1)
+        else:
+            tool = torch.zeros((sim.n_envs, 0, 7), device="cuda")
+        outputs = [self._squeeze(torch.cat(parts, -1)).to(device), self._squeeze(tool).to(device)]
         for i in self.return_grid:
-            outputs.append(self.sim.compute_grid_mass(f, i, device=device))
+            outputs.append(sim.compute_grid_mass(f, i, device=device))
         return tuple(outputs)
 
     def _ensure_frontier(self, f):
@@ -70,20 +85,20 @@ class GradModel:
             self._frontier = f
 
     def set_obs_grad(self, s, particle_grad, tool_grad, *args):
-        f = s * self.sim.substeps
+        sim, eng = self.sim, self.sim.engine
+        f = s * sim.substeps
         self._ensure_frontier(f)
         for idx, i in enumerate(self.return_grid):
-            if args[idx] is not None:
-                self.sim.compute_grid_mass(f, i, backward_grad=args[idx])
-        nb = self.sim.n_bodies
+            if idx < len(args) and args[idx] is not None:
+                sim.compute_grid_mass(f, i, backward_grad=args[idx])
+        E, n, nb = sim.n_envs, sim.n_particles, sim.n_bodies
+        pg = particle_grad.detach().to("cuda", torch.float32).reshape(E, n, 6 + nb)
         if nb:
-            self.sim.get_dists(f, particle_grad[:, 6:])
-        pg = particle_grad[:, :6].detach().cpu().numpy().astype(np.float32)
-        E, n = self.sim.n_envs, self.sim.n_particles
-        self.sim.engine.add_state_grad(f, gx=np.ascontiguousarray(pg[:, :3]).reshape(E, n, 3), gv=np.ascontiguousarray(pg[:, 3:]).reshape(E, n, 3))
+            eng.compute_dist_grad(f, pg[..., 6:].contiguous())
+        eng.add_state_grad(f, gx=pg[..., :3].contiguous(), gv=pg[..., 3:6].contiguous())
         if nb:
-            c = tool_grad.reshape(nb, 7).detach().cpu().numpy().astype(np.float32)
-            self.sim.engine.add_pose_grads(f, gpos=np.ascontiguousarray(c[:, :3]).reshape(E, nb, 3), grot=np.ascontiguousarray(c[:, 3:]).reshape(E, nb, 4))
+            c = tool_grad.detach().to("cuda", torch.float32).reshape(E, nb, 7)
+            eng.add_pose_grads(f, gpos=c[..., :3].contiguous(), grot=c[..., 3:].contiguous())
 
     @property
     def diff_forward(self):
@@ -94,11 +109,11 @@ class GradModel:
                 @staticmethod
                 def forward(ctx, s, pos, rot, *past_obs):
                     ctx.s = s
+                    ctx.shapes = (pos.shape, rot.shape)
                     ctx.zero = [torch.zeros_like(i) for i in past_obs]
                     S, f = model.substeps, s * model.substeps
                     model.sim.set_poses(f + 1, pos, rot)   # poses of states f+1 .. f+S in one call
-                    model.sim.forward_range(f, S)
-                    model.sim.sync()
+                    model.sim.forward_range(f, S)          # (re-sorts at f when it continues a rollout)
                     return model.get_obs(s + 1, pos.device)
 
                 @staticmethod
@@ -108,10 +123,8 @@ class GradModel:
                     model.set_obs_grad(s + 1, *obs_grad)
                     model.sim.backward_range(f, S)
                     model._frontier = f
-                    gp, gr = model.sim.engine.get_pose_grads(f + 1, S)
-                    pos_grad = torch.tensor(gp[:, 0], device=model.device)
-                    rot_grad = torch.tensor(gr[:, 0], device=model.device)
-                    return (None, pos_grad, rot_grad) + tuple(ctx.zero)
+                    gp, gr = model.sim.engine.get_pose_grads(f + 1, S, device=True)  # (S, E, nb, 3|4), on the device
+                    return (None, gp.reshape(ctx.shapes[0]), gr.reshape(ctx.shapes[1])) + tuple(ctx.zero)
 
             self._forward_func = forward
         return self._forward_func.apply
@@ -125,6 +138,7 @@ class GradModel:
                 @staticmethod
                 def forward(ctx, s, pos, rot):
                     ctx.s = s
+                    ctx.shapes = (pos.shape, rot.shape)
                     model.sim.set_pose(s * model.substeps, pos, rot)
                     return model.get_obs(s, pos.device)
 
@@ -133,8 +147,8 @@ class GradModel:
                     s = ctx.s
                     f = s * model.substeps
                     model.set_obs_grad(s, *obs_grad)
-                    gp, gr = model.sim.engine.get_pose_grads(f, 1)
-                    return (None, torch.tensor(gp[0, 0], device=model.device), torch.tensor(gr[0, 0], device=model.device))
+                    gp, gr = model.sim.engine.get_pose_grads(f, 1, device=True)
+                    return (None, gp.reshape(ctx.shapes[0]), gr.reshape(ctx.shapes[1]))
 
             self._set_pose_func = SetPose.apply
         return self._set_pose_func

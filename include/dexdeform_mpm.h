@@ -138,6 +138,9 @@ typedef struct {
   int tile_mode;       /* 1: warp-private shared-memory tiles for the scatters + grid kernels on active bricks only; 0: global reductions on the dense grid */
   int grid_ckpt;       /* 1: keep every substep's grid in HBM when it fits, so the adjoint does not replay scatter + grid update */
   int chunk_max;       /* particles per warp-chunk in tile mode (0 = choose from the problem size) */
+  int resort_interval; /* tile mode: re-sort the particles on the device every this many substeps inside dd_sim_forward (0 = only in
+                          dd_sim_set_state).  States at multiples of the interval are stored in both orders; the adjoint permutes
+                          the gradient back.  mpm/simulator.py has no equivalent (its kernels are order independent). */
 } dd_sim_config;
 
 const char *dd_last_error(void);
@@ -149,8 +152,12 @@ int dd_sim_set_bodies(dd_sim *sim, const float *tfsr, const float *args);   /* (
 int dd_sim_set_state(dd_sim *sim, int f, const float *x, const float *v, const float *F, const float *C, cudaStream_t stream);
 int dd_sim_get_state(dd_sim *sim, int f, float *x, float *v, float *F, float *C, cudaStream_t stream);   /* any may be NULL; synchronises */
 int dd_sim_set_poses(dd_sim *sim, int f0, int count, const float *pos, const float *rot, cudaStream_t stream);
+int dd_sim_get_poses(dd_sim *sim, int f0, int count, float *pos, float *rot, cudaStream_t stream);
+/* rolling window of MPMSimulator.step (mpm/simulator.py:626-634): state f_src (particles + poses) becomes state 0, re-sorted on the device */
+int dd_sim_roll(dd_sim *sim, int f_src, cudaStream_t stream);
 int dd_sim_forward(dd_sim *sim, int f0, int n_substeps, cudaStream_t stream);    /* slots f0 -> f0+n */
 int dd_sim_zero_grad(dd_sim *sim, int f, cudaStream_t stream);                   /* start a backward pass at state f */
+int dd_sim_zero_pose_grads(dd_sim *sim, int f0, int count, cudaStream_t stream);  /* pose gradients of states f0 .. f0+count-1 only */
 int dd_sim_add_state_grad(dd_sim *sim, int f, const float *gx, const float *gv, const float *gF, const float *gC, cudaStream_t stream);
 int dd_sim_get_state_grad(dd_sim *sim, int f, float *gx, float *gv, float *gF, float *gC, cudaStream_t stream);
 int dd_sim_backward(dd_sim *sim, int f0, int n_substeps, cudaStream_t stream);   /* substeps f0+n-1 ... f0 */
@@ -162,11 +169,14 @@ int dd_sim_compute_dist_grad(dd_sim *sim, int f, const float *dist_grad, cudaStr
 int dd_sim_compute_grid_mass(dd_sim *sim, int f, const int *ids, int id, float *out, cudaStream_t stream);
 int dd_sim_compute_grid_mass_grad(dd_sim *sim, int f, const int *ids, int id, const float *grid_m_grad, cudaStream_t stream);
 int dd_sim_sync(dd_sim *sim, cudaStream_t stream);
+/* diagnostics (synchronises): out[8] = {segment of state f, chunks, active bricks, occupied bricks, epoch, linked, n segments, interval} */
+int dd_sim_segment_info(dd_sim *sim, int f, int *out, cudaStream_t stream);
 /* measurement aid: device time of every kernel of one forward + backward substep (CUDA events on `stream`) */
 int dd_sim_profile_substep(dd_sim *sim, int f, int reps, float *ms_out, char *names_out, int names_cap, int *n_out, cudaStream_t stream);
 
 /* device pointers of the engine's pose table: float4 (x,y,z,0) and (w,x,y,z) per (slot, env, body) */
 int dd_sim_pose_table(dd_sim *sim, float **pos, float **rot, int *slots, int *n_envs, int *n_bodies);
+int dd_sim_pose_grad_table(dd_sim *sim, float **gpos, float **grot);   /* same layout, gradients */
 
 /* ---- Shadow-hand kinematics on the device (replaces HandSimulator.JointVel_Fk + hand_forward_kinematics, mpm/hand.py:347-428).
  * Tables as produced by dexdeform_b200.mujoco_parser.hand_tables; all pointer arguments of dd_hand_fk are DEVICE pointers. */

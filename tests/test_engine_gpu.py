@@ -54,6 +54,7 @@ def reference_spread(lib, sc, S, seedg, ref):
 
 def run_engine(sc, S, seedg, E=1, **kw):
     sim = FusedSim.from_scene(sc, n_envs=E, max_steps=S, **kw)
+    l0 = sim.launch_count()  # (the cell sort of set_state is counted too; the assertions below are about the substeps)
     sim.forward(0, S)
     sim.zero_grad(S)
     t = lambda a: np.ascontiguousarray(np.broadcast_to(a[None], (E,) + a.shape))
@@ -61,7 +62,8 @@ def run_engine(sc, S, seedg, E=1, **kw):
     sim.backward(0, S)
     out = dict(state=sim.get_state(S), grad=sim.get_state_grad(0))
     out["gpos"], out["grot"] = sim.get_pose_grads(0, S + 1)
-    out["launches"] = sim.launch_count()
+    out["launches"] = sim.launch_count() - l0
+    out["info"] = sim.segment_info(0) if kw.get("tile_mode", True) else None
     sim.close()
     return out
 
@@ -187,13 +189,102 @@ def test_tiled_path_equals_dense_path_with_drift_and_dense_cells(svd_mode):
     assert np.abs(b["gpos"] - a["gpos"]).max() < 2e-3 * max(np.abs(a["gpos"]).max(), 1.0)
 
 
-def test_tiled_path_reports_runaway_particles():
-    sc = make_scene(512, 32, box_center=(0.3, 0.5, 0.5), box_width=(0.05, 0.05, 0.05), steps=3, nb=0, seed=3, ground_friction=0.0)
-    sc["v"][:] = np.array([3000.0, 0.0, 0.0], np.float32)  # 4.8 cells per substep: leaves the active region at once
-    sim = FusedSim.from_scene(sc, max_steps=3, tile_mode=True)
-    sim.forward(0, 3)
-    with pytest.raises(EngineError, match="re-sort more often"):
-        sim.sync()
+def test_tiled_path_follows_runaway_particles():
+    """Particles that out-run the region that was active at the last sort (4.8 cells per substep here) activate the bricks
+    they reach on the fly (engine.cu:activate_bricks): same result as the dense path, forward and adjoint, no error."""
+    S = 3
+    sc = make_scene(512, 32, box_center=(0.3, 0.5, 0.5), box_width=(0.05, 0.05, 0.05), steps=S, nb=0, seed=3, ground_friction=0.0)
+    sc["v"][:] = np.array([1500.0, 200.0, -300.0], np.float32)
+    seedg = loss_seed(512, 4)
+    a = run_engine(sc, S, seedg, tile_mode=False, use_graphs=False, grid_ckpt=False)
+    sim = FusedSim.from_scene(sc, max_steps=S, tile_mode=True)
+    before = sim.segment_info(0)["active_bricks"]
+    sim.forward(0, S)
+    sim.sync()
+    after = sim.segment_info(0)["active_bricks"]
+    assert after > before, (before, after)
+    sim.zero_grad(S)
+    sim.add_state_grad(S, seedg["x_grad"][None], seedg["v_grad"][None], seedg["F_grad"][None], seedg["C_grad"][None])
+    sim.backward(0, S)
+    st, gr = sim.get_state(S), sim.get_state_grad(0)
+    assert np.abs(st["x"][0] - sc["x"]).max() > 4 * sc["dx"]   # they did travel
+    for k in ("x", "v", "F", "C"):
+        assert rel_err(st[k], a["state"][k]) < 2e-5, (k, rel_err(st[k], a["state"][k]))
+    for k in ("x", "v"):
+        assert_close_rows(gr[k][0], a["grad"][k][0], 5e-4, k + "_grad")
+    # a second rollout from a new initial state reuses the engine: stale grid contents of the earlier run must not leak
+    sc["v"][:] = np.array([-900.0, 100.0, 500.0], np.float32)
+    sim.set_state(0, sc["x"][None], sc["v"][None], sc["F"][None], sc["C"][None])
+    sim.forward(0, S)
+    b = run_engine(sc, S, seedg, tile_mode=False, use_graphs=False, grid_ckpt=False)
+    st = sim.get_state(S)
+    for k in ("x", "v", "F", "C"):
+        assert rel_err(st[k], b["state"][k]) < 2e-5, (k, rel_err(st[k], b["state"][k]))
+    sim.close()
+
+
+@pytest.mark.parametrize("interval,graphs", [(4, True), (5, False), (1, True)])
+def test_resort_inside_rollout_matches_single_ordering(interval, graphs):
+    """Device-side re-sort every `interval` substeps (states at the boundaries stored in both orders, gradient permuted back in
+    the adjoint) against the same rollout in one ordering and against the dense path: identical physics, so states, state
+    gradients and pose gradients must agree to rounding.  The block moves ~0.5 cells per substep."""
+    S = 12
+    sc = make_scene(3000, 32, box_center=(0.4, 0.35, 0.5), box_width=(0.14, 0.1, 0.14), steps=S, perturb=0.02, nb=4, seed=17, ground_friction=0.3)
+    sc["v"][:] = np.array([160.0, -60.0, 90.0], np.float32) * (1.0 + 0.02 * np.random.default_rng(1).normal(size=(3000, 3)).astype(np.float32))
+    seedg = loss_seed(3000, 6)
+    a = run_engine(sc, S, seedg, tile_mode=False, use_graphs=False, grid_ckpt=False)
+    b = run_engine(sc, S, seedg, tile_mode=True, use_graphs=graphs)
+    c = run_engine(sc, S, seedg, tile_mode=True, use_graphs=graphs, resort_interval=interval)
+    assert c["info"]["n_segments"] == (S + interval - 1) // interval and b["info"]["n_segments"] == 1
+    for other in (a, b):
+        for k in ("x", "v", "F", "C"):
+            assert rel_err(c["state"][k], other["state"][k]) < 2e-5, (k, rel_err(c["state"][k], other["state"][k]))
+        for k in ("x", "v", "F", "C"):
+            assert_close_rows(c["grad"][k][0], other["grad"][k][0], 1e-3, k + "_grad")
+        assert np.abs(c["gpos"] - other["gpos"]).max() < 2e-3 * max(np.abs(other["gpos"]).max(), 1.0)
+        assert np.abs(c["grot"] - other["grot"]).max() < 2e-3 * max(np.abs(other["grot"]).max(), 1.0)
+
+
+def test_resort_in_pieces_and_stale_slots():
+    """forward / backward called per segment (as GradModel does, one env step at a time) gives the same result as one call over
+    the whole range; slots written under an ordering that was replaced are refused instead of returned permuted."""
+    S, L = 8, 4
+    sc = make_scene(2000, 32, box_width=(0.12, 0.1, 0.12), steps=S, perturb=0.02, vel_scale=0.5, on_floor=True, nb=3, seed=5)
+    seedg = loss_seed(2000, 7)
+    whole = run_engine(sc, S, seedg, resort_interval=L)
+    sim = FusedSim.from_scene(sc, max_steps=S, resort_interval=L)
+    sim.forward(0, L)
+    x_mid = sim.get_state(L, ("x",))["x"]          # tail copy (the next segment is not built yet)
+    sim.forward(L, L)
+    assert np.array_equal(sim.get_state(L, ("x",))["x"], x_mid)   # head copy: same particles, caller's order
+    sim.zero_grad(S)
+    sim.add_state_grad(S, seedg["x_grad"][None], seedg["v_grad"][None], seedg["F_grad"][None], seedg["C_grad"][None])
+    sim.backward(L, L)
+    g_mid = sim.get_state_grad(L, ("x",))["x"]
+    sim.backward(0, L)
+    gr = sim.get_state_grad(0)
+    for k in ("x", "v", "F", "C"):
+        assert_close_rows(gr[k][0], whole["grad"][k][0], 1e-4, k + "_grad")
+    assert np.isfinite(g_mid).all() and np.abs(g_mid).max() > 0
+    gp, _ = sim.get_pose_grads(0, S + 1)
+    assert np.abs(gp - whole["gpos"]).max() < 1e-3 * max(np.abs(whole["gpos"]).max(), 1.0)
+    # a new initial state replaces the ordering of segment 0: its old slots are stale, segment 1 is untouched until re-run
+    sim.set_state(0, sc["x"][None], sc["v"][None], sc["F"][None], sc["C"][None])
+    with pytest.raises(EngineError, match="not available"):
+        sim.get_state(2)
+    with pytest.raises(EngineError, match="no gradient seeded|not available"):
+        sim.backward(0, L)
+    sim.forward(0, L)
+    sim.get_state(2)
+    # rolling window on the device: state L becomes state 0 (re-sorted), poses included
+    xL = sim.get_state(L, ("x", "v", "F", "C"))
+    pL = sim.get_poses(L, 1)
+    sim.roll(L)
+    x0 = sim.get_state(0, ("x", "v", "F", "C"))
+    for k in xL:
+        assert np.array_equal(x0[k], xL[k]), k
+    p0 = sim.get_poses(0, 1)
+    assert np.array_equal(p0[0], pL[0]) and np.array_equal(p0[1], pL[1])
     sim.close()
 
 

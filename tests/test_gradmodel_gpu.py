@@ -137,3 +137,148 @@ def test_simulator_state_roundtrip_and_step():
     assert x1.shape == (N, 3) and np.isfinite(x1).all() and x1[:, 1].mean() < y0 + 1e-6   # gravity pulls the block down
     d = sim.get_dists(0, device="numpy")
     assert d.shape == (N, NB)
+
+
+# ---------------------------------------------------------------------------------------------------- long horizon
+def lift_scene(n=3000, steps=50, S=40):
+    """lift_box-like: a plasticine block resting on a two-piece platform that is raised by the actions -- the block travels
+    more than ten cells over the rollout (the tutorial's horizon, tutorials/1_trajectory_optimization.ipynb:184-199)."""
+    sc = make_scene(n, 64, box_center=(0.5, 0.25, 0.5), box_width=(0.08, 0.06, 0.08), steps=steps * S, seed=11, nb=2)
+    bottom = 0.25 - 0.03
+    sc["tfsr"] = np.float32([[0, 0.9, 666.0, 0], [0, 0.9, 666.0, 0]])          # two boxes, friction 0.9, softness 666
+    sc["args"] = np.float32([[0.035, 0.008, 0.07, 0], [0.035, 0.008, 0.07, 0]])
+    pos0 = np.float32([[0.5 - 0.035, bottom - 0.008 - 0.5 / 64, 0.5], [0.5 + 0.035, bottom - 0.008 - 0.5 / 64, 0.5]])
+    rot0 = np.float32([[1, 0, 0, 0], [1, 0, 0, 0]])
+    sc["pos"] = np.repeat(pos0[None], steps * S + 1, 0)
+    sc["rot"] = np.repeat(rot0[None], steps * S + 1, 0)
+    return sc
+
+
+def reference_rollout(ref_gpu, sc, action, S, steps, scale):
+    """mpm/torch_wrapper.py:110-141 re-enacted on the reference's library: per-substep pose upload + substep, then substep_grad
+    and per-substep pose-gradient downloads, torch autograd through the tool kinematics."""
+    n, nb = sc["n"], sc["nb"]
+    sim = Abi1Sim(ref_gpu, sc, S * steps)
+    pos_rot = (torch.tensor(sc["pos"][0]), torch.tensor(sc["rot"][0]))
+    poses = []
+    for s_ in range(steps):
+        a = action[s_].reshape(-1, 6).clamp(-1.0, 1.0) * scale
+        pos, rot = rigid_body_motion(pos_rot, a[None].expand(S, -1, -1) * (torch.arange(S)[:, None, None] + 1) / S)
+        pos_rot = (pos[-1], rot[-1])
+        poses.append((pos, rot))
+        for i in range(S):
+            f = s_ * S + i
+            sim.states[f + 1]["body_pos"].upload(pos[i].detach().numpy())
+            sim.states[f + 1]["body_rot"].upload(rot[i].detach().numpy())
+            sim.substep(f)
+    fe = S * steps
+    x = sim.get(fe, "x")["x"]
+    loss = -x[:, 1].mean()
+    gx = np.zeros((n, 3), np.float32)
+    gx[:, 1] = -1.0 / n
+    sim.states[fe]["x_grad"].upload(gx)
+    for f in range(fe - 1, -1, -1):
+        sim.substep_grad(f)
+    sim.sync()
+    total = 0.0
+    for s_ in range(steps):
+        gp = np.stack([sim.get(s_ * S + i + 1, "body_pos_grad")["body_pos_grad"] for i in range(S)])
+        gr = np.stack([sim.get(s_ * S + i + 1, "body_rot_grad")["body_rot_grad"] for i in range(S)])
+        total = total + (poses[s_][0] * torch.tensor(gp)).sum() + (poses[s_][1] * torch.tensor(gr)).sum()
+    total.backward()
+    return float(loss), action.grad.clone(), x
+
+
+def test_gradmodel_tutorial_horizon_50_steps_of_40_substeps(ref_gpu):
+    """The reference's tutorial horizon through GradModel: 50 env steps x 40 substeps with no set_state in between (the engine
+    re-sorts on the device at every env-step boundary), block lifted by more than 10 cells; loss and action gradients against
+    the reference chain.  Tolerance: rel-L2 <= 1e-2, cosine >= 0.999, or 5x the reference's own spread under a
+    permutation of the particle order if that is larger (2000 substeps of contact dynamics amplify its atomics' noise)."""
+    S_, STEPS_, n = 40, 50, 3000
+    sc = lift_scene(n, STEPS_, S_)
+    nb = sc["nb"]
+    scale = torch.tensor([[0.01] * 3 + [0.015] * 3] * nb, dtype=torch.float32)
+    rng = np.random.default_rng(3)
+    a0 = np.float32(rng.uniform(-0.05, 0.05, (STEPS_, nb, 6)))
+    a0[:, :, 1] = 0.45   # raise the platform: 0.0045 per env step = 0.29 cells, 14 cells over the rollout
+    a0[:, :, 3:] *= 0.2
+    act_ref = torch.tensor(a0, requires_grad=True)
+    loss_ref, grad_ref, x_ref = reference_rollout(ref_gpu, sc, act_ref, S_, STEPS_, scale)
+    assert (x_ref[:, 1].mean() - sc["x"][:, 1].mean()) * 64 > 10, "the block must travel more than ten cells"
+    # the reference against itself with the particles listed in another order
+    perm = np.random.default_rng(0).permutation(n)
+    sc2 = dict(sc)
+    for k in ("x", "v", "F", "C", "mass", "vol", "mu_lam_yield"):
+        sc2[k] = np.ascontiguousarray(sc[k][perm])
+    act2 = torch.tensor(a0, requires_grad=True)
+    _, grad_ref2, _ = reference_rollout(ref_gpu, sc2, act2, S_, STEPS_, scale)
+    spread = rel_l2(grad_ref2.numpy(), grad_ref.numpy())
+
+    sim = MPMSimulator(nb, ground_friction=sc["ground_friction"], gravity=tuple(sc["gravity"].reshape(3) / 30), n_particles=n, dx=sc["dx"],
+                       dt=sc["dt"], max_steps=S_ * STEPS_, substeps=S_, yield_stress=50.0)
+    sim.init_bodies(sc["tfsr"][:, 0], sc["tfsr"][:, 2], sc["tfsr"][:, 1], sc["tfsr"][:, 3], sc["args"], action_scales=scale.tolist(),
+                    pos=sc["pos"][0], rot=sc["rot"][0])
+    sim.set_state(0, (sc["x"], sc["v"], sc["F"].reshape(-1, 3, 3), sc["C"].reshape(-1, 3, 3)) + tuple(np.r_[p, r] for p, r in zip(sc["pos"][0], sc["rot"][0])))
+    info = sim.engine.segment_info(0)
+    assert info["n_segments"] == STEPS_ and info["interval"] == S_
+    model = GradModel(sim, return_grid=())
+    grads = []
+    for it in range(2):   # two optimisation iterations on one engine: cached graphs and segment tables are reused
+        model.zero_grad()
+        if it:
+            sim.set_state(0, (sc["x"], sc["v"], sc["F"].reshape(-1, 3, 3), sc["C"].reshape(-1, 3, 3)) + tuple(np.r_[p, r] for p, r in zip(sc["pos"][0], sc["rot"][0])))
+        action = torch.tensor(a0, device="cuda:0", requires_grad=True)
+        obs = model.get_obs(0, "cuda:0")
+        for j in range(STEPS_):
+            obs = model.forward(j, action[j], *obs)
+        loss = -obs[0][:, 1].mean()
+        loss.backward()
+        grads.append(action.grad.cpu().numpy())
+    sim.sync()
+    x_end = obs[0][:, :3].detach().cpu().numpy()
+    assert abs(float(loss) - loss_ref) < 2e-4 * max(1.0, abs(loss_ref)), (float(loss), loss_ref)
+    print('final position difference', np.abs(x_end - x_ref).max())
+    assert np.abs(x_end - x_ref).max() < 2e-3, np.abs(x_end - x_ref).max()   # after 2000 substeps (0.13 cells)
+    g = grads[0]
+    assert np.isfinite(g).all() and np.abs(g).max() > 0
+    assert rel_l2(grads[1], g) < 1e-3, rel_l2(grads[1], g)   # the second iteration reproduces the first
+    e = rel_l2(g, grad_ref.numpy())
+    print(f"tutorial horizon: action-gradient rel-L2 {e:.3e} cos {cosine(g, grad_ref.numpy()):.6f}; reference self-spread {spread:.3e}")
+    assert e < max(1e-2, 5 * spread), (e, spread)
+    assert cosine(g, grad_ref.numpy()) > min(0.999, 1 - 10 * spread ** 2), cosine(g, grad_ref.numpy())
+
+
+def test_gradmodel_batched_environments():
+    """n_envs = 3: GradModel carries a leading environment axis; every environment's gradient equals the single-environment run."""
+    sc = build_scene()
+    rng = np.random.default_rng(2)
+    E = 3
+    a0 = np.float32(rng.uniform(-0.8, 0.8, (E, STEPS, NB, 6)))
+    a0[..., 1] = -0.9
+    singles = []
+    for e in range(E):
+        sim = make_sim(sc)
+        model = GradModel(sim, return_grid=())
+        model.zero_grad()
+        action = torch.tensor(a0[e], device="cuda:0", requires_grad=True)
+        obs = model.get_obs(0, "cuda:0")
+        for j in range(STEPS):
+            obs = model.forward(j, action[j], *obs)
+        loss = -obs[0][:, 1].mean() + 0.3 * obs[0][:, 6:].mean()
+        loss.backward()
+        singles.append((float(loss), action.grad.cpu().numpy()))
+        sim.engine.close()
+    sim = make_sim(sc, n_envs=E)
+    model = GradModel(sim, return_grid=())
+    model.zero_grad()
+    action = torch.tensor(a0, device="cuda:0", requires_grad=True)   # (E, STEPS, NB, 6)
+    obs = model.get_obs(0, "cuda:0")
+    assert obs[0].shape == (E, N, 6 + NB) and obs[1].shape == (E, NB, 7)
+    for j in range(STEPS):
+        obs = model.forward(j, action[:, j], *obs)
+    losses = -obs[0][..., 1].mean(1) + 0.3 * obs[0][..., 6:].mean((1, 2))
+    losses.sum().backward()
+    g = action.grad.cpu().numpy()
+    for e in range(E):
+        assert abs(float(losses[e]) - singles[e][0]) < 1e-5 * max(1.0, abs(singles[e][0]))
+        assert rel_l2(g[e], singles[e][1]) < 2e-3, (e, rel_l2(g[e], singles[e][1]))
