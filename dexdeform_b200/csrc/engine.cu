@@ -1218,6 +1218,158 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
   chunks_done(sched, lane);
 }
 
+// g2p_grad with ONE tile per warp, in two passes over the chunk (DD_G2PG_MODE=2).  Pass 1 fills the tile with the grid
+// velocities and does the gather half (read-only tile: no ordering constraints between the 27 loads) and writes the partial
+// dL/dx; pass 2 zeroes the same tile and does the scatter of the node adjoints.  The rows are staged twice (the second time
+// from L2), but a warp needs 11.5 KB of shared memory instead of 19.5 KB: 19 instead of 11 warps per SM for a kernel whose
+// time is latency, not throughput.
+#ifndef DD_LB_G2PG2
+#define DD_LB_G2PG2 18
+#endif
+__global__ void __launch_bounds__(32, DD_LB_G2PG2) k_g2p_grad_tile2(KP kp, SegView sg, const float *__restrict__ cur, const float *__restrict__ nxt,
+                                                                   const float4 *__restrict__ grid_v, const float *__restrict__ gin, float *__restrict__ gout,
+                                                                   float4 *__restrict__ ggrid_v, int *sched) {
+  extern __shared__ float4 dd_smem[];
+  const int lane = threadIdx.x & 31;
+  constexpr int kStage = kStageG2PG;
+  float4 *tile = dd_smem, *stage = tile + kTileN + lane;
+  const unsigned gbase = smem_u32(tile);
+  const int nchunks = sg.cnt[0];
+  const int4 *__restrict__ chunks = sg.chunks;
+  const V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+  const float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
+  auto stage_row = [&](int p) {
+    cp_async16(stage, plane4(cur, kp.EN, 0) + p);
+    cp_async16(stage + 32, plane4(nxt, kp.EN, 0) + p);
+    cp_async16(stage + 64, plane4(nxt, kp.EN, 1) + p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cp_async16(stage + 96 + 32 * k, plane4(gin, kp.EN, k) + p);
+    cp_async_commit();
+  };
+  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+    ChunkGeom cg = chunk_geom(chunks[ci], kp);
+    size_t goff = (size_t)cg.env * kp.G;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      stage_row(row_pos(cg, 0, lane));
+      if (pass == 0) fill_tile(tile, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane);
+      else for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      for (int j = 0; j < cg.R; ++j) {
+        bool act = lane_on(cg, j, lane);
+        int p = row_pos(cg, j, lane);
+        cp_async_wait_all();
+        float4 a = stage[0], n0 = stage[32], n1 = stage[64], g0_ = stage[96], g1_ = stage[128], g2_ = stage[160], g3_ = stage[192];
+        if (j + 1 < cg.R) stage_row(row_pos(cg, j + 1, lane));
+        V3 x = v3(a.x, a.y, a.z);
+        M3 gC = m3(g1_.z, g1_.w, g2_.x, g2_.y, g2_.z, g2_.w, g3_.x, g3_.y, g3_.z);
+        V3 gx = v3(g0_.x, g0_.y, g0_.z), gnv = v3(g0_.w, g1_.x, g1_.y), nvel = v3(n0.w, n1.x, n1.y);
+        V3 nx = x + nvel * kp.dt;
+        if (nx.x > hi.x || nx.x < lo) gx.x = 0;
+        if (nx.y > hi.y || nx.y < lo) gx.y = 0;
+        if (nx.z > hi.z || nx.z < lo) gx.z = 0;
+        gnv += gx * kp.dt;
+        Stencil st = make_stencil_safe(x, kp);
+        float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
+        V3 H0 = v3(gC.a00, gC.a10, gC.a20) * s4, H1 = v3(gC.a01, gC.a11, gC.a21) * s4, H2 = v3(gC.a02, gC.a12, gC.a22) * s4;
+        V3 h0 = gnv - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
+        int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
+        bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
+        if (pass == 0) {
+          // ---- gather: dL/dx = gx' (masked) - (4/dx^2) gC'^T v' + sum gradN_n (v_n . h_n), per (i,j) row in separable form
+          V3 d0, d1, d2;
+          stencil_dw(st, kp.inv_dx, d0, d1, d2);
+          float ex[3] = {d0.x, d1.x, d2.x}, ey[3] = {d0.y, d1.y, d2.y}, ez[3] = {d0.z, d1.z, d2.z};
+          V3 gxs = vzero();
+          auto rowsum = [&](int i, int jj, float4 t0, float4 t1, float4 t2) {
+            V3 hij = step_n(step_n(h0, H0, i), H1, jj), hk1 = hij + H2, hk2 = hk1 + H2;
+            float q0 = t0.x * hij.x + t0.y * hij.y + t0.z * hij.z, q1 = t1.x * hk1.x + t1.y * hk1.y + t1.z * hk1.z, q2 = t2.x * hk2.x + t2.y * hk2.y + t2.z * hk2.z;
+            float Sq = fmaf(wz[2], q2, fmaf(wz[1], q1, wz[0] * q0)), SEq = fmaf(ez[2], q2, fmaf(ez[1], q1, ez[0] * q0));
+            gxs.x = fmaf(ex[i] * wy[jj], Sq, gxs.x); gxs.y = fmaf(wx[i] * ey[jj], Sq, gxs.y); gxs.z = fmaf(wx[i] * wy[jj], SEq, gxs.z);
+          };
+          if (in_tile) {
+            const float4 *trow = tile + (tx << 6 | ty << 3);
+            int g0 = tz + 4 * ty + 2 * tx;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int jj = 0; jj < 3; ++jj) {
+                const float4 *r_ = trow + (i << 6 | jj << 3);
+                int g = g0 + 2 * i + 4 * jj;
+                rowsum(i, jj, r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7]);
+              }
+          } else if (act) {
+            const float4 *gg = grid_v + goff + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
+#pragma unroll 1
+            for (int i = 0; i < 3; ++i)
+#pragma unroll 1
+              for (int jj = 0; jj < 3; ++jj) {
+                const float4 *r_ = gg + (i * kp.gy + jj) * kp.gz;
+                // (rolled: weights picked at run time)
+                float wxi = pick(st.w0, st.w1, st.w2, i, 0), wyj = pick(st.w0, st.w1, st.w2, jj, 1), exi = pick(d0, d1, d2, i, 0), eyj = pick(d0, d1, d2, jj, 1);
+                float4 t0 = __ldg(r_), t1 = __ldg(r_ + 1), t2 = __ldg(r_ + 2);
+                V3 hij = h0 + H0 * (float)i + H1 * (float)jj, hk1 = hij + H2, hk2 = hk1 + H2;
+                float q0 = t0.x * hij.x + t0.y * hij.y + t0.z * hij.z, q1 = t1.x * hk1.x + t1.y * hk1.y + t1.z * hk1.z, q2 = t2.x * hk2.x + t2.y * hk2.y + t2.z * hk2.z;
+                float Sq = fmaf(wz[2], q2, fmaf(wz[1], q1, wz[0] * q0)), SEq = fmaf(ez[2], q2, fmaf(ez[1], q1, ez[0] * q0));
+                gxs.x = fmaf(exi * wyj, Sq, gxs.x); gxs.y = fmaf(wxi * eyj, Sq, gxs.y); gxs.z = fmaf(wxi * wyj, SEq, gxs.z);
+              }
+          }
+          gx += gxs - (kp.inv_dx * s4) * mul_t(gC, nvel);  // sum_n w_n v_n is the velocity g2p stored in the next slot
+          if (act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
+        } else {
+          // ---- scatter of w_n h_n into the tile; lanes sharing a cell with a lower lane of this row go straight to the grid
+          unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
+          unsigned peers = __match_any_sync(0xffffffffu, key);
+          bool mine = in_tile && __popc(peers & ((1u << lane) - 1u)) == 0;
+          int txs = in_tile ? tx : 0, tys = in_tile ? ty : 0, tzs = in_tile ? tz : 0;
+          unsigned growb = gbase + 16u * (unsigned)(txs << 6 | tys << 3);
+          int g0 = tzs + 4 * tys + 2 * txs;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            V3 hi_ = step_n(h0, H0, i);
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+              V3 hij = step_n(hi_, H1, jj);
+              float wij = wx[i] * wy[jj];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                V3 h = step_n(hij, H2, k);
+                float w = wij * wz[k];
+                unsigned ga = growb + 16u * (unsigned)((i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7));
+                float4 o = lds_v4(ga);
+                o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
+                sts_v4_if(ga, o, mine);
+              }
+            }
+          }
+          if (act && !mine) {  // shares its cell with a lower lane, or left the tile since the last sort (rolled, rare)
+#pragma unroll 1
+            for (int i = 0; i < 3; ++i)
+#pragma unroll 1
+              for (int jj = 0; jj < 3; ++jj)
+#pragma unroll 1
+                for (int k = 0; k < 3; ++k) {
+                  float w = pick(st.w0, st.w1, st.w2, i, 0) * pick(st.w0, st.w1, st.w2, jj, 1) * pick(st.w0, st.w1, st.w2, k, 2);
+                  V3 h = h0 + H0 * (float)i + H1 * (float)jj + H2 * (float)k;
+                  red_add_v4(ggrid_v + goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, w * h.x, w * h.y, w * h.z, 0.f);
+                }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    for (int n = lane; n < kTileN; n += 32) {
+      int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
+      float4 t = tile[tile_slot(txx, tyy, tzz)];
+      int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
+      if ((t.x != 0.f || t.y != 0.f || t.z != 0.f) && (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
+        red_add_v4(ggrid_v + goff + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, 0.f);
+    }
+    __syncwarp();
+  }
+  chunks_done(sched, lane);
+}
+
 // p2g_grad on tiles
 // asynchronous copies of one particle's inputs into its staging slots, in the two groups the adjoint consumes them in
 struct P2ggStager {
@@ -1851,6 +2003,7 @@ struct dd_sim {
   // persistent launch geometry of the tiled kernels (resident blocks per SM x SMs) and which gather variants run
   int sms = 1;
   int pb_p2g = 0, pb_g2pg = 0, pb_g2p = 0, pb_p2gg = 0;
+  int g2pg_mode = 1, pb_g2pg2 = 0;  // 1: two tiles per warp, one pass; 2: one tile, two passes (k_g2p_grad_tile2)
   bool g2p_tiled = false, p2gg_tiled = false, fuse_gather = false;  // fuse_gather: gather half of the g2p adjoint inside k_p2g_grad_tile
   int w_p2g = 4, w_g2pg = 1, w_g2p = 4, w_p2gg = 4;  // warps per block (the warps of a block are independent; this only sets the shared-memory granularity)
   // upper-bound grids: the live counts are read on the device
@@ -1922,7 +2075,8 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
       k_p2g_tile<SVD, false><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->grid, s->counters + 4);
       k_grid_b<<<s->brick_blocks(), kT, 0, st>>>(kp, sg.cnt, sg.active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
-    if (s->fuse_gather) k_g2p_grad_tile<false><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
+    if (s->g2pg_mode == 2 && !s->fuse_gather) k_g2p_grad_tile2<<<s->tile_blocks(s->pb_g2pg2, 1), 32, (kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
+    else if (s->fuse_gather) k_g2p_grad_tile<false><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
     else k_g2p_grad_tile<true><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
     mark(mk, "g2p_grad_tile");
     k_grid_grad_b<<<s->brick_blocks(), kT, 0, st>>>(kp, sg.cnt, sg.active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
@@ -2211,6 +2365,13 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
         s->pb_g2pg = per_device(k_g2p_grad_tile<true>, s->w_g2pg, two);
       }
       s->pb_g2p = per_device(k_g2p_tile, s->w_g2p, one_g2p);
+      {
+        const char *e4 = getenv("DD_G2PG_MODE");
+        s->g2pg_mode = e4 ? atoi(e4) : 1;
+        size_t sm2 = (kTileN + kStageG2PG * 32) * sizeof(float4);
+        cudaFuncSetAttribute(k_g2p_grad_tile2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+        s->pb_g2pg2 = per_device(k_g2p_grad_tile2, 1, sm2);
+      }
       const char *e1 = getenv("DD_G2P_TILE"), *e2 = getenv("DD_P2GG_TILE");
       s->g2p_tiled = !(e1 && atoi(e1) == 0);  // default: tiled gather
       s->p2gg_tiled = e2 ? atoi(e2) != 0 : cfg->svd_mode == 1;  // default: the staged tile kernel with the fp32 SVD, the flat kernel otherwise
