@@ -146,6 +146,9 @@ DD_DEV int tile_slot(int tx, int ty, int tz) { return tx << 6 | ty << 3 | tile_g
 DD_DEV void red_add_v4(float4 *addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// programmatic dependent launch: let the next kernel on the stream be scheduled / wait for the previous one to complete
+DD_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+DD_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 DD_DEV int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 // a + n b for a stencil offset n in {0,1,2} known after unrolling: nothing, one add or one fma per component (a plain a + b * 0.f
 // costs an fma per component, which IEEE rules keep the compiler from dropping)
@@ -968,10 +971,12 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 *tile = dd_smem + warp * (kTileN + kStageP2G * 32), *stage = tile + kTileN + lane;
   unsigned tbase = smem_u32(tile);
-  const int nchunks = sg.cnt[0];
-  const int4 *__restrict__ chunks = sg.chunks;
+  pdl_launch_dependents();
   for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
+  pdl_wait();  // nothing produced by earlier kernels (tickets, counts, particles) is touched before this point
+  const int nchunks = sg.cnt[0];
+  const int4 *__restrict__ chunks = sg.chunks;
   auto stage_row = [&](int p) {  // x,v,C | 8 of F | quaternion | material: 8 float4; then F22 and the yield stress
 #pragma unroll
     for (int k = 0; k < 6; ++k) cp_async16(stage + 32 * k, plane4(cur, kp.EN, k) + p);
@@ -1089,6 +1094,8 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
   constexpr int kStage = kStageG2PG;  // staged float4s per particle: x | next (x,v) | incoming (gx, gv, gC)
   float4 *tv = dd_smem + warp * ((GATHER ? 2 : 1) * kTileN + kStage * 32), *tg = GATHER ? tv + kTileN : tv, *stage = tg + kTileN + lane;
   unsigned vbase = smem_u32(tv), gbase = smem_u32(tg);
+  pdl_launch_dependents();
+  pdl_wait();
   const int nchunks = sg.cnt[0];
   const int4 *__restrict__ chunks = sg.chunks;
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
@@ -1234,6 +1241,8 @@ __global__ void __launch_bounds__(32, DD_LB_G2PG2) k_g2p_grad_tile2(KP kp, SegVi
   constexpr int kStage = kStageG2PG;
   float4 *tile = dd_smem, *stage = tile + kTileN + lane;
   const unsigned gbase = smem_u32(tile);
+  pdl_launch_dependents();
+  pdl_wait();
   const int nchunks = sg.cnt[0];
   const int4 *__restrict__ chunks = sg.chunks;
   const V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
@@ -1408,6 +1417,8 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 *tile = dd_smem + warp * ((G2PG ? 2 : 1) * kTileN + (STAGED ? kStageP2GG * 32 : 0)), *tile_v = tile + kTileN;
   P2ggStager stager{kp, cur, nxt, gin, yield, mat0, gout, tile + kTileN + lane, -1};
+  pdl_launch_dependents();
+  pdl_wait();
   const int nchunks = sg.cnt[0];
   const int4 *__restrict__ chunks = sg.chunks;
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
@@ -1440,6 +1451,8 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 *tile = dd_smem + warp * kTileN;
+  pdl_launch_dependents();
+  pdl_wait();
   const int nchunks = sg.cnt[0];
   const int4 *__restrict__ chunks = sg.chunks;
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
@@ -1486,6 +1499,8 @@ DD_DEV int brick_node(int brick, int local, const KP &kp, int &env, int &gx_, in
 }
 // (the active-brick count lives in device memory, cnt[1]: launches use a fixed upper-bound grid and stride over the list)
 __global__ void __launch_bounds__(kT) k_zero_bricks(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *a, float4 *b) {
+  pdl_launch_dependents();
+  pdl_wait();
   int total = cnt[1] * 64;
   for (int t = blockIdx.x * kT + threadIdx.x; t < total; t += gridDim.x * kT) {
     int env, x, y, z;
@@ -1534,8 +1549,10 @@ DD_DEV unsigned long long stage_bodies(GridSm &sm, const KP &kp, const BodyTable
 __global__ void __launch_bounds__(kT, 4) k_grid_b(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *__restrict__ grid,
                                                float4 *__restrict__ grid_v, BodyTables bt, float4 *__restrict__ zero_next, int zero_self) {
   __shared__ GridSm sm;
+  pdl_launch_dependents();
+  stage_shapes(sm, kp, bt);  // (shape tables are never written by a kernel)
+  pdl_wait();
   const int nactive = cnt[1], grp = threadIdx.x >> 6, g = threadIdx.x & 63;
-  stage_shapes(sm, kp, bt);
   for (int blk = blockIdx.x; blk * 4 < nactive; blk += gridDim.x) {
     if (blk != (int)blockIdx.x) __syncthreads();  // the previous iteration is done with the staged poses
     int t = blk * kT + threadIdx.x;
@@ -1571,8 +1588,10 @@ __global__ void __launch_bounds__(kT, 4) k_grid_grad_b(KP kp, const int *__restr
                                                     float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos,
                                                     float4 *grot, float4 *gnpos, float4 *gnrot, int zero_m) {
   __shared__ GridSm sm;
+  pdl_launch_dependents();
+  stage_shapes(sm, kp, bt);  // (shape tables are never written by a kernel)
+  pdl_wait();
   const int nactive = cnt[1], grp = threadIdx.x >> 6, g = threadIdx.x & 63;
-  stage_shapes(sm, kp, bt);
   for (int blk = blockIdx.x; blk * 4 < nactive; blk += gridDim.x) {
     if (blk != (int)blockIdx.x) __syncthreads();
     int t = blk * kT + threadIdx.x;
@@ -2002,6 +2021,7 @@ struct dd_sim {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // persistent launch geometry of the tiled kernels (resident blocks per SM x SMs) and which gather variants run
   int sms = 1;
+  bool pdl = false;          // programmatic dependent launch between the hot kernels (DD_PDL=1; measured: no gain inside CUDA graphs, -2 % at config D)
   int pb_p2g = 0, pb_g2pg = 0, pb_g2p = 0, pb_p2gg = 0;
   int g2pg_mode = 1, pb_g2pg2 = 0;  // 1: two tiles per warp, one pass; 2: one tile, two passes (k_g2p_grad_tile2)
   bool g2p_tiled = false, p2gg_tiled = false, fuse_gather = false;  // fuse_gather: gather half of the g2p adjoint inside k_p2g_grad_tile
@@ -2031,6 +2051,21 @@ struct dd_sim {
 
 namespace {
 
+// Launch of a hot-path kernel.  With programmatic dependent launch (DD_PDL=1) the kernel may be scheduled while its
+// predecessor on the stream drains: its blocks become resident as SM resources free up, run their prologue (zeroing the
+// shared-memory tile, ...) and block in griddepcontrol.wait until the predecessor has completed and flushed.  Every block of
+// every hot kernel executes the wait, so completion stays transitive along the chain of kernels.
+template <class K, class... A>
+void launch_hot(dd_sim *s, K kernel, int grid, int block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = s->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 using Mark = std::function<void(const char *)>;
 inline void mark(const Mark *m, const char *name) { if (m) (*m)(name); }
 int fwd_launches(const dd_sim *s) { return 3; }
@@ -2045,12 +2080,12 @@ void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk =
   if (s->cfg.tile_mode) {
     // invariant: the scatter target of substep f is already zero on the active bricks (cleared by the previous grid
     // kernel, or by dd_sim_forward for the first substep of a range; bricks activated on the fly clear themselves)
-    k_p2g_tile<SVD, true><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->G(f), s->counters + 4);
+    launch_hot(s, k_p2g_tile<SVD, true>, s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->G(f), s->counters + 4);
     mark(mk, "p2g_tile (svd+return map+scatter)");
     float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
-    k_grid_b<<<s->brick_blocks(), kT, 0, st>>>(kp, sg.cnt, sg.active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
+    launch_hot(s, k_grid_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_b (grid update + contact)");
-    if (s->g2p_tiled) k_g2p_tile<<<s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * kTileN * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), s->counters + 4);
+    if (s->g2p_tiled) launch_hot(s, k_g2p_tile, s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * kTileN * sizeof(float4), st, kp, sg.view(), cur, nxt, s->GV(f), s->counters + 4);
     else k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, cur, nxt, s->GV(f));
     mark(mk, "g2p");
   } else {
@@ -2072,17 +2107,17 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
   if (s->cfg.tile_mode) {
     // invariant: ggrid_v is zero on the active bricks (k_grid_grad_b clears what it consumes)
     if (!s->grid_ckpt) {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
-      k_p2g_tile<SVD, false><<<s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->grid, s->counters + 4);
-      k_grid_b<<<s->brick_blocks(), kT, 0, st>>>(kp, sg.cnt, sg.active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
+      launch_hot(s, k_p2g_tile<SVD, false>, s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->grid, s->counters + 4);
+      launch_hot(s, k_grid_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
-    if (s->g2pg_mode == 2 && !s->fuse_gather) k_g2p_grad_tile2<<<s->tile_blocks(s->pb_g2pg2, 1), 32, (kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
-    else if (s->fuse_gather) k_g2p_grad_tile<false><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
-    else k_g2p_grad_tile<true><<<s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
+    if (s->g2pg_mode == 2 && !s->fuse_gather) launch_hot(s, k_g2p_grad_tile2, s->tile_blocks(s->pb_g2pg2, 1), 32, (kTileN + kStageG2PG * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
+    else if (s->fuse_gather) launch_hot(s, k_g2p_grad_tile<false>, s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (kTileN + kStageG2PG * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
+    else launch_hot(s, k_g2p_grad_tile<true>, s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
     mark(mk, "g2p_grad_tile");
-    k_grid_grad_b<<<s->brick_blocks(), kT, 0, st>>>(kp, sg.cnt, sg.active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
+    launch_hot(s, k_grid_grad_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
-    if (s->fuse_gather) k_p2g_grad_tile<SVD, true><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * 2 * kTileN * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, s->GV(f), gin, gout, s->counters + 4);
-    else if (s->p2gg_tiled) k_p2g_grad_tile<SVD, false><<<s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * (kTileN + (SVD == 1 ? kStageP2GG * 32 : 0)) * sizeof(float4), st>>>(kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, nullptr, gin, gout, s->counters + 4);
+    if (s->fuse_gather) launch_hot(s, k_p2g_grad_tile<SVD, true>, s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * 2 * kTileN * sizeof(float4), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, s->GV(f), gin, gout, s->counters + 4);
+    else if (s->p2gg_tiled) launch_hot(s, k_p2g_grad_tile<SVD, false>, s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * (kTileN + (SVD == 1 ? kStageP2GG * 32 : 0)) * sizeof(float4), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, nullptr, gin, gout, s->counters + 4);
     else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, cur, nxt, sg.mat0, sg.yield, s->ggrid, gin, gout);
     mark(mk, "p2g_grad (+svd adjoint)");
   } else {
@@ -2354,6 +2389,8 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       s->w_p2g = knob("DD_WPB_P2G", s->w_p2g); s->w_g2pg = knob("DD_WPB_G2PG", s->w_g2pg); s->w_g2p = knob("DD_WPB_G2P", s->w_g2p); s->w_p2gg = knob("DD_WPB_P2GG", s->w_p2gg);
       size_t one = kTileN * sizeof(float4), two = (2 * kTileN + kStageG2PG * 32) * sizeof(float4), one_p2g = (kTileN + kStageP2G * 32) * sizeof(float4), one_g2p = kTileN * sizeof(float4);
       auto per_device = [&](auto kernel, int wpb, size_t smem) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * wpb, smem * wpb); return std::max(occ, 1) * sms; };
+      const char *e0 = getenv("DD_PDL");
+      s->pdl = e0 && atoi(e0) != 0;
       const char *e3 = getenv("DD_FUSE_GATHER");
       s->fuse_gather = e3 && atoi(e3) != 0;  // default off: measured slower at config D (p2g_grad_tile loses more than g2p_grad_tile gains)
       if (cfg->svd_mode == 0) s->pb_p2g = per_device(k_p2g_tile<0, true>, s->w_p2g, one_p2g); else s->pb_p2g = per_device(k_p2g_tile<1, true>, s->w_p2g, one_p2g);
@@ -2612,7 +2649,7 @@ int dd_sim_forward(dd_sim *s, int f0, int n, cudaStream_t st) {
       if (resort) enqueue_build(s, s->seg_of(f), nullptr, s->phys_tail(f), s->seg_of(f - 1), s->phys_cur(f), q);
       if (s->cfg.tile_mode && (f == f0 || resort)) {  // scatter target of the first substep under this active list
         const Segment &sg = s->segs[s->seg_of(f)];
-        k_zero_bricks<<<s->brick_blocks(), kT, 0, q>>>(s->kp, sg.cnt, sg.active, s->G(f), nullptr);
+        launch_hot(s, k_zero_bricks, s->brick_blocks(), kT, 0, q, s->kp, sg.cnt, sg.active, s->G(f), nullptr);
         s->launches += 1;
       }
       if (s->cfg.svd_mode == 0) enqueue_forward_substep<0>(s, f, q); else enqueue_forward_substep<1>(s, f, q);
@@ -2788,7 +2825,7 @@ int dd_sim_profile_substep(dd_sim *s, int f, int reps, float *ms_out, char *name
       if (k >= ev.size()) { cudaEvent_t e_; cudaEventCreate(&e_); ev.push_back(e_); }
       cudaEventRecord(ev[k++], st);
     };
-    k_zero_bricks<<<s->brick_blocks(), kT, 0, st>>>(s->kp, sg.cnt, sg.active, s->G(f), nullptr);  // untimed: scatter target of this substep
+    launch_hot(s, k_zero_bricks, s->brick_blocks(), kT, 0, st, s->kp, sg.cnt, sg.active, s->G(f), nullptr);  // untimed: scatter target of this substep
     new_event();
     Mark mk = [&](const char *name) { if (r == 0) names.push_back(name); new_event(); };
     if (s->cfg.svd_mode == 0) { enqueue_forward_substep<0>(s, f, st, &mk); enqueue_backward_substep<0>(s, f, st, &mk); }
