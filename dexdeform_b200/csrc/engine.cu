@@ -202,9 +202,9 @@ __global__ void __launch_bounds__(kT) k_p2g(KP kp, const float *__restrict__ cur
   M3 F = load_F(cur, kp.EN, p);
   float4 m0 = __ldg(mat0 + p);
   Constit c;
-  float4 q = load_q(cur, kp.EN, p), qu;
+  float4 q = load_q(cur, kp.EN, p), qu = make_float4(0.f, 0.f, 0.f, 1.f);
   constitutive<SVD>(s, F, m0, __ldg(yield + p), kp, c, q, 6, &qu);
-  if (WRITE_F) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); if (SVD == 1) store_constit(nxt, kp.EN, p, c, qu); }
+  if (WRITE_F) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); store_constit(nxt, kp.EN, p, c, qu); }
   Stencil st = make_stencil_safe(s.x, kp);
   float m = m0.x;
   V3 mv = m * s.v;
@@ -318,8 +318,9 @@ __global__ void __launch_bounds__(kT) k_grid(KP kp, const float4 *__restrict__ g
 // and C' = (4/dx) (those moments - v' (x) fx): ~9 instead of 16 floating-point instructions per node.
 template <class Fetch>
 DD_DEV void g2p_gather(Fetch fetch, const float (&wx)[3], const float (&wy)[3], const float (&wz)[3], V3 fx, float s4, V3 &nv, M3 &nC) {
-  V3 Cx = vzero(), Cy = vzero(), Cz = vzero();
-  nv = vzero();
+  // components (x, y) of every sum travel as one packed pair (FFMA2 with the weight broadcast), z as a scalar
+  float2 nvp = pk(0.f, 0.f), Cxp = nvp, Cyp = nvp, Czp = nvp;
+  float nvz = 0.f, Cxz = 0.f, Cyz = 0.f, Czz = 0.f;
   const float kz1 = wz[1], kz2 = 2.f * wz[2];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -327,14 +328,18 @@ DD_DEV void g2p_gather(Fetch fetch, const float (&wx)[3], const float (&wy)[3], 
     for (int j = 0; j < 3; ++j) {
       float wij = wx[i] * wy[j];
       float4 t0 = fetch(i, j, 0), t1 = fetch(i, j, 1), t2 = fetch(i, j, 2);
-      V3 A = v3(fmaf(wz[2], t2.x, fmaf(wz[1], t1.x, wz[0] * t0.x)), fmaf(wz[2], t2.y, fmaf(wz[1], t1.y, wz[0] * t0.y)), fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z)));
-      V3 B = v3(fmaf(kz2, t2.x, kz1 * t1.x), fmaf(kz2, t2.y, kz1 * t1.y), fmaf(kz2, t2.z, kz1 * t1.z));
-      nv.x = fmaf(wij, A.x, nv.x); nv.y = fmaf(wij, A.y, nv.y); nv.z = fmaf(wij, A.z, nv.z);
-      Cz.x = fmaf(wij, B.x, Cz.x); Cz.y = fmaf(wij, B.y, Cz.y); Cz.z = fmaf(wij, B.z, Cz.z);
-      if (i > 0) { float wi = wij * (float)i; Cx.x = fmaf(wi, A.x, Cx.x); Cx.y = fmaf(wi, A.y, Cx.y); Cx.z = fmaf(wi, A.z, Cx.z); }
-      if (j > 0) { float wj = wij * (float)j; Cy.x = fmaf(wj, A.x, Cy.x); Cy.y = fmaf(wj, A.y, Cy.y); Cy.z = fmaf(wj, A.z, Cy.z); }
+      float2 Ap = fma2(wz[2], pk(t2.x, t2.y), fma2(wz[1], pk(t1.x, t1.y), mul2(wz[0], pk(t0.x, t0.y))));
+      float Az = fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z));
+      float2 Bp = fma2(kz2, pk(t2.x, t2.y), mul2(kz1, pk(t1.x, t1.y)));
+      float Bz = fmaf(kz2, t2.z, kz1 * t1.z);
+      nvp = fma2(wij, Ap, nvp); nvz = fmaf(wij, Az, nvz);
+      Czp = fma2(wij, Bp, Czp); Czz = fmaf(wij, Bz, Czz);
+      if (i > 0) { float wi = wij * (float)i; Cxp = fma2(wi, Ap, Cxp); Cxz = fmaf(wi, Az, Cxz); }
+      if (j > 0) { float wj = wij * (float)j; Cyp = fma2(wj, Ap, Cyp); Cyz = fmaf(wj, Az, Cyz); }
     }
   }
+  nv = v3(nvp.x, nvp.y, nvz);
+  V3 Cx = v3(Cxp.x, Cxp.y, Cxz), Cy = v3(Cyp.x, Cyp.y, Cyz), Cz = v3(Czp.x, Czp.y, Czz);
   V3 c0 = (Cx - nv * fx.x) * s4, c1 = (Cy - nv * fx.y) * s4, c2 = (Cz - nv * fx.z) * s4;
   nC = m3(c0.x, c1.x, c2.x, c0.y, c1.y, c2.y, c0.z, c1.z, c2.z);
 }
@@ -608,6 +613,12 @@ constexpr int kTileN = 512;          // 8^3 nodes
 constexpr int kTileWarps = 4;        // chunks per thread block (launch-bound hint; the launch picks the real number)
 constexpr int kStageP2G = 9;         // staged float4 slots per lane: p2g_tile
 constexpr int kStageG2PG = 7;        // g2p_grad_tile
+constexpr int kStageP2GG = 16;       // p2g_grad_tile (slots listed at P2ggStager)
+constexpr int kQueueF4 = 8;          // deferred-lane queue: 32 ints per warp (DeferQueue)
+constexpr size_t kSmemP2G = (kTileN + kStageP2G * 32 + kQueueF4) * sizeof(float4);        // bytes per warp
+constexpr size_t kSmemG2PG = (2 * kTileN + kStageG2PG * 32 + kQueueF4) * sizeof(float4);
+constexpr size_t kSmemG2P = kTileN * sizeof(float4);
+constexpr size_t kSmemP2GG = (kTileN + kStageP2GG * 32) * sizeof(float4);                 // fp32-SVD variant; the fp64 variant does not stage
 // a chunk is stored as R rows of 32 particles (the last row holds the remaining `last`); row j starts at start + 32 j
 struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, last, bx, by, bz; unsigned lastmask; };
 // lanes (columns) of the short last row are given by a bit mask chosen at sort time (the columns whose bank group has particles
@@ -728,19 +739,15 @@ DD_DEV void activate_bricks(const KP &kp, int env, bool miss, int sbx, int sby, 
 }
 
 // TILE = true: node adjoints are read from a swizzled shared-memory tile at (tx,ty,tz); otherwise from the dense grid
-// G2PG = true: the gather half of the g2p adjoint (integrator.cu:1527-1614) is done here as well, from a second tile holding the
-// grid velocities: dL/dx += gx' (clamp-masked) + sum gradN_n (v_n . h_n) - (4/dx^2) gC'^T v',  h_n = gv' + dt gx' + (4/dx) gC' (offset_n - fx),
-// with sum w_n v_n = v' taken from the next slot.  k_g2p_grad_tile then only scatters, with one tile instead of two.
 // Staged inputs (tiled kernel, svd_mode 1): `stg` points at this lane's first staging slot (stride 32 float4); slots as in
 // kP2ggSlot*.  hook.phase1_done() / hook.phase2_done() are called as soon as the respective slots have been read, so that the
 // caller can start the asynchronous copies of the next round into them.
 struct NoHook { DD_DEV void phase1_done() const {} DD_DEV void phase2_done() const {} };
-constexpr int kStageP2GG = 16;  // 0 x|v  1 v|C  2 material  3-5 affine, sigma | 6,7 C  8,9 F  10 qU  11 qV  12,13 gF  14 partial gx  15 (F22, yield, gF22, -)
-template <int SVD, bool TILE, bool G2PG = false, class Hook = NoHook>
+// staging slots: 0 x|v  1 v|C  2 material  3-5 affine, sigma | 6,7 C  8,9 F  10 qU  11 qV  12,13 gF  14 partial gx  15 (F22, yield, gF22, -)
+template <int SVD, bool TILE, class Hook = NoHook>
 DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur, const float *__restrict__ nxt, const float4 *__restrict__ mat0,
                               const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *tile, int ox, int oy, int oz,
-                              const float *__restrict__ gin, float *__restrict__ gout, const float4 *tile_v = nullptr,
-                              const float4 *__restrict__ grid_v = nullptr, const float4 *stg = nullptr, const Hook &hook = Hook()) {
+                              const float *__restrict__ gin, float *__restrict__ gout, const float4 *stg = nullptr, const Hook &hook = Hook()) {
   // svd_mode 1: the gather needs only x, v, the mass and the affine matrix the forward pass left in the next slot; everything
   // else (F, C, the SVD factors, the incoming F gradient) is loaded after the gather so that it does not sit in registers
   XVC s;
@@ -783,45 +790,22 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   //   sum_k dwz_k ( ... )             = m EM + E . val_ij + EB . c2        -> the z component
   //   Sv = sum w_ij A,  sum N k g_mv = sum w_ij B,  sum N i g_mv = sum (i w_ij) A,  sum N j g_mv = sum (j w_ij) A
   // T = sum N g_mv (x) (offset - fx) dx follows from those four sums after the loop (~24 instead of ~33 instructions a node).
+  // Every sum comes in two flavours, with the z weights wz_k and with their derivatives ez_k: the two are computed together as
+  // packed pairs (FFMA2, the node value broadcast to both halves), .x = weight flavour, .y = derivative flavour.
   V3 Sv = vzero(), g_x = vzero(), Tx = vzero(), Ty = vzero(), Tz = vzero();
-  const float kz1 = wz[1], kz2 = 2.f * wz[2], ek1 = ez[1], ek2 = 2.f * ez[2];
-  V3 h0 = vzero(), H0 = vzero(), H1 = vzero(), H2 = vzero(), gxs = vzero(), g2p_x = vzero();
-  if (G2PG) {  // inputs of the g2p adjoint: gradients of state t+1 and the clamp mask of its position update
-    XVC g = load_xvc(gin, kp.EN, p);
-    float4 n0 = ldg_stream(plane4(nxt, kp.EN, 0) + p), n1 = ldg_stream(plane4(nxt, kp.EN, 1) + p);
-    V3 nvel = v3(n0.w, n1.x, n1.y), nx = s.x + nvel * kp.dt;
-    V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
-    float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
-    V3 gx = g.x;
-    if (nx.x > hi.x || nx.x < lo) gx.x = 0;
-    if (nx.y > hi.y || nx.y < lo) gx.y = 0;
-    if (nx.z > hi.z || nx.z < lo) gx.z = 0;
-    H0 = v3(g.C.a00, g.C.a10, g.C.a20) * s4; H1 = v3(g.C.a01, g.C.a11, g.C.a21) * s4; H2 = v3(g.C.a02, g.C.a12, g.C.a22) * s4;
-    h0 = g.v + gx * kp.dt - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
-    g2p_x = gx - (kp.inv_dx * s4) * mul_t(g.C, nvel);
-  }
-  auto row = [&](int i, int j, float wxi, float wyj, float exi, float eyj, float4 t0, float4 t1, float4 t2, float4 u0, float4 u1, float4 u2) {
+  const float2 WE0 = pk(wz[0], ez[0]), WE1 = pk(wz[1], ez[1]), WE2 = pk(wz[2], ez[2]), KE2 = pk(2.f * wz[2], 2.f * ez[2]);
+  auto row = [&](int i, int j, float wxi, float wyj, float exi, float eyj, float4 t0, float4 t1, float4 t2) {
     float wij = wxi * wyj, a1 = exi * wyj, a2 = wxi * eyj;
-    if (G2PG) {
-      V3 hij = step_n(step_n(h0, H0, i), H1, j), hk1 = hij + H2, hk2 = hk1 + H2;
-      float q0 = u0.x * hij.x + u0.y * hij.y + u0.z * hij.z, q1 = u1.x * hk1.x + u1.y * hk1.y + u1.z * hk1.z, q2 = u2.x * hk2.x + u2.y * hk2.y + u2.z * hk2.z;
-      float Sq = fmaf(wz[2], q2, fmaf(wz[1], q1, wz[0] * q0)), SEq = fmaf(ez[2], q2, fmaf(ez[1], q1, ez[0] * q0));
-      gxs.x = fmaf(a1, Sq, gxs.x); gxs.y = fmaf(a2, Sq, gxs.y); gxs.z = fmaf(wij, SEq, gxs.z);
-    }
     V3 vij = step_n(step_n(base, c0, i), c1, j);
-    V3 A = v3(fmaf(wz[2], t2.x, fmaf(wz[1], t1.x, wz[0] * t0.x)), fmaf(wz[2], t2.y, fmaf(wz[1], t1.y, wz[0] * t0.y)), fmaf(wz[2], t2.z, fmaf(wz[1], t1.z, wz[0] * t0.z)));
-    V3 B = v3(fmaf(kz2, t2.x, kz1 * t1.x), fmaf(kz2, t2.y, kz1 * t1.y), fmaf(kz2, t2.z, kz1 * t1.z));
-    float M = fmaf(wz[2], t2.w, fmaf(wz[1], t1.w, wz[0] * t0.w));
-    V3 E = v3(fmaf(ez[2], t2.x, fmaf(ez[1], t1.x, ez[0] * t0.x)), fmaf(ez[2], t2.y, fmaf(ez[1], t1.y, ez[0] * t0.y)), fmaf(ez[2], t2.z, fmaf(ez[1], t1.z, ez[0] * t0.z)));
-    V3 EB = v3(fmaf(ek2, t2.x, ek1 * t1.x), fmaf(ek2, t2.y, ek1 * t1.y), fmaf(ek2, t2.z, ek1 * t1.z));
-    float EM = fmaf(ez[2], t2.w, fmaf(ez[1], t1.w, ez[0] * t0.w));
-    float S = fmaf(B.z, c2.z, fmaf(B.y, c2.y, fmaf(B.x, c2.x, fmaf(A.z, vij.z, fmaf(A.y, vij.y, fmaf(A.x, vij.x, m_p * M))))));
-    float SE = fmaf(EB.z, c2.z, fmaf(EB.y, c2.y, fmaf(EB.x, c2.x, fmaf(E.z, vij.z, fmaf(E.y, vij.y, fmaf(E.x, vij.x, m_p * EM))))));
-    g_x.x = fmaf(a1, S, g_x.x); g_x.y = fmaf(a2, S, g_x.y); g_x.z = fmaf(wij, SE, g_x.z);
-    Sv.x = fmaf(wij, A.x, Sv.x); Sv.y = fmaf(wij, A.y, Sv.y); Sv.z = fmaf(wij, A.z, Sv.z);
-    Tz.x = fmaf(wij, B.x, Tz.x); Tz.y = fmaf(wij, B.y, Tz.y); Tz.z = fmaf(wij, B.z, Tz.z);
-    if (i > 0) { float wi = wij * (float)i; Tx.x = fmaf(wi, A.x, Tx.x); Tx.y = fmaf(wi, A.y, Tx.y); Tx.z = fmaf(wi, A.z, Tx.z); }
-    if (j > 0) { float wj = wij * (float)j; Ty.x = fmaf(wj, A.x, Ty.x); Ty.y = fmaf(wj, A.y, Ty.y); Ty.z = fmaf(wj, A.z, Ty.z); }
+    float2 AEx = fma2(t2.x, WE2, fma2(t1.x, WE1, mul2(t0.x, WE0))), AEy = fma2(t2.y, WE2, fma2(t1.y, WE1, mul2(t0.y, WE0)));   // (A, E)
+    float2 AEz = fma2(t2.z, WE2, fma2(t1.z, WE1, mul2(t0.z, WE0))), AEm = fma2(t2.w, WE2, fma2(t1.w, WE1, mul2(t0.w, WE0)));   // .. (M, EM)
+    float2 BEx = fma2(t2.x, KE2, mul2(t1.x, WE1)), BEy = fma2(t2.y, KE2, mul2(t1.y, WE1)), BEz = fma2(t2.z, KE2, mul2(t1.z, WE1));  // (B, EB)
+    float2 SS = fma2(c2.z, BEz, fma2(c2.y, BEy, fma2(c2.x, BEx, fma2(vij.z, AEz, fma2(vij.y, AEy, fma2(vij.x, AEx, mul2(m_p, AEm)))))));  // (S, SE)
+    g_x.x = fmaf(a1, SS.x, g_x.x); g_x.y = fmaf(a2, SS.x, g_x.y); g_x.z = fmaf(wij, SS.y, g_x.z);
+    Sv.x = fmaf(wij, AEx.x, Sv.x); Sv.y = fmaf(wij, AEy.x, Sv.y); Sv.z = fmaf(wij, AEz.x, Sv.z);
+    Tz.x = fmaf(wij, BEx.x, Tz.x); Tz.y = fmaf(wij, BEy.x, Tz.y); Tz.z = fmaf(wij, BEz.x, Tz.z);
+    if (i > 0) { float wi = wij * (float)i; Tx.x = fmaf(wi, AEx.x, Tx.x); Tx.y = fmaf(wi, AEy.x, Tx.y); Tx.z = fmaf(wi, AEz.x, Tx.z); }
+    if (j > 0) { float wj = wij * (float)j; Ty.x = fmaf(wj, AEx.x, Ty.x); Ty.y = fmaf(wj, AEy.x, Ty.y); Ty.z = fmaf(wj, AEz.x, Ty.z); }
   };
   if (in_tile) {
     const float4 *trow = tile + (tx << 6 | ty << 3);
@@ -832,13 +816,7 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
       for (int j = 0; j < 3; ++j) {
         const float4 *r_ = trow + (i << 6 | j << 3);
         int g = g0 + 2 * i + 4 * j;
-        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (G2PG) {
-          const float4 *v_ = tile_v + (tx << 6 | ty << 3) + (i << 6 | j << 3);
-          row(i, j, wx[i], wy[j], ex[i], ey[j], r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7], v_[g & 7], v_[(g + 1) & 7], v_[(g + 2) & 7]);
-        } else {
-          row(i, j, wx[i], wy[j], ex[i], ey[j], r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7], z4, z4, z4);
-        }
+        row(i, j, wx[i], wy[j], ex[i], ey[j], r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7]);
       }
   } else if (TILE) {  // left the tile since the last sort (rare): rolled loop over the dense grid, kept small on purpose
 #pragma unroll 1
@@ -846,9 +824,7 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
         const float4 *r_ = gg + (i * kp.gy + j) * kp.gz;
-        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), u0 = z4, u1 = z4, u2 = z4;
-        if (G2PG) { const float4 *v_ = grid_v + (r_ - ggrid); u0 = __ldg(v_); u1 = __ldg(v_ + 1); u2 = __ldg(v_ + 2); }
-        row(i, j, pick(st.w0, st.w1, st.w2, i, 0), pick(st.w0, st.w1, st.w2, j, 1), pick(d0, d1, d2, i, 0), pick(d0, d1, d2, j, 1), __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2), u0, u1, u2);
+        row(i, j, pick(st.w0, st.w1, st.w2, i, 0), pick(st.w0, st.w1, st.w2, j, 1), pick(d0, d1, d2, i, 0), pick(d0, d1, d2, j, 1), __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2));
       }
   } else {
 #pragma unroll
@@ -856,8 +832,7 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const float4 *r_ = gg + (i * kp.gy + j) * kp.gz;
-        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        row(i, j, wx[i], wy[j], ex[i], ey[j], __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2), z4, z4, z4);
+        row(i, j, wx[i], wy[j], ex[i], ey[j], __ldg(r_), __ldg(r_ + 1), __ldg(r_ + 2));
       }
   }
   M3 gF_next;
@@ -873,7 +848,7 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
       qu = ldg_stream(aux4(nxt, kp.EN, 3) + p); q = load_q(nxt, kp.EN, p);
       g0 = ldg_stream(plane4(gin, kp.EN, 4) + p); g1 = ldg_stream(plane4(gin, kp.EN, 5) + p);
       sc = make_float4(__ldg(cur + (size_t)24 * kp.EN + p), __ldg(yield + p), __ldg(gin + (size_t)24 * kp.EN + p), 0.f);
-      if (!G2PG) part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by the g2p adjoint
+      part = plane4(gout, kp.EN, 0)[p];  // partial dL/dx written by the g2p adjoint
     }
     hook.phase2_done();
     s.C = m3(p1.z, p1.w, cc.x, cc.y, cc.z, cc.w, d.x, d.y, d.z);
@@ -895,9 +870,9 @@ DD_DEV void p2g_grad_particle(const KP &kp, int p, const float *__restrict__ cur
   V3 g_v = m_p * Sv;
   if (SVD != 1) {
     gF_next = load_F(gin, kp.EN, p);
-    if (!G2PG) part = plane4(gout, kp.EN, 0)[p];
+    part = plane4(gout, kp.EN, 0)[p];
   }
-  if (G2PG) g_x += g2p_x + gxs; else g_x += v3(part.x, part.y, part.z);
+  g_x += v3(part.x, part.y, part.z);
   // Adjoint of stress -> (F_new, R = U V^T, J) and of the return map, then through the SVD (integrator.cu:541-620, 131-159),
   // regrouped: with W = U^T g_R V and Y = U^T g_Fnew V every U/V gradient the reference materialises is
   //   U^T gU = W + Y E,   V^T gV = W^T + Y^T E      (E = diag(exp eps), plastic branch only)
@@ -963,13 +938,62 @@ __global__ void __launch_bounds__(kT, DD_LB_P2G_GRAD) k_p2g_grad(KP kp, const in
 // (dense cells, drift) are detected with match.any and serialised.  The tile is flushed with one vector reduction per
 // touched node instead of one per (particle, node).
 
+// Lanes that cannot use the tile in their row -- a lane whose cell is also the cell of a lower lane of the same row (the
+// read-modify-write of the row would lose one of the two updates), or whose stencil has left the tile since the last sort --
+// are not served inside the row loop (a second dependent pass of 27 updates for one or two lanes of the warp): their storage
+// positions go to a small per-warp queue, and whenever 32 are waiting (and at the end of the kernel) every lane takes one,
+// reads its inputs back and sends its 27 contributions straight to the grid.  Half a percent of the particles collide after
+// a fresh sort, but a quarter of the rows hold one of them.
+struct DeferQueue {
+  int *slots;  // 32 ints of shared memory, private to the warp
+  int n;       // warp-uniform
+  template <class Flush>
+  DD_DEV void push(bool defer, int p, int lane, Flush flush) {
+    unsigned dm = __ballot_sync(0xffffffffu, defer);
+    if (dm == 0u) return;
+    int k = __popc(dm);
+    if (n + k > 32) flush();
+    if (defer) slots[n + __popc(dm & ((1u << lane) - 1u))] = p;
+    n += k;
+  }
+};
+// scatter of one particle straight to the grid from what the forward pass stored: x, v of state t, the affine matrix in slot t+1
+__device__ __noinline__ void p2g_direct(const KP &kp, int p, const float *cur, const float *nxt, const float4 *__restrict__ mat0, float4 *__restrict__ grid) {
+  float4 a = __ldcg(plane4(cur, kp.EN, 0) + p), b = __ldcg(plane4(cur, kp.EN, 1) + p), m0 = __ldg(mat0 + p);
+  float4 a0 = __ldcg(aux4(nxt, kp.EN, 0) + p), a1 = __ldcg(aux4(nxt, kp.EN, 1) + p), a2 = __ldcg(aux4(nxt, kp.EN, 2) + p);
+  V3 x = v3(a.x, a.y, a.z), v = v3(a.w, b.x, b.y);
+  Stencil st = make_stencil_safe(x, kp);
+  float m = m0.x;
+  V3 c0 = v3(a0.x, a0.w, a1.z) * kp.dx, c1 = v3(a0.y, a1.x, a1.w) * kp.dx, c2 = v3(a0.z, a1.y, a2.x) * kp.dx;
+  V3 base = m * v - (c0 * st.fx.x + c1 * st.fx.y + c2 * st.fx.z);
+  float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
+  float4 *g = grid + (size_t)(p / kp.N) * kp.G + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    V3 vi = step_n(base, c0, i);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      V3 vij = step_n(vi, c1, j);
+      float wij = wx[i] * wy[j];
+      float4 *r_ = g + (i * kp.gy + j) * kp.gz;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        V3 val = step_n(vij, c2, k);
+        float w = wij * wz[k];
+        red_add_v4(r_ + k, val.x * w, val.y * w, val.z * w, m * w);
+      }
+    }
+  }
+}
+
 template <int SVD, bool WRITE_F>
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP kp, SegView sg, const float *__restrict__ cur,
                                                                  float *__restrict__ nxt, const float4 *__restrict__ mat0,
                                                                  const float *__restrict__ yield, float4 *__restrict__ grid, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tile = dd_smem + warp * (kTileN + kStageP2G * 32), *stage = tile + kTileN + lane;
+  float4 *tile = dd_smem + warp * (kTileN + kStageP2G * 32 + kQueueF4), *stage = tile + kTileN + lane;
+  DeferQueue dq{reinterpret_cast<int *>(tile + kTileN + kStageP2G * 32), 0};
   unsigned tbase = smem_u32(tile);
   pdl_launch_dependents();
   for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -986,6 +1010,12 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     cp_async4(reinterpret_cast<float *>(stage + 256) + 1, yield + p);
     cp_async_commit();
   };
+  auto flush_queue = [&]() {
+    __syncwarp();  // the affine matrices the queued particles' lanes stored are visible to the whole warp
+    if (lane < dq.n) p2g_direct(kp, dq.slots[lane], cur, nxt, mat0, grid);
+    __syncwarp();
+    dq.n = 0;
+  };
   // (no look-ahead across chunks: a warp that holds a chunk in reserve lengthens the tail of the launch -- measured)
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
@@ -996,7 +1026,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     bool act = lane_on(cg, j, lane);
     int p = row_pos(cg, j, lane);  // idle lanes shadow a valid particle, contribute nothing
     cp_async_wait_all();
-    float4 r0 = stage[0], r1 = stage[32], r2 = stage[64], r3 = stage[96], r4 = stage[128], r5 = stage[160], q = stage[192], m0 = stage[224], r8 = stage[256], qu;
+    float4 r0 = stage[0], r1 = stage[32], r2 = stage[64], r3 = stage[96], r4 = stage[128], r5 = stage[160], q = stage[192], m0 = stage[224], r8 = stage[256], qu = make_float4(0.f, 0.f, 0.f, 1.f);
     if (j + 1 < cg.R) stage_row(row_pos(cg, j + 1, lane));
     XVC s;
     s.x = v3(r0.x, r0.y, r0.z);
@@ -1005,7 +1035,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     M3 F = m3(r4.x, r4.y, r4.z, r4.w, r5.x, r5.y, r5.z, r5.w, r8.x);
     Constit c;
     constitutive<SVD>(s, F, m0, r8.y, kp, c, q, 6, &qu);
-    if (WRITE_F && act) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); if (SVD == 1) store_constit(nxt, kp.EN, p, c, qu); }
+    if (WRITE_F && act) { store_F(nxt, kp.EN, p, c.nF); store_q(nxt, kp.EN, p, q); store_constit(nxt, kp.EN, p, c, qu); }
     Stencil st = make_stencil_safe(s.x, kp);
     float m = m0.x;
     V3 c0 = v3(c.affine.a00, c.affine.a10, c.affine.a20) * kp.dx, c1 = v3(c.affine.a01, c.affine.a11, c.affine.a21) * kp.dx,
@@ -1023,45 +1053,27 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
-    int rank = __popc(peers & ((1u << lane) - 1u));
-    int maxr = __reduce_max_sync(0xffffffffu, rank);
+    bool mine = in_tile && (peers & ((1u << lane) - 1u)) == 0u;  // lowest lane of its cell in this row
     if (!in_tile) { tx = ty = tz = 0; }
-    // one pass unless two lanes of this round share a cell (measured: cheaper here than sending the collided lanes' 27
-    // contributions straight to the grid, which is what the lighter g2p adjoint does)
-    for (int r = 0; r <= maxr; ++r) {
-      bool mine = in_tile && rank == r;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        V3 vi = step_n(base, c0, i);
+    for (int i = 0; i < 3; ++i) {
+      V3 vi = step_n(base, c0, i);
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-          V3 vij = step_n(vi, c1, jj);
-          float wij = wx[i] * wy[jj];
+      for (int jj = 0; jj < 3; ++jj) {
+        V3 vij = step_n(vi, c1, jj);
+        float wij = wx[i] * wy[jj];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            V3 val = step_n(vij, c2, k);
-            float w = wij * wz[k];
-            unsigned a = tbase + 16u * (unsigned)tile_slot(tx + i, ty + jj, tz + k);
-            float4 t = lds_v4(a);
-            t.x = fmaf(val.x, w, t.x); t.y = fmaf(val.y, w, t.y); t.z = fmaf(val.z, w, t.z); t.w = fmaf(m, w, t.w);
-            sts_v4_if(a, t, mine);
-          }
+        for (int k = 0; k < 3; ++k) {
+          V3 val = step_n(vij, c2, k);
+          float w = wij * wz[k];
+          unsigned a = tbase + 16u * (unsigned)tile_slot(tx + i, ty + jj, tz + k);
+          float4 t = lds_v4(a);
+          t.x = fmaf(val.x, w, t.x); t.y = fmaf(val.y, w, t.y); t.z = fmaf(val.z, w, t.z); t.w = fmaf(m, w, t.w);
+          sts_v4_if(a, t, mine);
         }
       }
     }
-    if (act && !in_tile) {  // drifted more than one cell since the last sort: straight to the grid
-      tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
-#pragma unroll 1
-      for (int i = 0; i < 3; ++i)
-#pragma unroll 1
-        for (int jj = 0; jj < 3; ++jj)
-#pragma unroll 1
-          for (int k = 0; k < 3; ++k) {
-            float w = pick(st.w0, st.w1, st.w2, i, 0) * pick(st.w0, st.w1, st.w2, jj, 1) * pick(st.w0, st.w1, st.w2, k, 2);
-            V3 a = (base + c0 * (float)i + c1 * (float)jj + c2 * (float)k) * w;
-            red_add_v4(g + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, a.x, a.y, a.z, m * w);
-          }
-    }
+    dq.push(act && !mine, p, lane, flush_queue);  // shares its cell with a lower lane of the row, or has left the tile
   }
   __syncwarp();
   for (int n = lane; n < kTileN; n += 32) {  // flush, and leave the tile zeroed for the next chunk
@@ -1077,29 +1089,72 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
   }
   __syncwarp();
   }
+  flush_queue();
   chunks_done(sched, lane);
 }
 
 // g2p_grad on tiles (integrator.cu:1527-1614): grid velocities are gathered from a tile copy, their adjoint is scattered
 // into a second tile.  With h_n = gv' + (4/dx) gC' (offset_n - fx) (affine in the offset, so evaluated incrementally):
 //   d/d v_n  = w_n h_n ;  dL/dx = -(4/dx^2) gC'^T (sum w_n v_n) + sum gradN_n (v_n . h_n)
-// GATHER = false: scatter only (one tile); the gather half then runs inside k_p2g_grad_tile<.., true>
-template <bool GATHER>
-__global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD_LB_G2PG_SCATTER) k_g2p_grad_tile(KP kp, SegView sg, const float *__restrict__ cur,
+struct G2pgIn { V3 x, gx, gnv, nvel; M3 gC; };
+DD_DEV G2pgIn g2pg_inputs(const KP &kp, float4 a, float4 n0, float4 n1, float4 g0, float4 g1, float4 g2, float4 g3) {
+  G2pgIn r;
+  r.x = v3(a.x, a.y, a.z);
+  r.nvel = v3(n0.w, n1.x, n1.y);
+  r.gx = v3(g0.x, g0.y, g0.z);
+  r.gnv = v3(g0.w, g1.x, g1.y);
+  r.gC = m3(g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z);
+  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
+  float lo = kp.gh * kp.dx;
+  V3 nx = r.x + r.nvel * kp.dt;
+  if (nx.x > hi.x || nx.x < lo) r.gx.x = 0;
+  if (nx.y > hi.y || nx.y < lo) r.gx.y = 0;
+  if (nx.z > hi.z || nx.z < lo) r.gx.z = 0;
+  r.gnv += r.gx * kp.dt;
+  return r;
+}
+// scatter half of one queued particle straight to the grid (see DeferQueue)
+__device__ __noinline__ void g2pg_direct(const KP &kp, int p, const float *__restrict__ cur, const float *__restrict__ nxt, const float *__restrict__ gin, float4 *__restrict__ ggrid_v) {
+  G2pgIn in = g2pg_inputs(kp, ldg_stream(plane4(cur, kp.EN, 0) + p), ldg_stream(plane4(nxt, kp.EN, 0) + p), ldg_stream(plane4(nxt, kp.EN, 1) + p),
+                          ldg_stream(plane4(gin, kp.EN, 0) + p), ldg_stream(plane4(gin, kp.EN, 1) + p), ldg_stream(plane4(gin, kp.EN, 2) + p), ldg_stream(plane4(gin, kp.EN, 3) + p));
+  Stencil st = make_stencil_safe(in.x, kp);
+  float s4 = kp.inv_dx * 4.f;
+  float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
+  V3 H0 = v3(in.gC.a00, in.gC.a10, in.gC.a20) * s4, H1 = v3(in.gC.a01, in.gC.a11, in.gC.a21) * s4, H2 = v3(in.gC.a02, in.gC.a12, in.gC.a22) * s4;
+  V3 h0 = in.gnv - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
+  float4 *g = ggrid_v + (size_t)(p / kp.N) * kp.G + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    V3 hi_ = step_n(h0, H0, i);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      V3 hij = step_n(hi_, H1, j);
+      float wij = wx[i] * wy[j];
+      float4 *r_ = g + (i * kp.gy + j) * kp.gz;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        V3 h = step_n(hij, H2, k);
+        float w = wij * wz[k];
+        red_add_v4(r_ + k, w * h.x, w * h.y, w * h.z, 0.f);
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_tile(KP kp, SegView sg, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout,
                                                                       float4 *__restrict__ ggrid_v, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kStage = kStageG2PG;  // staged float4s per particle: x | next (x,v) | incoming (gx, gv, gC)
-  float4 *tv = dd_smem + warp * ((GATHER ? 2 : 1) * kTileN + kStage * 32), *tg = GATHER ? tv + kTileN : tv, *stage = tg + kTileN + lane;
-  unsigned vbase = smem_u32(tv), gbase = smem_u32(tg);
+  float4 *tv = dd_smem + warp * (2 * kTileN + kStage * 32 + kQueueF4), *tg = tv + kTileN, *stage = tg + kTileN + lane;
+  DeferQueue dq{reinterpret_cast<int *>(tg + kTileN + kStage * 32), 0};
+  unsigned gbase = smem_u32(tg);
   pdl_launch_dependents();
   pdl_wait();
   const int nchunks = sg.cnt[0];
   const int4 *__restrict__ chunks = sg.chunks;
-  V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
-  float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
+  const float s4 = kp.inv_dx * 4.f;
   auto stage_row = [&](int p) {
     cp_async16(stage, plane4(cur, kp.EN, 0) + p);
     cp_async16(stage + 32, plane4(nxt, kp.EN, 0) + p);
@@ -1108,91 +1163,67 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
     for (int k = 0; k < 4; ++k) cp_async16(stage + 96 + 32 * k, plane4(gin, kp.EN, k) + p);
     cp_async_commit();
   };
+  auto flush_queue = [&]() {
+    if (lane < dq.n) g2pg_direct(kp, dq.slots[lane], cur, nxt, gin, ggrid_v);
+    __syncwarp();
+    dq.n = 0;
+  };
   // (no look-ahead across chunks: a warp that holds a chunk in reserve lengthens the tail of the launch -- measured)
   for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   stage_row(row_pos(cg, 0, lane));
   size_t goff = (size_t)cg.env * kp.G;
-  if (GATHER) fill_tile(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
-  else for (int n = lane; n < kTileN; n += 32) tg[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fill_tile(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane_on(cg, j, lane);
     int p = row_pos(cg, j, lane);
     cp_async_wait_all();
-    float4 a = stage[0], n0 = stage[32], n1 = stage[64], g0_ = stage[96], g1_ = stage[128], g2_ = stage[160], g3_ = stage[192];
+    G2pgIn in = g2pg_inputs(kp, stage[0], stage[32], stage[64], stage[96], stage[128], stage[160], stage[192]);
     if (j + 1 < cg.R) stage_row(row_pos(cg, j + 1, lane));
-    V3 x = v3(a.x, a.y, a.z);
-    XVC g;
-    g.x = v3(g0_.x, g0_.y, g0_.z);
-    g.v = v3(g0_.w, g1_.x, g1_.y);
-    g.C = m3(g1_.z, g1_.w, g2_.x, g2_.y, g2_.z, g2_.w, g3_.x, g3_.y, g3_.z);
-    V3 gx = g.x, gnv = g.v;
-    V3 nx = x + v3(n0.w, n1.x, n1.y) * kp.dt;
-    if (nx.x > hi.x || nx.x < lo) gx.x = 0;
-    if (nx.y > hi.y || nx.y < lo) gx.y = 0;
-    if (nx.z > hi.z || nx.z < lo) gx.z = 0;
-    gnv += gx * kp.dt;
-    Stencil st = make_stencil_safe(x, kp);
+    Stencil st = make_stencil_safe(in.x, kp);
     V3 d0, d1, d2;
     stencil_dw(st, kp.inv_dx, d0, d1, d2);
     float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
     float ex[3] = {d0.x, d1.x, d2.x}, ey[3] = {d0.y, d1.y, d2.y}, ez[3] = {d0.z, d1.z, d2.z};
-    V3 H0 = v3(g.C.a00, g.C.a10, g.C.a20) * s4, H1 = v3(g.C.a01, g.C.a11, g.C.a21) * s4, H2 = v3(g.C.a02, g.C.a12, g.C.a22) * s4;
-    V3 h0 = gnv - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
+    V3 H0 = v3(in.gC.a00, in.gC.a10, in.gC.a20) * s4, H1 = v3(in.gC.a01, in.gC.a11, in.gC.a21) * s4, H2 = v3(in.gC.a02, in.gC.a12, in.gC.a22) * s4;
+    V3 h0 = in.gnv - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
     int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;  // (every brick this stencil needs was activated by the forward pass)
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
-    int rank = __popc(peers & ((1u << lane) - 1u));
+    bool mine = in_tile && (peers & ((1u << lane) - 1u)) == 0u;  // lowest lane of its cell in this row: scatters into the tile
     if (!in_tile) { tx = ty = tz = 0; }
     V3 gxs = vzero();
     const float4 *tvrow = tv + (tx << 6 | ty << 3);
     unsigned growb = gbase + 16u * (unsigned)(tx << 6 | ty << 3);
     int g0 = tz + 4 * ty + 2 * tx;
-    {  // first pass: the gather half (read-only tile, every lane) and the scatter of the lanes that own their cell this round
-      bool mine = in_tile && rank == 0;
+    // the gather half (read-only tile, every lane) and the scatter of the lanes that own their cell in this row
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        V3 hi_ = step_n(h0, H0, i);
+    for (int i = 0; i < 3; ++i) {
+      V3 hi_ = step_n(h0, H0, i);
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-          V3 hij = step_n(hi_, H1, jj);
-          float wij = wx[i] * wy[jj], a1 = ex[i] * wy[jj], a2 = wx[i] * ey[jj];
+      for (int jj = 0; jj < 3; ++jj) {
+        V3 hij = step_n(hi_, H1, jj);
+        float wij = wx[i] * wy[jj], a1 = ex[i] * wy[jj], a2 = wx[i] * ey[jj];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            V3 h = step_n(hij, H2, k);
-            float w = wij * wz[k];
-            int so = (i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7);
-            float4 t = GATHER ? tvrow[so] : make_float4(0.f, 0.f, 0.f, 0.f);
-            unsigned ga = growb + 16u * (unsigned)so;
-            float4 o = lds_v4(ga);
-            o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
-            sts_v4_if(ga, o, mine);
-            if (GATHER) {
-              float qn = t.x * h.x + t.y * h.y + t.z * h.z;
-              float tt = wz[k] * qn, uu = ez[k] * qn;
-              gxs.x = fmaf(a1, tt, gxs.x); gxs.y = fmaf(a2, tt, gxs.y); gxs.z = fmaf(wij, uu, gxs.z);
-            }
-          }
+        for (int k = 0; k < 3; ++k) {
+          V3 h = step_n(hij, H2, k);
+          float w = wij * wz[k];
+          int so = (i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7);
+          float4 t = tvrow[so];
+          unsigned ga = growb + 16u * (unsigned)so;
+          float4 o = lds_v4(ga);
+          o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
+          sts_v4_if(ga, o, mine);
+          float qn = t.x * h.x + t.y * h.y + t.z * h.z;
+          float tt = wz[k] * qn, uu = ez[k] * qn;
+          gxs.x = fmaf(a1, tt, gxs.x); gxs.y = fmaf(a2, tt, gxs.y); gxs.z = fmaf(wij, uu, gxs.z);
         }
       }
     }
-    if (in_tile && rank > 0) {  // cell shared with a lower lane: scatter straight to the grid (rolled, rare)
-#pragma unroll 1
-      for (int i = 0; i < 3; ++i)
-#pragma unroll 1
-        for (int jj = 0; jj < 3; ++jj)
-#pragma unroll 1
-          for (int k = 0; k < 3; ++k) {
-            float w = pick(st.w0, st.w1, st.w2, i, 0) * pick(st.w0, st.w1, st.w2, jj, 1) * pick(st.w0, st.w1, st.w2, k, 2);
-            V3 h = h0 + H0 * (float)i + H1 * (float)jj + H2 * (float)k;
-            red_add_v4(ggrid_v + goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, w * h.x, w * h.y, w * h.z, 0.f);
-          }
-    }
     if (!in_tile) gxs = vzero();
-    if (act && !in_tile) {
-      tx = st.bx - cg.ox; ty = st.by - cg.oy; tz = st.bz - cg.oz;
+    if (act && !in_tile) {  // left the tile since the last sort (rare): gather from the grid, rolled
 #pragma unroll 1
       for (int i = 0; i < 3; ++i)
 #pragma unroll 1
@@ -1200,17 +1231,15 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
 #pragma unroll 1
           for (int k = 0; k < 3; ++k) {
             float wxi = pick(st.w0, st.w1, st.w2, i, 0), wyj = pick(st.w0, st.w1, st.w2, jj, 1), wzk = pick(st.w0, st.w1, st.w2, k, 2);
-            float w = wxi * wyj * wzk;
             V3 h = h0 + H0 * (float)i + H1 * (float)jj + H2 * (float)k;
-            size_t node = goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k;
-            float4 t = GATHER ? __ldg(grid_v + node) : make_float4(0.f, 0.f, 0.f, 0.f);
-            red_add_v4(ggrid_v + node, w * h.x, w * h.y, w * h.z, 0.f);
+            float4 t = __ldg(grid_v + goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k);
             float qn = t.x * h.x + t.y * h.y + t.z * h.z;
             gxs += v3(pick(d0, d1, d2, i, 0) * wyj * wzk, wxi * pick(d0, d1, d2, jj, 1) * wzk, wxi * wyj * pick(d0, d1, d2, k, 2)) * qn;
           }
     }
-    gx += gxs - (kp.inv_dx * s4) * mul_t(g.C, v3(n0.w, n1.x, n1.y));  // sum_n w_n v_n is the velocity g2p stored in the next slot
-    if (GATHER && act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
+    dq.push(act && !mine, p, lane, flush_queue);
+    V3 gx = in.gx + gxs - (kp.inv_dx * s4) * mul_t(in.gC, in.nvel);  // sum_n w_n v_n is the velocity g2p stored in the next slot
+    if (act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
   }
   __syncwarp();
   for (int n = lane; n < kTileN; n += 32) {
@@ -1222,160 +1251,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, GATHER ? DD_LB_G2PG_TILE : DD
   }
   __syncwarp();
   }
-  chunks_done(sched, lane);
-}
-
-// g2p_grad with ONE tile per warp, in two passes over the chunk (DD_G2PG_MODE=2).  Pass 1 fills the tile with the grid
-// velocities and does the gather half (read-only tile: no ordering constraints between the 27 loads) and writes the partial
-// dL/dx; pass 2 zeroes the same tile and does the scatter of the node adjoints.  The rows are staged twice (the second time
-// from L2), but a warp needs 11.5 KB of shared memory instead of 19.5 KB: 19 instead of 11 warps per SM for a kernel whose
-// time is latency, not throughput.
-#ifndef DD_LB_G2PG2
-#define DD_LB_G2PG2 18
-#endif
-__global__ void __launch_bounds__(32, DD_LB_G2PG2) k_g2p_grad_tile2(KP kp, SegView sg, const float *__restrict__ cur, const float *__restrict__ nxt,
-                                                                   const float4 *__restrict__ grid_v, const float *__restrict__ gin, float *__restrict__ gout,
-                                                                   float4 *__restrict__ ggrid_v, int *sched) {
-  extern __shared__ float4 dd_smem[];
-  const int lane = threadIdx.x & 31;
-  constexpr int kStage = kStageG2PG;
-  float4 *tile = dd_smem, *stage = tile + kTileN + lane;
-  const unsigned gbase = smem_u32(tile);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int nchunks = sg.cnt[0];
-  const int4 *__restrict__ chunks = sg.chunks;
-  const V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
-  const float lo = kp.gh * kp.dx, s4 = kp.inv_dx * 4.f;
-  auto stage_row = [&](int p) {
-    cp_async16(stage, plane4(cur, kp.EN, 0) + p);
-    cp_async16(stage + 32, plane4(nxt, kp.EN, 0) + p);
-    cp_async16(stage + 64, plane4(nxt, kp.EN, 1) + p);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cp_async16(stage + 96 + 32 * k, plane4(gin, kp.EN, k) + p);
-    cp_async_commit();
-  };
-  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
-    ChunkGeom cg = chunk_geom(chunks[ci], kp);
-    size_t goff = (size_t)cg.env * kp.G;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      stage_row(row_pos(cg, 0, lane));
-      if (pass == 0) fill_tile(tile, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane);
-      else for (int n = lane; n < kTileN; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-      __syncwarp();
-      for (int j = 0; j < cg.R; ++j) {
-        bool act = lane_on(cg, j, lane);
-        int p = row_pos(cg, j, lane);
-        cp_async_wait_all();
-        float4 a = stage[0], n0 = stage[32], n1 = stage[64], g0_ = stage[96], g1_ = stage[128], g2_ = stage[160], g3_ = stage[192];
-        if (j + 1 < cg.R) stage_row(row_pos(cg, j + 1, lane));
-        V3 x = v3(a.x, a.y, a.z);
-        M3 gC = m3(g1_.z, g1_.w, g2_.x, g2_.y, g2_.z, g2_.w, g3_.x, g3_.y, g3_.z);
-        V3 gx = v3(g0_.x, g0_.y, g0_.z), gnv = v3(g0_.w, g1_.x, g1_.y), nvel = v3(n0.w, n1.x, n1.y);
-        V3 nx = x + nvel * kp.dt;
-        if (nx.x > hi.x || nx.x < lo) gx.x = 0;
-        if (nx.y > hi.y || nx.y < lo) gx.y = 0;
-        if (nx.z > hi.z || nx.z < lo) gx.z = 0;
-        gnv += gx * kp.dt;
-        Stencil st = make_stencil_safe(x, kp);
-        float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
-        V3 H0 = v3(gC.a00, gC.a10, gC.a20) * s4, H1 = v3(gC.a01, gC.a11, gC.a21) * s4, H2 = v3(gC.a02, gC.a12, gC.a22) * s4;
-        V3 h0 = gnv - (H0 * st.fx.x + H1 * st.fx.y + H2 * st.fx.z);
-        int tx = st.bx - cg.ox, ty = st.by - cg.oy, tz = st.bz - cg.oz;
-        bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
-        if (pass == 0) {
-          // ---- gather: dL/dx = gx' (masked) - (4/dx^2) gC'^T v' + sum gradN_n (v_n . h_n), per (i,j) row in separable form
-          V3 d0, d1, d2;
-          stencil_dw(st, kp.inv_dx, d0, d1, d2);
-          float ex[3] = {d0.x, d1.x, d2.x}, ey[3] = {d0.y, d1.y, d2.y}, ez[3] = {d0.z, d1.z, d2.z};
-          V3 gxs = vzero();
-          auto rowsum = [&](int i, int jj, float4 t0, float4 t1, float4 t2) {
-            V3 hij = step_n(step_n(h0, H0, i), H1, jj), hk1 = hij + H2, hk2 = hk1 + H2;
-            float q0 = t0.x * hij.x + t0.y * hij.y + t0.z * hij.z, q1 = t1.x * hk1.x + t1.y * hk1.y + t1.z * hk1.z, q2 = t2.x * hk2.x + t2.y * hk2.y + t2.z * hk2.z;
-            float Sq = fmaf(wz[2], q2, fmaf(wz[1], q1, wz[0] * q0)), SEq = fmaf(ez[2], q2, fmaf(ez[1], q1, ez[0] * q0));
-            gxs.x = fmaf(ex[i] * wy[jj], Sq, gxs.x); gxs.y = fmaf(wx[i] * ey[jj], Sq, gxs.y); gxs.z = fmaf(wx[i] * wy[jj], SEq, gxs.z);
-          };
-          if (in_tile) {
-            const float4 *trow = tile + (tx << 6 | ty << 3);
-            int g0 = tz + 4 * ty + 2 * tx;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int jj = 0; jj < 3; ++jj) {
-                const float4 *r_ = trow + (i << 6 | jj << 3);
-                int g = g0 + 2 * i + 4 * jj;
-                rowsum(i, jj, r_[g & 7], r_[(g + 1) & 7], r_[(g + 2) & 7]);
-              }
-          } else if (act) {
-            const float4 *gg = grid_v + goff + (st.bx * kp.gy + st.by) * kp.gz + st.bz;
-#pragma unroll 1
-            for (int i = 0; i < 3; ++i)
-#pragma unroll 1
-              for (int jj = 0; jj < 3; ++jj) {
-                const float4 *r_ = gg + (i * kp.gy + jj) * kp.gz;
-                // (rolled: weights picked at run time)
-                float wxi = pick(st.w0, st.w1, st.w2, i, 0), wyj = pick(st.w0, st.w1, st.w2, jj, 1), exi = pick(d0, d1, d2, i, 0), eyj = pick(d0, d1, d2, jj, 1);
-                float4 t0 = __ldg(r_), t1 = __ldg(r_ + 1), t2 = __ldg(r_ + 2);
-                V3 hij = h0 + H0 * (float)i + H1 * (float)jj, hk1 = hij + H2, hk2 = hk1 + H2;
-                float q0 = t0.x * hij.x + t0.y * hij.y + t0.z * hij.z, q1 = t1.x * hk1.x + t1.y * hk1.y + t1.z * hk1.z, q2 = t2.x * hk2.x + t2.y * hk2.y + t2.z * hk2.z;
-                float Sq = fmaf(wz[2], q2, fmaf(wz[1], q1, wz[0] * q0)), SEq = fmaf(ez[2], q2, fmaf(ez[1], q1, ez[0] * q0));
-                gxs.x = fmaf(exi * wyj, Sq, gxs.x); gxs.y = fmaf(wxi * eyj, Sq, gxs.y); gxs.z = fmaf(wxi * wyj, SEq, gxs.z);
-              }
-          }
-          gx += gxs - (kp.inv_dx * s4) * mul_t(gC, nvel);  // sum_n w_n v_n is the velocity g2p stored in the next slot
-          if (act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
-        } else {
-          // ---- scatter of w_n h_n into the tile; lanes sharing a cell with a lower lane of this row go straight to the grid
-          unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
-          unsigned peers = __match_any_sync(0xffffffffu, key);
-          bool mine = in_tile && __popc(peers & ((1u << lane) - 1u)) == 0;
-          int txs = in_tile ? tx : 0, tys = in_tile ? ty : 0, tzs = in_tile ? tz : 0;
-          unsigned growb = gbase + 16u * (unsigned)(txs << 6 | tys << 3);
-          int g0 = tzs + 4 * tys + 2 * txs;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            V3 hi_ = step_n(h0, H0, i);
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) {
-              V3 hij = step_n(hi_, H1, jj);
-              float wij = wx[i] * wy[jj];
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                V3 h = step_n(hij, H2, k);
-                float w = wij * wz[k];
-                unsigned ga = growb + 16u * (unsigned)((i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7));
-                float4 o = lds_v4(ga);
-                o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
-                sts_v4_if(ga, o, mine);
-              }
-            }
-          }
-          if (act && !mine) {  // shares its cell with a lower lane, or left the tile since the last sort (rolled, rare)
-#pragma unroll 1
-            for (int i = 0; i < 3; ++i)
-#pragma unroll 1
-              for (int jj = 0; jj < 3; ++jj)
-#pragma unroll 1
-                for (int k = 0; k < 3; ++k) {
-                  float w = pick(st.w0, st.w1, st.w2, i, 0) * pick(st.w0, st.w1, st.w2, jj, 1) * pick(st.w0, st.w1, st.w2, k, 2);
-                  V3 h = h0 + H0 * (float)i + H1 * (float)jj + H2 * (float)k;
-                  red_add_v4(ggrid_v + goff + ((st.bx + i) * kp.gy + st.by + jj) * kp.gz + st.bz + k, w * h.x, w * h.y, w * h.z, 0.f);
-                }
-          }
-        }
-      }
-      __syncwarp();
-    }
-    for (int n = lane; n < kTileN; n += 32) {
-      int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
-      float4 t = tile[tile_slot(txx, tyy, tzz)];
-      int nx = cg.ox + txx, ny = cg.oy + tyy, nz = cg.oz + tzz;
-      if ((t.x != 0.f || t.y != 0.f || t.z != 0.f) && (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz)
-        red_add_v4(ggrid_v + goff + (nx * kp.gy + ny) * kp.gz + nz, t.x, t.y, t.z, 0.f);
-    }
-    __syncwarp();
-  }
+  flush_queue();
   chunks_done(sched, lane);
 }
 
@@ -1407,15 +1283,15 @@ struct P2ggStager {
   DD_DEV void phase2_done() const { if (p_next >= 0) stage2(p_next); }
 };
 
-template <int SVD, bool G2PG>
+template <int SVD>
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_tile(KP kp, SegView sg, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ mat0,
-                                                                      const float *__restrict__ yield, const float4 *__restrict__ ggrid, const float4 *__restrict__ grid_v,
+                                                                      const float *__restrict__ yield, const float4 *__restrict__ ggrid,
                                                                       const float *__restrict__ gin, float *__restrict__ gout, int *sched) {
   extern __shared__ float4 dd_smem[];
-  constexpr bool STAGED = SVD == 1 && !G2PG;
+  constexpr bool STAGED = SVD == 1;
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tile = dd_smem + warp * ((G2PG ? 2 : 1) * kTileN + (STAGED ? kStageP2GG * 32 : 0)), *tile_v = tile + kTileN;
+  float4 *tile = dd_smem + warp * (kTileN + (STAGED ? kStageP2GG * 32 : 0));
   P2ggStager stager{kp, cur, nxt, gin, yield, mat0, gout, tile + kTileN + lane, -1};
   pdl_launch_dependents();
   pdl_wait();
@@ -1425,7 +1301,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
     ChunkGeom cg = chunk_geom(chunks[ci], kp);
     if (STAGED) { int p0 = row_pos(cg, 0, lane); stager.stage1(p0); stager.stage2(p0); }
     fill_tile(tile, ggrid + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
-    if (G2PG) fill_tile(tile_v, grid_v + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
     __syncwarp();
     for (int j = 0; j < cg.R; ++j) {
       if (STAGED) {
@@ -1433,11 +1308,11 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
         bool act = lane_on(cg, j, lane);
         stager.p_next = j + 1 < cg.R ? row_pos(cg, j + 1, lane) : -1;
         cp_async_wait_all();
-        if (act) p2g_grad_particle<SVD, true, G2PG, P2ggStager>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, tile_v, grid_v, stager.stg, stager);
+        if (act) p2g_grad_particle<SVD, true, P2ggStager>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, stager.stg, stager);
         else { stager.phase1_done(); stager.phase2_done(); }
       } else {
         if (!lane_on(cg, j, lane)) continue;
-        p2g_grad_particle<SVD, true, G2PG>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout, tile_v, grid_v);
+        p2g_grad_particle<SVD, true>(kp, row_pos(cg, j, lane), cur, nxt, mat0, yield, ggrid, tile, cg.ox, cg.oy, cg.oz, gin, gout);
       }
     }
     __syncwarp();
@@ -2023,12 +1898,11 @@ struct dd_sim {
   int sms = 1;
   bool pdl = false;          // programmatic dependent launch between the hot kernels (DD_PDL=1; measured: no gain inside CUDA graphs, -2 % at config D)
   int pb_p2g = 0, pb_g2pg = 0, pb_g2p = 0, pb_p2gg = 0;
-  int g2pg_mode = 1, pb_g2pg2 = 0;  // 1: two tiles per warp, one pass; 2: one tile, two passes (k_g2p_grad_tile2)
-  bool g2p_tiled = false, p2gg_tiled = false, fuse_gather = false;  // fuse_gather: gather half of the g2p adjoint inside k_p2g_grad_tile
+  bool g2p_tiled = false, p2gg_tiled = false;
   int w_p2g = 4, w_g2pg = 1, w_g2p = 4, w_p2gg = 4;  // warps per block (the warps of a block are independent; this only sets the shared-memory granularity)
   // upper-bound grids: the live counts are read on the device
   int tile_blocks(int per_device, int wpb) const { return std::max(1, std::min((chunk_cap + wpb - 1) / wpb, per_device)); }
-  int brick_blocks() const { return std::max(1, std::min((NBtot + 3) / 4, sms * 16)); }
+  int brick_blocks() const { return std::max(1, std::min((NBtot + 3) / 4, sms * 32)); }  // (one resident wave striding over the list measured slower: E=64, grid_grad_b 70 -> 119 us)
 
   // ---- logical state f <-> segment and physical slot
   int seg_of(int f) const { return L > 0 ? std::min(f / L, nseg - 1) : 0; }          // segment in which state f is the INPUT of a substep
@@ -2080,12 +1954,12 @@ void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk =
   if (s->cfg.tile_mode) {
     // invariant: the scatter target of substep f is already zero on the active bricks (cleared by the previous grid
     // kernel, or by dd_sim_forward for the first substep of a range; bricks activated on the fly clear themselves)
-    launch_hot(s, k_p2g_tile<SVD, true>, s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->G(f), s->counters + 4);
+    launch_hot(s, k_p2g_tile<SVD, true>, s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * kSmemP2G, st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->G(f), s->counters + 4);
     mark(mk, "p2g_tile (svd+return map+scatter)");
     float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
     launch_hot(s, k_grid_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_b (grid update + contact)");
-    if (s->g2p_tiled) launch_hot(s, k_g2p_tile, s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * kTileN * sizeof(float4), st, kp, sg.view(), cur, nxt, s->GV(f), s->counters + 4);
+    if (s->g2p_tiled) launch_hot(s, k_g2p_tile, s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * kSmemG2P, st, kp, sg.view(), cur, nxt, s->GV(f), s->counters + 4);
     else k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, cur, nxt, s->GV(f));
     mark(mk, "g2p");
   } else {
@@ -2107,17 +1981,14 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
   if (s->cfg.tile_mode) {
     // invariant: ggrid_v is zero on the active bricks (k_grid_grad_b clears what it consumes)
     if (!s->grid_ckpt) {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
-      launch_hot(s, k_p2g_tile<SVD, false>, s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * (kTileN + kStageP2G * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->grid, s->counters + 4);
+      launch_hot(s, k_p2g_tile<SVD, false>, s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * kSmemP2G, st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->grid, s->counters + 4);
       launch_hot(s, k_grid_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
     }
-    if (s->g2pg_mode == 2 && !s->fuse_gather) launch_hot(s, k_g2p_grad_tile2, s->tile_blocks(s->pb_g2pg2, 1), 32, (kTileN + kStageG2PG * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
-    else if (s->fuse_gather) launch_hot(s, k_g2p_grad_tile<false>, s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (kTileN + kStageG2PG * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
-    else launch_hot(s, k_g2p_grad_tile<true>, s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * (2 * kTileN + kStageG2PG * 32) * sizeof(float4), st, kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
+    launch_hot(s, k_g2p_grad_tile, s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * kSmemG2PG, st, kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
     mark(mk, "g2p_grad_tile");
     launch_hot(s, k_grid_grad_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
     mark(mk, "grid_grad_b");
-    if (s->fuse_gather) launch_hot(s, k_p2g_grad_tile<SVD, true>, s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * 2 * kTileN * sizeof(float4), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, s->GV(f), gin, gout, s->counters + 4);
-    else if (s->p2gg_tiled) launch_hot(s, k_p2g_grad_tile<SVD, false>, s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * (kTileN + (SVD == 1 ? kStageP2GG * 32 : 0)) * sizeof(float4), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, nullptr, gin, gout, s->counters + 4);
+    if (s->p2gg_tiled) launch_hot(s, k_p2g_grad_tile<SVD>, s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * (SVD == 1 ? kSmemP2GG : kSmemG2P), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, gin, gout, s->counters + 4);
     else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, cur, nxt, sg.mat0, sg.yield, s->ggrid, gin, gout);
     mark(mk, "p2g_grad (+svd adjoint)");
   } else {
@@ -2367,18 +2238,16 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
     if ((kp.gx | kp.gy | kp.gz) & 3) { dd_sim_destroy(s); return fail("dd_sim_create: tile_mode needs grid dimensions that are multiples of 4"); }
     s->NBtot = kp.E * (kp.gx >> 2) * (kp.gy >> 2) * (kp.gz >> 2);
     {
-      int big = 8 * (kTileN + kStageP2G * 32) * (int)sizeof(float4), big2 = std::min(8 * (2 * kTileN + kStageG2PG * 32) * (int)sizeof(float4), 227 * 1024);
-      cudaFuncSetAttribute(k_g2p_grad_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big2);
-      cudaFuncSetAttribute(k_g2p_grad_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_g2p_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_grad_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-      cudaFuncSetAttribute(k_p2g_grad_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(8 * (kTileN + kStageP2GG * 32) * (int)sizeof(float4), 227 * 1024));
-      cudaFuncSetAttribute(k_p2g_grad_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * big);
-      cudaFuncSetAttribute(k_p2g_grad_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * big);
+      const int cap = 227 * 1024;
+      auto up_to = [&](size_t per_warp) { return (int)std::min<size_t>(8 * per_warp, (size_t)cap); };
+      cudaFuncSetAttribute(k_g2p_grad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, up_to(kSmemG2PG));
+      cudaFuncSetAttribute(k_g2p_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, up_to(kSmemG2P));
+      cudaFuncSetAttribute(k_p2g_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, up_to(kSmemP2G));
+      cudaFuncSetAttribute(k_p2g_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, up_to(kSmemP2G));
+      cudaFuncSetAttribute(k_p2g_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, up_to(kSmemP2G));
+      cudaFuncSetAttribute(k_p2g_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, up_to(kSmemP2G));
+      cudaFuncSetAttribute(k_p2g_grad_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, up_to(kSmemG2P));
+      cudaFuncSetAttribute(k_p2g_grad_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, up_to(kSmemP2GG));
     }
     {
       int dev = 0, occ = 1;
@@ -2387,28 +2256,13 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
       const int sms = s->sms;
       auto knob = [](const char *name, int dflt) { const char *e = getenv(name); int v = e ? atoi(e) : dflt; return v >= 1 && v <= 8 ? v : dflt; };
       s->w_p2g = knob("DD_WPB_P2G", s->w_p2g); s->w_g2pg = knob("DD_WPB_G2PG", s->w_g2pg); s->w_g2p = knob("DD_WPB_G2P", s->w_g2p); s->w_p2gg = knob("DD_WPB_P2GG", s->w_p2gg);
-      size_t one = kTileN * sizeof(float4), two = (2 * kTileN + kStageG2PG * 32) * sizeof(float4), one_p2g = (kTileN + kStageP2G * 32) * sizeof(float4), one_g2p = kTileN * sizeof(float4);
       auto per_device = [&](auto kernel, int wpb, size_t smem) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * wpb, smem * wpb); return std::max(occ, 1) * sms; };
       const char *e0 = getenv("DD_PDL");
       s->pdl = e0 && atoi(e0) != 0;
-      const char *e3 = getenv("DD_FUSE_GATHER");
-      s->fuse_gather = e3 && atoi(e3) != 0;  // default off: measured slower at config D (p2g_grad_tile loses more than g2p_grad_tile gains)
-      if (cfg->svd_mode == 0) s->pb_p2g = per_device(k_p2g_tile<0, true>, s->w_p2g, one_p2g); else s->pb_p2g = per_device(k_p2g_tile<1, true>, s->w_p2g, one_p2g);
-      if (s->fuse_gather) {
-        s->pb_p2gg = cfg->svd_mode == 0 ? per_device(k_p2g_grad_tile<0, true>, s->w_p2gg, 2 * one) : per_device(k_p2g_grad_tile<1, true>, s->w_p2gg, 2 * one);
-        s->pb_g2pg = per_device(k_g2p_grad_tile<false>, s->w_g2pg, one + kStageG2PG * 32 * sizeof(float4));
-      } else {
-        s->pb_p2gg = cfg->svd_mode == 0 ? per_device(k_p2g_grad_tile<0, false>, s->w_p2gg, one) : per_device(k_p2g_grad_tile<1, false>, s->w_p2gg, one + kStageP2GG * 32 * sizeof(float4));
-        s->pb_g2pg = per_device(k_g2p_grad_tile<true>, s->w_g2pg, two);
-      }
-      s->pb_g2p = per_device(k_g2p_tile, s->w_g2p, one_g2p);
-      {
-        const char *e4 = getenv("DD_G2PG_MODE");
-        s->g2pg_mode = e4 ? atoi(e4) : 1;
-        size_t sm2 = (kTileN + kStageG2PG * 32) * sizeof(float4);
-        cudaFuncSetAttribute(k_g2p_grad_tile2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-        s->pb_g2pg2 = per_device(k_g2p_grad_tile2, 1, sm2);
-      }
+      if (cfg->svd_mode == 0) s->pb_p2g = per_device(k_p2g_tile<0, true>, s->w_p2g, kSmemP2G); else s->pb_p2g = per_device(k_p2g_tile<1, true>, s->w_p2g, kSmemP2G);
+      s->pb_p2gg = cfg->svd_mode == 0 ? per_device(k_p2g_grad_tile<0>, s->w_p2gg, kSmemG2P) : per_device(k_p2g_grad_tile<1>, s->w_p2gg, kSmemP2GG);
+      s->pb_g2pg = per_device(k_g2p_grad_tile, s->w_g2pg, kSmemG2PG);
+      s->pb_g2p = per_device(k_g2p_tile, s->w_g2p, kSmemG2P);
       const char *e1 = getenv("DD_G2P_TILE"), *e2 = getenv("DD_P2GG_TILE");
       s->g2p_tiled = !(e1 && atoi(e1) == 0);  // default: tiled gather
       s->p2gg_tiled = e2 ? atoi(e2) != 0 : cfg->svd_mode == 1;  // default: the staged tile kernel with the fp32 SVD, the flat kernel otherwise

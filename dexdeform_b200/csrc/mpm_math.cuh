@@ -44,11 +44,23 @@ DD_DEV M3 operator*(float s, M3 a) { return a * s; }
 DD_DEV void operator+=(M3 &a, M3 b) { a = a + b; }
 // elementwise product (mat3.h:117-129)
 DD_DEV M3 hadamard(M3 a, M3 b) { return m3(a.a00 * b.a00, a.a01 * b.a01, a.a02 * b.a02, a.a10 * b.a10, a.a11 * b.a11, a.a12 * b.a12, a.a20 * b.a20, a.a21 * b.a21, a.a22 * b.a22); }
-// matrix product, k accumulated 0,1,2 (mat3.h:86-96)
+// Packed fp32 pairs (sm_100): one FFMA2 / FMUL2 instruction works on an aligned register pair, and either multiplicand may be
+// a single register broadcast to both halves -- "scalar times row" costs two issue slots instead of three for a 3-vector.
+// Each half is an ordinary IEEE fma / mul, so results equal the scalar formulation with the same association.
+DD_DEV float2 pk(float a, float b) { return make_float2(a, b); }
+DD_DEV float2 fma2(float s, float2 v, float2 acc) { return __ffma2_rn(make_float2(s, s), v, acc); }
+DD_DEV float2 fma2(float2 a, float2 b, float2 acc) { return __ffma2_rn(a, b, acc); }
+DD_DEV float2 mul2(float s, float2 v) { return __fmul2_rn(make_float2(s, s), v); }
+DD_DEV float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+// matrix product, k accumulated 0,1,2 (mat3.h:86-96); columns 0,1 of every row as one packed pair
 DD_DEV M3 mul(M3 a, M3 b) {
-  return m3(a.a00 * b.a00 + a.a01 * b.a10 + a.a02 * b.a20, a.a00 * b.a01 + a.a01 * b.a11 + a.a02 * b.a21, a.a00 * b.a02 + a.a01 * b.a12 + a.a02 * b.a22,
-            a.a10 * b.a00 + a.a11 * b.a10 + a.a12 * b.a20, a.a10 * b.a01 + a.a11 * b.a11 + a.a12 * b.a21, a.a10 * b.a02 + a.a11 * b.a12 + a.a12 * b.a22,
-            a.a20 * b.a00 + a.a21 * b.a10 + a.a22 * b.a20, a.a20 * b.a01 + a.a21 * b.a11 + a.a22 * b.a21, a.a20 * b.a02 + a.a21 * b.a12 + a.a22 * b.a22);
+  float2 b0 = pk(b.a00, b.a01), b1 = pk(b.a10, b.a11), b2 = pk(b.a20, b.a21);
+  float2 r0 = fma2(a.a02, b2, fma2(a.a01, b1, mul2(a.a00, b0)));
+  float2 r1 = fma2(a.a12, b2, fma2(a.a11, b1, mul2(a.a10, b0)));
+  float2 r2 = fma2(a.a22, b2, fma2(a.a21, b1, mul2(a.a20, b0)));
+  return m3(r0.x, r0.y, fmaf(a.a02, b.a22, fmaf(a.a01, b.a12, a.a00 * b.a02)),
+            r1.x, r1.y, fmaf(a.a12, b.a22, fmaf(a.a11, b.a12, a.a10 * b.a02)),
+            r2.x, r2.y, fmaf(a.a22, b.a22, fmaf(a.a21, b.a12, a.a20 * b.a02)));
 }
 // a * b^T and a^T * b without materialising the transpose
 DD_DEV M3 mul_nt(M3 a, M3 b) { return mul(a, transpose(b)); }

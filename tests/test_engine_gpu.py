@@ -305,12 +305,11 @@ def test_recompute_mode_matches_checkpoint_mode():
     assert a["launches"] == 6 * S + 1 and b["launches"] == 8 * S + 1
 
 
-@pytest.mark.parametrize("g2pg_mode", [1, 2])
 @pytest.mark.parametrize("n,E,chunk_max", [(4, 1, 32), (36, 2, 32), (1000, 3, 32), (5000, 1, 96), (5000, 2, 0)])
-def test_tiled_rows_small_ragged_and_short_chunks(n, E, chunk_max, g2pg_mode, monkeypatch):
-    """Row tables with one short row, chunks much smaller than a brick (many spills into foreign columns), several
-    environments: the production tile path (fp32 SVD, staged kernels, ticket scheduling) against the dense path."""
-    monkeypatch.setenv("DD_G2PG_MODE", str(g2pg_mode))   # both variants of the g2p adjoint (two tiles / one tile in two passes)
+def test_tiled_rows_small_ragged_and_short_chunks(n, E, chunk_max):
+    """Row tables with one short row, chunks much smaller than a brick (many spills into foreign columns, many lanes that
+    share a cell within a row and go through the deferred-lane queue), several environments: the production tile path
+    (fp32 SVD, staged kernels, ticket scheduling) against the dense path."""
     S = 4
     w = 0.05 + 0.1 * min(1.0, n / 5000.0)
     sc = make_scene(n, 32, box_center=(0.5, 0.3, 0.5), box_width=(w, w, w), steps=S, perturb=0.02, vel_scale=0.5, on_floor=True, nb=4, seed=77)
