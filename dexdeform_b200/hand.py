@@ -13,6 +13,7 @@ import os
 import numpy as np
 import torch
 
+from .cuda_env import CudaEnv
 from .mujoco_parser import default_assets_dir, hand_tables, load_hand
 from .robots import ACTUATORS, DEFAULT_INITIAL_QPOS, JOINTS, N_ACTUATORS, N_JOINTS, actuator_of_joint, joint_limits
 from .rotations import axis_angle_to_matrix, euler2mat, matrix_to_quaternion, quaternion_to_matrix
@@ -21,6 +22,11 @@ from .shapes import Shapes
 from .simulator import MPMSimulator
 
 SUPPORTED_ENVS = ["folding", "rope", "bun", "dumpling", "wrap", "flip", "lift_box"]
+# primitive index ranges of the hands (hand.py:14-17): 19 collision primitives per hand, left hand first
+LH_PRIM_RANGE = list(range(0, 19))
+RH_PRIM_RANGE = list(range(19, 38))
+SINGLE_PRIM_RANGE = list(range(0, 19))
+DUAL_PRIM_RANGE = list(range(0, 38))
 
 
 def rigid_body_motion_hand(state, actions, T):
@@ -138,9 +144,11 @@ def read_poses(engine, f0, count):
 
 
 class HandSimulator(MPMSimulator):
-    def __init__(self, n_bodies, hand_cfg, cfg=None, quality=None, action_scale=None, device="cuda:0", mode=None, scale=None, ctrl_type=None,
+    def __init__(self, n_bodies, hand_cfg, cfg=None, quality=None, action_scale=None, device=None, mode=None, scale=None, ctrl_type=None,
                  hand_friction=None, fixed_base=False, **engine_kwargs):
         cfg = dict(cfg or {})
+        if device is None:  # the reference hard-codes cuda:0 (hand.py:74); one process per GPU uses its current device
+            device = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
         quality = cfg.get("quality", quality if quality is not None else 1)
         fixed_base = cfg.get("fixed_base", fixed_base)
         dt = 0.5e-4 / quality
@@ -191,6 +199,84 @@ class HandSimulator(MPMSimulator):
         pose = np.concatenate([pos[0].detach().cpu().numpy(), rot[0].detach().cpu().numpy()], 1)
         super().set_state(index, tuple(state[:4]) + tuple(pose))
 
+    # ---- renderer-facing state (hand.py:212-234); only positions and the kinematic state travel
+    def get_state_render_only(self, f=0, device="numpy"):
+        return self.get_x(f), self.base_pose[f].cpu().numpy(), self.joint_rot[f].cpu().numpy()
+
+    def set_state_render_only(self, p, base_pose, joint_rot, f=0):
+        base_pose = torch.tensor(np.asarray(base_pose), device=self.device, dtype=torch.float32)
+        joint_rot = torch.tensor(np.asarray(joint_rot), device=self.device, dtype=torch.float32)
+        pos, rot = self.hand_forward_kinematics(base_pose[None, :], joint_rot[None, :])
+        self.states[f].x.upload(p)
+        self.states[f].body_pos.upload(pos[0].detach().cpu().numpy())
+        self.states[f].body_rot.upload(rot[0].detach().cpu().numpy())
+
+    # ---- signed distances of arbitrary points to the hand primitives (hand.py:236-341; used by policy/preprocess)
+    def lh_sdf_given_p(self, p):
+        return self.primitive_sdf_given_p(p, LH_PRIM_RANGE)
+
+    def rh_sdf_given_p(self, p):
+        return self.primitive_sdf_given_p(p, RH_PRIM_RANGE)
+
+    def _dists_of_points(self, pts):
+        """(n_particles, nb) distances with state 0's particle positions replaced by `pts` (hand.py:248-252)."""
+        self.states[0].x.upload(pts)
+        return self.get_dists(f=0, device="numpy")
+
+    def primitive_sdf_given_p(self, p, hand_inds):
+        init_state = self.get_state(0)
+        num_points = len(p)
+        assert num_points <= self.n_particles
+        tmp_p = np.ones((self.n_particles, 3))
+        tmp_p[:num_points] = p[:num_points]
+        sdf_vals = self._dists_of_points(tmp_p)[:num_points, hand_inds].min(-1)
+        self.set_state(0, init_state)
+        return sdf_vals
+
+    def sample_pts_helper(self, num_points, hand_inds, center=None, hot_start=None):
+        """Rejection sampling of points inside the primitives `hand_inds` from the unit cube around `center` (hand.py:254-290)."""
+        points = np.ones((num_points, 3)) * 5
+        remain_cnt, started = num_points, False
+        while remain_cnt > 0:
+            p_samples = (np.random.random((self.n_particles, 3)) - 0.5) + center
+            if not started and hot_start is not None:
+                tmp_len = min(self.n_particles, len(hot_start))
+                p_samples[:tmp_len] = hot_start[:tmp_len]
+                started = True
+            accept_map = self._dists_of_points(p_samples)[:, hand_inds].min(-1) <= 0
+            accept_cnt = int(accept_map.sum())
+            start = num_points - remain_cnt
+            points[start:start + accept_cnt] = p_samples[accept_map][:min(accept_cnt, remain_cnt)]
+            remain_cnt -= accept_cnt
+        assert np.all(points != 5)
+        return points
+
+    def sample_pts_inside_primitives(self, n_pts, mode=None, hot_start=None):
+        """hand.py:292-341 -> (points, their distances to every primitive, hand labels)."""
+        init_state = self.get_state(0)
+        body_pos = self.states[0].body_pos.download()
+        if mode == "dual":
+            half = n_pts // 2
+            p1 = self.sample_pts_helper(half, LH_PRIM_RANGE, body_pos[LH_PRIM_RANGE, :].mean(0), hot_start)
+            p2 = self.sample_pts_helper(half, RH_PRIM_RANGE, body_pos[RH_PRIM_RANGE, :].mean(0), hot_start)
+            p = np.concatenate((p1, p2), axis=0)
+            labels = np.concatenate((np.zeros((len(p1), 1)), np.ones((len(p2), 1))), axis=0)
+        elif mode in ("lh", "rh"):
+            hand_inds = (LH_PRIM_RANGE if mode == "lh" else RH_PRIM_RANGE) if self.n_hands == 2 else SINGLE_PRIM_RANGE
+            p = self.sample_pts_helper(n_pts, hand_inds, body_pos[hand_inds, :].mean(0), hot_start)
+            labels = np.zeros((len(p), 0 if mode == "lh" else 1))  # (sic: hand.py:322 / 331)
+        else:
+            raise ValueError("Mode is not supported!")
+        num_valid = len(p)
+        p_samples = np.zeros(shape=(self.n_particles, 3))
+        p_samples[:num_valid] = p
+        p_sdf_vals = self._dists_of_points(p_samples)[:num_valid]
+        self.set_state(0, init_state)
+        return p, p_sdf_vals, labels
+
+    def mat2pos_rot(self, mat):
+        return mat[..., :3, 3], matrix_to_quaternion(mat[..., :3, :3])
+
     def JointVel_Fk(self, f, actions, pos_rot=None):
         """hand.py:383-428: action ([E,] nh, 26) -> poses of the S substeps + the end-of-step kinematic state."""
         curr_base, curr_q = (self.base_pose[f], self.joint_rot[f]) if pos_rot is None else pos_rot
@@ -238,34 +324,81 @@ def _parse_tuple(v):
     return eval(v, {"np": np}) if isinstance(v, str) else v
 
 
-class HandEnv:
+class HandEnv(CudaEnv):
     """hand.py:436-649 without the renderer: cfg (dict from the env YAML) -> particles, MJCF primitives, HandSimulator."""
 
-    def __init__(self, cfg, assets_dir=None, device="cuda:0", **engine_kwargs):
+    def __init__(self, cfg, MANIPULATORS=None, env_name=None, assets_dir=None, device=None, tables=None, **engine_kwargs):
+        """``tables``: pre-built kinematic tables (tests on machines without the MJCF assets); otherwise parsed from the assets."""
         self.cfg = cfg
+        self.assets_dir = assets_dir
+        d = self.describe(cfg, MANIPULATORS, tables)
+        self.fixed_base = d["fixed_base"]
+        self.particle_colors = np.zeros(d["n_particles"]) + 0xdf73ff
+        n_bodies, kwargs = self.parse_tools(d["primitives"])
+        kwargs.pop("pos"), kwargs.pop("rot")  # (the reference uploads the tool defaults first; the kinematics below overwrite them)
+        self.simulator = HandSimulator(n_bodies, d["hand_cfg"], cfg=d["sim_cfg"], device=device, **engine_kwargs)
+        self.simulator.init_bodies(**kwargs)
+        n = self.simulator.n_particles
+        # State buffers start as zeros (mpm/types.py:303-306); SHAPES fill the first len(objects) positions (hand.py:465-467)
+        x = np.zeros((n, 3), np.float32)
+        if d["objects"] is not None:
+            x[: len(d["objects"])] = d["objects"]
+        self.simulator.states[0].x.upload(x)
+        self.renderer = None
+        self.initialize(d["root_matrix"], d["joint_pos"])
+        self.init_state = self.simulator.get_state(0)
+
+    def describe(self, cfg, MANIPULATORS=None, tables=None):
+        """Everything hand.py:436-476 derives from the configuration before a simulator exists (no GPU needed): particle
+        positions of the SHAPES section, the simulator section with the final particle count, the tool entries of the hand's
+        collision primitives, the kinematic description, and the initial wrist frames / joint positions."""
         sim_cfg = dict(cfg["SIMULATOR"])
         objects = None
         if cfg.get("SHAPES"):
             objects, colors, _, mly = Shapes(cfg["SHAPES"]).get()
             sim_cfg["n_particles"] = max(int(sim_cfg.get("n_particles", 0)), len(objects))
-        mode, scale = sim_cfg.get("mode", "rh"), float(sim_cfg.get("scale", 1.0))
-        sides = {"lh": ["left_hand"], "rh": ["right_hand"], "dual": ["left_hand", "right_hand"], "lh+rh": ["left_hand", "right_hand"]}[mode]
-        models = [load_hand(s, scale, assets_dir) for s in sides]
-        tables = hand_tables(models)
-        nb = len(tables.prim_type)
-        self.simulator = HandSimulator(nb, {"tables": tables, "n_hands": len(sides)}, cfg=sim_cfg, device=device, **engine_kwargs)
-        friction = float(sim_cfg.get("hand_friction", 0.9))
-        # mpm/cuda_env.py:76-90: softness is hard-wired to 666, round 0
-        self.simulator.init_bodies(tables.prim_type.astype(np.float32), np.full(nb, 666.0, np.float32), np.full(nb, friction, np.float32),
-                                   np.zeros(nb, np.float32), tables.prim_size, action_scales=[()] * nb)
-        n = self.simulator.n_particles
-        x = np.random.random((n, 3)) * 0.2 + np.array((0.4, 0.1, 0.4))
-        if objects is not None:
-            x[: len(objects)] = objects
-        root, qpos = self.parse_manip_cfgs(cfg["MANIPULATORS"])
-        F = np.tile(np.eye(3, dtype=np.float32)[None], (n, 1, 1))
-        self.simulator.set_state(0, (np.float32(x), np.zeros((n, 3), np.float32), F, np.zeros((n, 3, 3), np.float32), np.float32(root), np.float32(qpos)))
-        self.init_state = self.simulator.get_state(0)
+        env_params = self.parse_sim_cfg(sim_cfg, tables)
+        root_matrix, joint_pos = self.parse_manip_cfgs(MANIPULATORS if MANIPULATORS is not None else cfg["MANIPULATORS"])
+        return {"sim_cfg": sim_cfg, "objects": objects, "n_particles": int(sim_cfg["n_particles"]), "fixed_base": sim_cfg.get("fixed_base", False),
+                "primitives": env_params["primitives"], "hand_cfg": env_params["hand_cfg"], "root_matrix": root_matrix, "joint_pos": joint_pos}
+
+    def initialize(self, root_frame=None, joint_pos=None):
+        """hand.py:478-489: F = I, the hands at their configured root frames / joint positions."""
+        state = list(self.simulator.get_state(0))
+        state[2] = np.tile(np.eye(3, dtype=np.float32)[None], (self.simulator.n_particles, 1, 1))
+        if root_frame is not None:
+            state[-2] = np.float32(np.broadcast_to(root_frame, state[-2].shape))
+        if joint_pos is not None:
+            state[-1] = np.float32(np.broadcast_to(joint_pos, state[-1].shape))
+        self.simulator.set_color(self.particle_colors)
+        self.simulator.set_state(0, tuple(state))
+
+    def set_particle_color(self, col):
+        self.particle_colors[:] = col
+        self.simulator.set_color(self.particle_colors)
+
+    def parse_sim_cfg(self, cfg, tables=None):
+        """hand.py:540-624: MJCF -> tool configs of the collision primitives (``primitives``) + kinematic description (``hand_cfg``)."""
+        mode, scale, hand_friction = cfg.get("mode", "rh"), float(cfg.get("scale", 1.0)), float(cfg.get("hand_friction", 0.9))
+        if mode in ("lh", "rh"):
+            sides = ["left_hand" if mode == "lh" else "right_hand"]
+        elif mode in ("dual", "lh+rh"):
+            sides = ["left_hand", "right_hand"]
+        else:
+            raise ValueError(f"incorrect hand mode: {mode}")
+        if tables is None:
+            tables = hand_tables([load_hand(s, scale, getattr(self, "assets_dir", None)) for s in sides])
+        assert tables.n_hands == len(sides)
+        primitives = []
+        for t, size in zip(tables.prim_type, tables.prim_size):
+            tool = self.default_tool_config()
+            tool["shape"] = "Capsule" if int(t) == 1 else "Box"
+            tool["size"] = tuple(float(v) for v in (size[:2] if int(t) == 1 else size[:3]))
+            tool["round"] = 0
+            tool["friction"] = hand_friction
+            primitives.append(tool)
+        hand_cfg = {"n_hands": len(sides), "tables": tables, "root_frame": tables.root_frame}
+        return {"primitives": primitives, "hand_cfg": hand_cfg}
 
     @staticmethod
     def get_root_matrix(pos, rot):
@@ -298,7 +431,19 @@ class HandEnv:
         if pos is not None and rot is not None:
             state[-2][hand_idx] = self.get_root_matrix(pos, rot)
         if joint_pos is not None:
+            assert self.simulator.n_joints_per_hand == len(joint_pos)
             state[-1][hand_idx] = joint_pos
+        self.simulator.set_state(0, tuple(state))
+
+    def set_dual_hand_pose(self, pos=None, rot=None, joint_pos=None):
+        """hand.py:640-649."""
+        state = list(self.simulator.get_state(0))
+        if pos is not None and rot is not None:
+            assert self.simulator.n_hands == len(pos) == len(rot) == 2
+            state[-2][:] = np.stack([self.get_root_matrix(p, r) for p, r in zip(pos, rot)], axis=0)
+        if joint_pos is not None:
+            assert self.simulator.n_hands == len(joint_pos) and self.simulator.n_joints_per_hand == len(joint_pos[0])
+            state[-1][:] = np.stack([x for x in joint_pos], axis=0)
         self.simulator.set_state(0, tuple(state))
 
 

@@ -167,6 +167,15 @@ class MPMSimulator:
         full = lambda a, shp: np.ascontiguousarray(np.broadcast_to(a, shp), np.float32)
         self.engine.set_material(full(mass, (E, n)), full(vol, (E, n)), full(mly, (E, n, 3)))
 
+    def set_color(self, inp):
+        """mpm/simulator.py:263-266: per-particle colours for the renderer (kept on the host; rendering is out of scope)."""
+        self.particle_color = np.zeros(self.n_particles, np.float64) if getattr(self, "particle_color", None) is None else self.particle_color
+        self.particle_color[:] = inp
+
+    def get_object_id(self, device="numpy"):
+        assert device == "numpy"
+        return self.object_id
+
     def set_object_id(self, object_id):
         self.object_id = np.ascontiguousarray(object_id, np.int32)
         assert self.object_id.shape[-1] == self.n_particles

@@ -31,7 +31,7 @@ class GradModel:
         self._set_pose_func = None
         self.return_grid = tuple(return_grid)
         self.return_svd = return_svd
-        self.device = "cuda:0"
+        self.device = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
         self._frontier = None  # state index whose gradient slot currently holds a valid gradient
         self.pos_rot = None
 

@@ -180,3 +180,182 @@ def test_hand_simulator_step_and_gradmodel():
     loss = obs[0][:, 1].mean() + 0.1 * obs[0][:, 6:].mean()
     loss.backward()
     assert torch.isfinite(a.grad).all() and a.grad.abs().sum() > 0
+
+
+# ---- pinned against the reference's own parser and kinematics code (tests/golden/make_hand_ref.py ran mpm/mujoco_parser.py and
+# ---- mpm/hand.py from the checkout; only the pytorch3d / transforms3d conversions were stand-ins)
+REF_FIX = os.path.join(ROOT, "tests", "golden", "shadow_ref.npz")
+
+
+def ref_case(tag):
+    z = np.load(REF_FIX)
+    return {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith(tag + ".")}
+
+
+@pytest.mark.parametrize("tag", ["rh15", "rh25", "dual15"])
+def test_tables_equal_reference_parser(tag):
+    t, r = tables(tag), ref_case(tag)
+    nh = int(r["n_hands"])
+    assert t.n_hands == nh
+    assert np.array_equal(t.prim_type, r["prim_type"])                                   # order and kind of the 19 / 38 primitives
+    assert np.allclose(t.prim_size, r["prim_args"], rtol=0, atol=1e-7)                   # args as cuda_env.parse_tools passes them
+    assert np.allclose(t.root_frame, r["root_frame"], atol=1e-6)
+    assert np.allclose(t.joint_pos, r["joint_pos"], atol=1e-7) and np.allclose(t.joint_axis, r["joint_axis"], atol=1e-7)
+    assert np.array_equal(np.asarray(t.geom_joint), r["geom_index"])
+    assert np.allclose(np.asarray(t.geom_local).reshape(r["geometries"].shape), r["geometries"], atol=1e-6)   # incl. the capsule Rx(90 deg) fix-up
+    lim = joint_limits()
+    assert np.allclose(lim[:, 0], r["q_lower"], atol=1e-7) and np.allclose(lim[:, 1], r["q_upper"], atol=1e-7)
+    assert np.array_equal(actuator_of_joint(), r["action_map"])
+
+
+@pytest.mark.parametrize("tag,fixed_base", [("rh15", False), ("rh25", True), ("dual15", False)])
+def test_torch_fk_equals_reference_fk(tag, fixed_base):
+    """One env step of joint-velocity control (hand.py:383-428) and the rest pose: our tables + FK against poses computed by the
+    reference's HandSimulator code."""
+    from dexdeform_b200.robots import DEFAULT_INITIAL_QPOS
+    t, r = tables(tag), ref_case(tag)
+    kin = HandKinematics(t)
+    S = int(r["substeps"])
+    sc = torch.tensor(r["action_scale"])
+    base, q0, act = torch.tensor(r["in_base"]), torch.tensor(r["in_q"]), torch.tensor(r["in_action"])
+    assert np.allclose(sc.numpy(), [0.33 * 0.002] * 20 + ([0.0] * 6 if fixed_base else [0.01] * 3 + [0.015] * 3))
+    nbase = rigid_body_motion_hand(base, act[:, -6:] * sc[None, -6:], S)
+    a = (act[:, :20].clamp(-1, 1) * sc[None, :20])[:, kin.action_map]
+    nq = (q0[None] + a[None] * (torch.arange(S)[:, None, None] + 1)).clamp(kin.q_lower, kin.q_upper)
+    pos, rot = kin.forward(nbase, nq)
+    assert np.allclose(pos.numpy(), r["out_pos"], atol=2e-6), np.abs(pos.numpy() - r["out_pos"]).max()
+    sign = np.sign((rot.numpy() * r["out_rot"]).sum(-1, keepdims=True))
+    assert np.allclose(rot.numpy() * sign, r["out_rot"], atol=5e-6)
+    assert np.allclose(nbase[-1].numpy(), r["out_base"], atol=2e-6) and np.allclose(nq[-1].numpy(), r["out_q"], atol=1e-7)
+    q_def = torch.tensor([DEFAULT_INITIAL_QPOS[j] for j in JOINTS], dtype=torch.float32)[None].expand(t.n_hands, -1)
+    assert np.allclose(q_def.numpy(), r["default_qpos"])
+    p0, r0 = kin.forward(torch.tensor(t.root_frame, dtype=torch.float32)[None], q_def[None])
+    assert np.allclose(p0.numpy(), r["rest_pos"], atol=2e-6)
+
+
+def test_cuda_env_parse_tools_matches_reference_semantics():
+    """mpm/cuda_env.py:51-103: softness is 666 whatever the entry says, Box args = (hx, hy, hz, 0), Capsule args = (r, half length, 0, 0)."""
+    from dexdeform_b200.cuda_env import CudaEnv
+    env = CudaEnv.__new__(CudaEnv)
+    n, kw = env.parse_tools([dict(shape="Box", size=(0.1, 0.2, 0.3), round=0.01, friction=0.5, softness=3.0, init_pos=(0.5, 0.5, 0.5)),
+                             dict(shape="Capsule", size=(0.02, 0.06), round=0, action=dict(dim=6, scale=(0.01,) * 6))])
+    assert n == 2 and kw["types"] == [0, 1] and kw["softness"] == [666.0, 666.0] and kw["mu"] == [0.5, 0.9] and kw["round"] == [0.01, 0]
+    assert kw["args"] == [[0.1, 0.2, 0.3, 0], [0.02, 0.06, 0, 0]] and kw["action_scales"] == [(), (0.01,) * 6]
+    assert kw["pos"] == [(0.5, 0.5, 0.5), (0.3, 0.3, 0.3)] and kw["rot"] == [(1.0, 0.0, 0.0, 0.0)] * 2
+    d = env.default_tool_config()
+    assert d.friction == 0.9 and d.action.dim == 0 and d["action"]["scale"] == () and d.mass == 1.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/mpm"), reason="reference checkout not present")
+def test_reference_fixture_is_current():
+    """Re-runs the generator (the reference's parser + kinematics under stubs) and compares with the committed fixture."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        env = dict(os.environ)
+        src = open(os.path.join(ROOT, "tests", "golden", "make_hand_ref.py")).read().replace('path = os.path.join(HERE, "shadow_ref.npz")', f'path = os.path.join({d!r}, "shadow_ref.npz")')
+        script = os.path.join(d, "gen.py")
+        open(script, "w").write(src.replace("HERE = os.path.dirname(os.path.abspath(__file__))", f"HERE = {os.path.join(ROOT, 'tests', 'golden')!r}"))
+        subprocess.run([sys.executable, script], check=True, capture_output=True, env=env)
+        a, b = np.load(os.path.join(d, "shadow_ref.npz")), np.load(REF_FIX)
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            assert np.allclose(a[k], b[k], atol=1e-6), k
+
+
+ENV_FIX = os.path.join(ROOT, "tests", "golden", "env_ref.npz")
+
+
+@pytest.mark.skipif(not HAVE_ASSETS, reason="DexDeform asset files not present")
+@pytest.mark.parametrize("name", ["folding", "rope", "bun", "dumpling", "wrap", "flip", "lift_box"])
+def test_env_description_equals_reference_for_every_shipped_yaml(name):
+    """HandEnv.describe (everything mpm/hand.py:436-476 derives from an env YAML before a simulator exists) against the same
+    quantities computed by the reference's own Shapes / parse_sim_cfg / parse_manip_cfgs (tests/golden/make_env_ref.py)."""
+    import hashlib
+    from dexdeform_b200.hand import HandEnv, load_env_cfg
+    z = np.load(ENV_FIX)
+    r = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith(name + ".")}
+    env = HandEnv.__new__(HandEnv)
+    env.assets_dir = None
+    d = env.describe(load_env_cfg(name))
+    assert d["n_particles"] == int(r["n_particles"]) and len(d["objects"]) == int(r["n_objects"])
+    obj = np.ascontiguousarray(d["objects"], np.float32)
+    assert np.array_equal(obj[:8], r["objects_head"]) and hashlib.sha256(obj.tobytes()).hexdigest() == str(r["objects_sha256"])   # bit for bit
+    n, kw = env.parse_tools(d["primitives"])
+    assert n == len(r["prim_type"]) and kw["types"] == r["prim_type"].tolist() and kw["softness"] == [666.0] * n
+    assert np.allclose(np.float32(kw["args"]), r["prim_args"], rtol=0, atol=1e-7) and np.allclose(kw["mu"], r["prim_friction"])
+    assert d["hand_cfg"]["n_hands"] == int(r["n_hands"])
+    assert np.allclose(d["root_matrix"], r["root_matrix"], atol=1e-12) and np.allclose(d["joint_pos"], r["joint_pos"], atol=0)
+
+
+def _env_cfg(mode="rh", n=3000, max_steps=45):
+    """lift_box.yml's sections with a smaller block (the YAML files themselves do not exist on the GPU box)."""
+    manip = [dict(hand_idx=0, init_pos="(0.5, 0.2, 0.3)", init_rot="(0., 0., np.pi)", init_qpos="zero")]
+    if mode == "dual":
+        manip = [dict(hand_idx=0, init_pos="(0.3, 0.25, 0.3)", init_rot="(0., 0., np.pi)", init_qpos="default"),
+                 dict(hand_idx=1, init_pos="(0.7, 0.25, 0.3)", init_rot="(0., 0., np.pi)", init_qpos="zero")]
+    return {"SIMULATOR": dict(n_particles=n, E=5e3, nu=0.2, yield_stress=50.0, ground_friction=0.3, quality=1, max_steps=max_steps, gravity="(0., -2., 0.)",
+                              mode=mode, ctrl_type="vel", scale=1.5, hand_friction=0.9),
+            "SHAPES": [dict(shape="box", width="(0.09, 0.09, 0.09)", init_pos="(0.49, 0.22, 0.45)", n_particles=n)],
+            "MANIPULATORS": manip}
+
+
+@pytest.mark.gpu
+def test_hand_env_construction_and_sdf_helpers():
+    """HandEnv (hand.py:436-649) from a config + fixture tables: initialize, set_single_hand_pose, the signed-distance helpers
+    policy/preprocess uses (hand.py:236-341) and the render-only state."""
+    from dexdeform_b200.hand import HandEnv, SINGLE_PRIM_RANGE
+    env = HandEnv(_env_cfg(), tables=tables("rh15"))
+    sim = env.simulator
+    st = env.init_state
+    assert len(st) == 4 + 19 + 2 and np.array_equal(st[2], np.tile(np.eye(3, dtype=np.float32)[None], (sim.n_particles, 1, 1)))
+    assert np.allclose(st[-2][0], HandEnv.get_root_matrix((0.5, 0.2, 0.3), (0.0, 0.0, np.pi)), atol=1e-6) and np.all(st[-1] == 0)
+    assert np.abs(st[0] - np.array([0.49, 0.22, 0.45])).max() <= 0.045 + 1e-6       # the block of the SHAPES section
+    # body poses of state 0 are the forward kinematics of the configured wrist frame
+    kin = HandKinematics(tables("rh15"))
+    p0, _ = kin.forward(torch.tensor(st[-2])[None], torch.tensor(st[-1])[None])
+    assert np.allclose(np.stack(st[4:4 + 19])[:, :3], p0[0].numpy(), atol=2e-6)
+    # signed distances of given points: primitive centres are inside, far points outside; the state is restored afterwards
+    centres = np.stack(st[4:4 + 19])[:, :3]
+    far = centres + np.array([0.0, 0.3, 0.0])
+    d_in, d_out = sim.primitive_sdf_given_p(centres, SINGLE_PRIM_RANGE), sim.primitive_sdf_given_p(far, SINGLE_PRIM_RANGE)
+    assert d_in.shape == (19,) and (d_in < 0).all() and (d_out > 0.05).all()
+    assert np.array_equal(sim.get_state(0)[0], st[0])
+    np.random.seed(0)
+    pts, sdf, labels = sim.sample_pts_inside_primitives(200, mode="rh")
+    assert pts.shape == (200, 3) and sdf.shape == (200, 19) and labels.shape == (200, 1) and (sdf.min(-1) <= 0).all()
+    # render-only state round trip and a new wrist pose
+    p, base, q = sim.get_state_render_only(0)
+    sim.set_state_render_only(p + 0.01, base, q)
+    assert np.allclose(sim.get_x(0), p + 0.01, atol=1e-7)
+    env.set_single_hand_pose(0, pos=(0.5, 0.3, 0.3), rot=(0.0, 0.0, np.pi), joint_pos=[0.1] * 24)
+    st2 = sim.get_state(0)
+    assert np.allclose(st2[-2][0][:3, 3], (0.5, 0.3, 0.3)) and np.allclose(st2[-1][0], 0.1)
+    assert not np.allclose(np.stack(st2[4:4 + 19])[:, :3], centres)
+    env.set_particle_color(0xff0000)
+    # one env step still runs from this state
+    sim.step(np.zeros((1, 26), np.float32))
+    assert np.isfinite(sim.get_x(0)).all()
+
+
+@pytest.mark.gpu
+def test_dual_hand_env():
+    from dexdeform_b200.hand import HandEnv, LH_PRIM_RANGE, RH_PRIM_RANGE
+    env = HandEnv(_env_cfg("dual"), tables=tables("dual15"))
+    sim = env.simulator
+    assert sim.n_hands == 2 and sim.n_bodies == 38
+    st = sim.get_state(0)
+    assert st[-2].shape == (2, 4, 4) and st[-1].shape == (2, 24) and np.all(st[-1][1] == 0) and np.abs(st[-1][0]).sum() > 0
+    env.set_dual_hand_pose(pos=[(0.3, 0.3, 0.3), (0.7, 0.3, 0.3)], rot=[(0.0, 0.0, np.pi)] * 2, joint_pos=[[0.05] * 24, [0.1] * 24])
+    st = sim.get_state(0)
+    poses = np.stack(st[4:4 + 38])
+    assert np.allclose(st[-2][:, :3, 3], [(0.3, 0.3, 0.3), (0.7, 0.3, 0.3)]) and np.allclose(st[-1][1], 0.1)
+    assert poses[LH_PRIM_RANGE, 0].mean() < 0.5 < poses[RH_PRIM_RANGE, 0].mean()
+    lh = sim.lh_sdf_given_p(poses[LH_PRIM_RANGE, :3])
+    rh = sim.rh_sdf_given_p(poses[LH_PRIM_RANGE, :3])
+    assert (lh < 0).all() and (rh > 0).all()
+    act = np.zeros((2, 26), np.float32)
+    act[:, :20] = 0.3
+    sim.step(act)
+    assert np.isfinite(sim.get_x(0)).all() and float(sim.joint_rot[0][1, 3]) > 0.1
