@@ -135,6 +135,13 @@ DD_DEV float4 lds_v4(unsigned a) {
 }
 DD_DEV void sts_v4_if(unsigned a, float4 v, bool pred) {
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4}; }" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) DD_TILE_CLOBBER);
+#ifdef DD_TILE_SYNCWARP
+  // Orders the read-modify-write of one stencil offset before the next one for ALL lanes in the sense of the CUDA memory model
+  // (lanes of a row alias each other's nodes at different offsets).  The default build relies on what the hardware does for a
+  // converged warp executing straight-line code -- shared-memory accesses of one warp are performed in program order -- and
+  // compute-sanitizer racecheck is run on the DD_TILE_SYNCWARP build (profiles/r02_sanitizer.md records both and the cost).
+  __syncwarp();
+#endif
 }
 // Tile slot of node (tx,ty,tz) in an 8^3 tile.  A 128-bit shared-memory access is served one quarter-warp (8 lanes) at a
 // time and is conflict-free when those 8 lanes hit 8 different 16-byte bank groups; the group of a node is the low three

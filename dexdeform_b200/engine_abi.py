@@ -44,6 +44,7 @@ ABI2 = {
     "dd_hand_create": (c_int, [c_int, c_int, P, P, P, c_int, P, P, P, c_int, P, P, P, P, P, P, P]),
     "dd_hand_destroy": (None, [P]),
     "dd_hand_fk": (c_int, [P, P, c_int, c_int, P, P, P, P, P, c_int, S]),
+    "dd_hand_fk_grad": (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P, c_int, S]),
     "dd_sim_profile_substep": (c_int, [P, c_int, c_int, P, P, c_int, P, S]),
 }
 

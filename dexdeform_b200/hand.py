@@ -126,6 +126,20 @@ class DeviceFK:
             raise RuntimeError(self.lib.dd_last_error().decode())
         return nb_, nq_
 
+    def run_grad(self, engine, f, S, base_pose, joint_rot, action, g_next_base=None, g_next_q=None, has_base_action=True):
+        """Reverse mode of ``run`` for the same inputs (after the engine's backward pass over f .. f+S): returns
+        (dL/daction (E, nh, 26), dL/dbase_pose (E, nh, 4, 4), dL/djoint_rot (E, nh, 24)) as CUDA tensors."""
+        base_pose, joint_rot, action = (a.detach().contiguous().float() for a in (base_pose, joint_rot, action))
+        ga, gb, gq = torch.zeros_like(action), torch.zeros_like(base_pose), torch.zeros_like(joint_rot)
+        ptr = lambda a: None if a is None else a.detach().contiguous().float().data_ptr()
+        keep = [None if a is None else a.detach().contiguous().float() for a in (g_next_base, g_next_q)]
+        rc = self.lib.dd_hand_fk_grad(self._h, engine._h, f, S, base_pose.data_ptr(), joint_rot.data_ptr(), action.data_ptr(),
+                                      None if keep[0] is None else keep[0].data_ptr(), None if keep[1] is None else keep[1].data_ptr(),
+                                      gb.data_ptr(), gq.data_ptr(), ga.data_ptr(), int(has_base_action), engine.stream)
+        if rc:
+            raise RuntimeError(self.lib.dd_last_error().decode())
+        return ga, gb, gq
+
 
 def read_poses(engine, f0, count):
     """Poses of states f0..f0+count-1 as CUDA tensors (count, E, nb, 3) / (count, E, nb, 4), copied device-to-device."""

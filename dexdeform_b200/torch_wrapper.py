@@ -34,6 +34,11 @@ class GradModel:
         self.device = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
         self._frontier = None  # state index whose gradient slot currently holds a valid gradient
         self.pos_rot = None
+        self._forward_fk_func = None
+        # hand kinematics and their adjoint on the device (dd_hand_fk / dd_hand_fk_grad) instead of the ~100-op torch graph per env
+        # step; DD_TORCH_FK=1 keeps the torch mirror of the reference's FK in the loop
+        import os
+        self.use_device_fk = getattr(self.sim, "device_fk", None) is not None and os.environ.get("DD_TORCH_FK", "0") != "1"
 
     @property
     def substeps(self):
@@ -130,6 +135,56 @@ class GradModel:
         return self._forward_func.apply
 
     @property
+    def diff_forward_fk(self):
+        """One env step with the hand kinematics on the device: ``(s, action, base_pose, joint_rot, *past_obs) -> obs(s+1) +
+        (next_base_pose, next_joint_rot)``.  Forward: dd_hand_fk writes the S poses straight into the engine, then the S substeps
+        run; backward: observation gradients in, the substeps' adjoint, then dd_hand_fk_grad turns the S pose gradients (and the
+        gradient of the end-of-step kinematic state) into gradients of the action and of the kinematic state the step began with."""
+        if self._forward_fk_func is None:
+            model = self
+
+            class forward_fk(Function):
+                @staticmethod
+                def forward(ctx, s, action, base, q, *past_obs):
+                    sim = model.sim
+                    S, f, E, nh = model.substeps, s * model.substeps, sim.n_envs, sim.n_hands
+                    ctx.s, ctx.shapes = s, (action.shape, base.shape, q.shape)
+                    ctx.zero = [torch.zeros_like(i) for i in past_obs]
+                    a = action.detach().float().reshape(-1, nh, action.shape[-1]).expand(E, -1, -1).contiguous()
+                    b = base.detach().float().reshape(-1, nh, 4, 4).expand(E, -1, -1, -1).contiguous()
+                    j = q.detach().float().reshape(-1, nh, q.shape[-1]).expand(E, -1, -1).contiguous()
+                    if a.shape[-1] < 26:  # fixed base: 20 actuator commands only
+                        a = torch.cat((a, torch.zeros((E, nh, 26 - a.shape[-1]), device=a.device)), -1)
+                    ctx.has_base = action.shape[-1] == 26
+                    ctx.inputs = (a, b, j)
+                    nb_, nq_ = sim.device_fk.run(sim.engine, f, S, b, j, a, has_base_action=ctx.has_base)
+                    sim.forward_range(f, S)
+                    if f + S < len(sim.base_pose):
+                        sim.base_pose[f + S], sim.joint_rot[f + S] = (nb_[0], nq_[0]) if E == 1 else (nb_, nq_)
+                    kin = (nb_[0], nq_[0]) if E == 1 else (nb_, nq_)
+                    return model.get_obs(s + 1, action.device) + kin
+
+                @staticmethod
+                def backward(ctx, *grads):
+                    sim, s = model.sim, ctx.s
+                    S, f, E, nh = model.substeps, s * model.substeps, sim.n_envs, sim.n_hands
+                    obs_grad, g_nb, g_nq = grads[:-2], grads[-2], grads[-1]
+                    model.set_obs_grad(s + 1, *obs_grad)
+                    sim.backward_range(f, S)
+                    model._frontier = f
+                    a, b, j = ctx.inputs
+                    ga, gb, gq = sim.device_fk.run_grad(sim.engine, f, S, b, j, a, g_nb.reshape(E, nh, 4, 4), g_nq.reshape(E, nh, -1), has_base_action=ctx.has_base)
+
+                    def fit(g, shape):  # an input shared by all environments receives the sum of their gradients
+                        g = g[..., :shape[-1]] if g.shape[-1] != shape[-1] else g
+                        return g.reshape(shape) if g.numel() == int(torch.Size(shape).numel()) else g.sum(0).reshape(shape)
+
+                    return (None, fit(ga, ctx.shapes[0]), fit(gb, ctx.shapes[1]), fit(gq, ctx.shapes[2])) + tuple(ctx.zero)
+
+            self._forward_fk_func = forward_fk
+        return self._forward_fk_func.apply
+
+    @property
     def diff_set_pose(self):
         if self._set_pose_func is None:
             model = self
@@ -159,6 +214,10 @@ class GradModel:
         if pos_rot is not None:
             assert isinstance(pos_rot[0], torch.Tensor)
             past_obs = self.diff_set_pose(s, *pos_rot)
+        if self.use_device_fk and pos_rot is None:
+            out = self.diff_forward_fk(s, action, *self.pos_rot, *past_obs)
+            self.pos_rot = out[-2:]
+            return out[:-2]
         pos, rot, q_state = self.sim.compute_forward_kinematics(s * self.substeps, action, pos_rot=self.pos_rot)
         self.pos_rot = q_state
         return self.diff_forward(s, pos, rot, *past_obs)

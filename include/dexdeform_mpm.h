@@ -187,6 +187,12 @@ int dd_hand_create(int n_hands, int n_ops, const int *op_kind, const int *op_ind
 void dd_hand_destroy(dd_hand *hand);
 int dd_hand_fk(dd_hand *hand, dd_sim *sim, int f, int n_substeps, const float *base_pose, const float *joint_rot, const float *action,
                float *next_base, float *next_q, int has_base_action, cudaStream_t stream);
+/* Reverse mode of dd_hand_fk (what torch autograd computes for the reference's JointVel_Fk): reads the pose gradients of states
+ * f+1 .. f+n_substeps from the simulator and ADDS dL/d(base_pose) (E, nh, 4, 4), dL/d(joint_rot) (E, nh, 24), dL/d(action) (E, nh, 26)
+ * to the caller-zeroed device buffers; g_next_base / g_next_q: gradients w.r.t. the end-of-step kinematic state (may be NULL). */
+int dd_hand_fk_grad(dd_hand *hand, dd_sim *sim, int f, int n_substeps, const float *base_pose, const float *joint_rot, const float *action,
+                    const float *g_next_base, const float *g_next_q, float *g_base, float *g_q, float *g_action, int has_base_action,
+                    cudaStream_t stream);
 
 #ifdef __cplusplus
 }

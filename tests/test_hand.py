@@ -359,3 +359,49 @@ def test_dual_hand_env():
     act[:, :20] = 0.3
     sim.step(act)
     assert np.isfinite(sim.get_x(0)).all() and float(sim.joint_rot[0][1, 3]) > 0.1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,fixed_base,E", [("rh15", False, 1), ("rh15", True, 2), ("dual15", False, 2)])
+def test_device_fk_adjoint_matches_torch_autograd(tag, fixed_base, E, monkeypatch):
+    """Action gradients of a two-step rollout through GradModel: kinematics + adjoint on the device (dd_hand_fk / dd_hand_fk_grad)
+    against the torch mirror of the reference's FK differentiated by autograd (hand.py:347-428).  The MPM part is the same engine
+    in both runs, so any difference is the kinematics adjoint."""
+    from dexdeform_b200.hand import HandEnv, HandSimulator
+    from dexdeform_b200.torch_wrapper import GradModel
+    t = tables(tag)
+    nb, nh, n = len(t.prim_type), t.n_hands, 2000
+    cfg = dict(n_particles=n, E=5e3, nu=0.2, yield_stress=50.0, ground_friction=0.3, quality=1, max_steps=85, gravity=(0.0, -2.0, 0.0), fixed_base=fixed_base)
+    rng = np.random.default_rng(1)
+    x = ((rng.random((n, 3)) * 2 - 1) * 0.04 + np.array([0.5, 0.2, 0.45])).astype(np.float32)
+    roots = np.stack([HandEnv.get_root_matrix((0.5 + 0.12 * (2 * h - nh + 1), 0.2, 0.3), (0.0, 0.0, np.pi)) for h in range(nh)])
+    state = (x, np.zeros((n, 3), np.float32), np.tile(np.eye(3, dtype=np.float32)[None], (n, 1, 1)), np.zeros((n, 3, 3), np.float32), np.float32(roots),
+             np.float32(rng.random((nh, 24)) * 0.2))
+    act0 = np.float32(rng.uniform(-1.3, 1.3, (2, E, nh, 26)))     # some commands beyond the clamp
+    act0[..., 21] = -0.6
+    grads, losses = {}, {}
+    for mode in ("device", "torch"):
+        monkeypatch.setenv("DD_TORCH_FK", "1" if mode == "torch" else "0")
+        sim = HandSimulator(nb, {"tables": t}, cfg=cfg, n_envs=E)
+        sim.init_bodies(t.prim_type.astype(np.float32), np.full(nb, 666.0, np.float32), np.full(nb, 0.9, np.float32), np.zeros(nb, np.float32), t.prim_size,
+                        action_scales=[()] * nb)
+        sim.set_state(0, state)
+        model = GradModel(sim, return_grid=())
+        assert model.use_device_fk == (mode == "device")
+        model.zero_grad()
+        a = torch.tensor(act0 if E > 1 else act0[:, 0], device="cuda", requires_grad=True)
+        obs = model.get_obs(0, "cuda")
+        for s in range(2):
+            obs = model.forward(s, a[s], *obs)
+        loss = obs[0][..., 1].mean() + 0.3 * obs[0][..., 6:].mean() + 0.1 * obs[1][..., :3].sum() + 0.05 * obs[1][..., 3:].square().sum()
+        loss.backward()
+        grads[mode], losses[mode] = a.grad.detach().cpu().numpy().copy(), float(loss)
+        sim.engine.close()
+    assert abs(losses["device"] - losses["torch"]) < 1e-5 * max(1.0, abs(losses["torch"]))
+    gd, gt = grads["device"].ravel(), grads["torch"].ravel()
+    assert np.abs(gt).max() > 0
+    rel = np.linalg.norm(gd - gt) / np.linalg.norm(gt)
+    cos = float(gd @ gt / (np.linalg.norm(gd) * np.linalg.norm(gt)))
+    assert rel < 2e-3 and cos > 0.99999, (rel, cos)
+    if fixed_base:
+        assert np.all(grads["device"][..., 20:] == 0)
