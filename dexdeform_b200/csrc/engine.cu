@@ -128,18 +128,20 @@ DD_DEV float4 *aux4(float *slot, int EN, int k) { return reinterpret_cast<float4
 #define DD_TILE_CLOBBER
 #endif
 DD_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-DD_DEV float4 lds_v4(unsigned a) {
-  float4 r;
-  asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) DD_TILE_CLOBBER);
+// (only the lanes that will store load: a lane that shares its cell with a lower lane of the row, or shadows an idle slot, would
+// otherwise read a node another lane is updating in the same step -- harmless, its value is discarded, but a reported hazard)
+DD_DEV float4 lds_v4_if(unsigned a, bool pred) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4]; }" : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w) : "r"(a), "r"((int)pred) DD_TILE_CLOBBER);
   return r;
 }
 DD_DEV void sts_v4_if(unsigned a, float4 v, bool pred) {
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4}; }" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) DD_TILE_CLOBBER);
-#ifdef DD_TILE_SYNCWARP
+#ifndef DD_TILE_NO_SYNCWARP
   // Orders the read-modify-write of one stencil offset before the next one for ALL lanes in the sense of the CUDA memory model
-  // (lanes of a row alias each other's nodes at different offsets).  The default build relies on what the hardware does for a
-  // converged warp executing straight-line code -- shared-memory accesses of one warp are performed in program order -- and
-  // compute-sanitizer racecheck is run on the DD_TILE_SYNCWARP build (profiles/r02_sanitizer.md records both and the cost).
+  // (lanes of a row alias each other's nodes at different offsets).  Without it the code relies on what the hardware does for a
+  // converged warp executing straight-line code (shared-memory accesses of one warp are performed in program order); measured
+  // cost of the barrier: none (config D 316 vs 317 us per substep pair), racecheck: profiles/r02_sanitizer.md.
   __syncwarp();
 #endif
 }
@@ -575,20 +577,32 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
       xform_inv_adj(bx, bq, gx, g_gxb, g_bx, g_bq, g_tmp);
     }
     // NOTE: a warp may straddle two environments only if G is not a multiple of 32; grids are multiples of 4^3
-    float r[14] = {g_np.x, g_np.y, g_np.z, g_nq.w, g_nq.x, g_nq.y, g_nq.z, g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z};
+    // Warp totals of the 14 pose-gradient components with a transposing butterfly: at every stage a lane hands half of its values
+    // to its partner and keeps the other half, so 16 shuffles (8 + 4 + 2 + 1 + 1) replace 14 x 5; afterwards the even lane 2 i holds
+    // the warp total of component i and adds it with ONE atomic (14 lanes in parallel instead of 14 atomics issued by lane 0).
+    float r[16] = {g_np.x, g_np.y, g_np.z, g_nq.w, g_nq.x, g_nq.y, g_nq.z, g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z, 0.f, 0.f};
+    const int lane_ = threadIdx.x & 31;
 #pragma unroll
-    for (int i = 0; i < 14; ++i) r[i] = warp_sum(r[i]);
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+      const bool hi = (lane_ & off) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        float send = hi ? r[i] : r[i + half], keep = hi ? r[i + half] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
     int wenv = __shfl_sync(0xffffffffu, env_, 0);  // a warp never straddles two environments
 #ifndef DD_NO_POSE_ATOMICS
-    if ((threadIdx.x & 31) == 0) {
-      int pb = wenv * kp.nb + b;
-      atomicAdd(&gnpos[pb].x, r[0]); atomicAdd(&gnpos[pb].y, r[1]); atomicAdd(&gnpos[pb].z, r[2]);
-      atomicAdd(&gnrot[pb].x, r[3]); atomicAdd(&gnrot[pb].y, r[4]); atomicAdd(&gnrot[pb].z, r[5]); atomicAdd(&gnrot[pb].w, r[6]);
-      atomicAdd(&gpos[pb].x, r[7]); atomicAdd(&gpos[pb].y, r[8]); atomicAdd(&gpos[pb].z, r[9]);
-      atomicAdd(&grot[pb].x, r[10]); atomicAdd(&grot[pb].y, r[11]); atomicAdd(&grot[pb].z, r[12]); atomicAdd(&grot[pb].w, r[13]);
+    {
+      const int comp = lane_ >> 1, pb = wenv * kp.nb + b;
+      if (!(lane_ & 1) && comp < 14) {
+        float *dst = comp < 3 ? &gnpos[pb].x + comp : comp < 7 ? &gnrot[pb].x + (comp - 3) : comp < 10 ? &gpos[pb].x + (comp - 7) : &grot[pb].x + (comp - 10);
+        atomicAdd(dst, r[0]);
+      }
     }
 #else
-    if (r[0] == 12345.f) gnpos[0].x = r[1] + r[2] + r[3] + r[4] + r[5] + r[6] + r[7] + r[8] + r[9] + r[10] + r[11] + r[12] + r[13] + (float)wenv;
+    if (r[0] == 12345.f) gnpos[0].x = r[0] + (float)wenv;
 #endif
   }
   if (inr) {
@@ -1074,7 +1088,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
           V3 val = step_n(vij, c2, k);
           float w = wij * wz[k];
           unsigned a = tbase + 16u * (unsigned)tile_slot(tx + i, ty + jj, tz + k);
-          float4 t = lds_v4(a);
+          float4 t = lds_v4_if(a, mine);
           t.x = fmaf(val.x, w, t.x); t.y = fmaf(val.y, w, t.y); t.z = fmaf(val.z, w, t.z); t.w = fmaf(m, w, t.w);
           sts_v4_if(a, t, mine);
         }
@@ -1220,7 +1234,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
           int so = (i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7);
           float4 t = tvrow[so];
           unsigned ga = growb + 16u * (unsigned)so;
-          float4 o = lds_v4(ga);
+          float4 o = lds_v4_if(ga, mine);
           o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
           sts_v4_if(ga, o, mine);
           float qn = t.x * h.x + t.y * h.y + t.z * h.z;

@@ -357,7 +357,8 @@ class HandEnv(CudaEnv):
         x = np.zeros((n, 3), np.float32)
         if d["objects"] is not None:
             x[: len(d["objects"])] = d["objects"]
-        self.simulator.states[0].x.upload(x)
+        zeros = np.zeros((1, n, 9), np.float32)
+        self.simulator.engine.set_state(0, x[None], zeros[..., :3].copy(), zeros, zeros)   # every buffer of a fresh State is zero
         self.renderer = None
         self.initialize(d["root_matrix"], d["joint_pos"])
         self.init_state = self.simulator.get_state(0)

@@ -21,9 +21,19 @@ from torch.autograd import Function
 
 
 class GradModel:
-    def __init__(self, env, return_grid=(-1,), return_svd=False):
+    def __init__(self, env, return_grid=(-1,), return_svd=False, windowed=None):
+        """``windowed`` (default: automatically, when the simulator was created with ``max_steps == substeps``): two-level
+        checkpointing.  The simulator then holds the per-substep checkpoints (states, constitutive factors, grids) of ONE env
+        step; the state at every env-step boundary of the rollout is kept here as device tensors (96 B per particle), and the
+        backward pass re-runs the forward substeps of an env step from its boundary state before differentiating it.  A rollout
+        of any length then needs the memory of one env step plus 96 B x particles per step, at the price of one extra forward
+        pass (the reference keeps 192 B x particles x substeps, mpm/simulator.py:206)."""
         self.env = env
         self.sim = env.simulator if hasattr(env, "simulator") else env
+        self.windowed = (self.sim.max_steps == self.sim.substeps) if windowed is None else bool(windowed)
+        if self.windowed and self.sim.max_steps < self.sim.substeps:
+            raise ValueError("windowed GradModel: the simulator needs max_steps >= substeps")
+        self._boundary, self._carry, self._resident = {}, None, None  # windowed mode: boundary states, gradient of the boundary above, window held
         self.dim = 3
         assert len(return_grid) == 0 or return_grid[0] == -1
         self.primitives = list(range(self.sim.n_bodies))
@@ -48,6 +58,7 @@ class GradModel:
         """mpm/torch_wrapper.py:24-30: a new optimisation iteration starts -- states[0]'s gradients are cleared (the forward
         pass clears those of every later state, mpm/simulator.py:570-571)."""
         self._frontier = None
+        self._boundary, self._carry, self._resident = {}, None, None
         self.sim.engine.zero_pose_grads(0, 1)
         if return_grid is not None:
             self.return_grid = tuple(return_grid)
@@ -67,9 +78,64 @@ class GradModel:
     def _squeeze(self, t):
         return t[0] if self.sim.n_envs == 1 else t
 
+    def _slot(self, s):
+        """Checkpoint slot that holds the state of env-step boundary ``s``."""
+        if not self.windowed:
+            return s * self.sim.substeps
+        if self._resident is not None and s == self._resident + 1:
+            return self.sim.substeps
+        if self._resident == s or (self._resident is None and s == 0):
+            return 0
+        raise RuntimeError(f"windowed GradModel: the state of env step {s} is not in the simulator (window {self._resident} is)")
+
+    # ---- two-level checkpointing (no-ops unless windowed)
+    def _window_forward(self, s):
+        """Before the substeps of env step ``s``: returns the slot its first state sits in."""
+        if not self.windowed:
+            return s * self.sim.substeps
+        eng, S = self.sim.engine, self.sim.substeps
+        if self._resident is not None and s == self._resident + 1:
+            eng.roll(S)                                   # state and poses of slot S become slot 0, re-sorted on the device
+        elif not (self._resident is None and s == 0) and self._resident != s:
+            raise RuntimeError("windowed GradModel: env steps must be run in order")
+        st = eng.get_state(0, device=True)
+        pos, rot = eng.get_poses(0, 1, device=True)
+        self._boundary[s] = (st["x"], st["v"], st["F"], st["C"], pos, rot)
+        self._resident = s
+        return 0
+
+    def _window_backward(self, s, replay):
+        """Before the adjoint of env step ``s``: its checkpoints are in the simulator (re-running the forward substeps from the
+        boundary state if another window is resident) and the gradient of the boundary above is seeded."""
+        if not self.windowed:
+            return s * self.sim.substeps
+        eng, S = self.sim.engine, self.sim.substeps
+        if self._resident != s:
+            x, v, F, C, pos, rot = self._boundary[s]
+            eng.set_state(0, x, v, F, C)
+            eng.set_poses(0, pos, rot)
+            replay()
+            eng.forward(0, S)
+            self._resident = s
+        eng.zero_grad(S)
+        eng.zero_pose_grads(0, 1)   # slot 0 is shared by all windows (the forward pass only clears slots 1 .. S)
+        self._frontier = S
+        if self._carry is not None and self._carry[0] == s + 1:
+            _, g, gp, gr = self._carry
+            eng.add_state_grad(S, gx=g["x"], gv=g["v"], gF=g["F"], gC=g["C"])
+            eng.add_pose_grads(S, gpos=gp[0], grot=gr[0])
+        return 0
+
+    def _window_backward_done(self, s):
+        if not self.windowed:
+            return
+        eng = self.sim.engine
+        gp, gr = eng.get_pose_grads(0, 1, device=True)
+        self._carry = (s, eng.get_state_grad(0, device=True), gp, gr)
+
     def get_obs(self, s, device):
         sim, eng = self.sim, self.sim.engine
-        f = s * sim.substeps
+        f = self._slot(s)
         st = eng.get_state(f, ("x", "v"), device=True)
         parts = [st["x"], st["v"]]
         if sim.n_bodies:
@@ -91,7 +157,7 @@ class GradModel:
 
     def set_obs_grad(self, s, particle_grad, tool_grad, *args):
         sim, eng = self.sim, self.sim.engine
-        f = s * sim.substeps
+        f = self._slot(s)
         self._ensure_frontier(f)
         for idx, i in enumerate(self.return_grid):
             if idx < len(args) and args[idx] is not None:
@@ -116,7 +182,8 @@ class GradModel:
                     ctx.s = s
                     ctx.shapes = (pos.shape, rot.shape)
                     ctx.zero = [torch.zeros_like(i) for i in past_obs]
-                    S, f = model.substeps, s * model.substeps
+                    S, f = model.substeps, model._window_forward(s)
+                    ctx.poses = (pos.detach(), rot.detach()) if model.windowed else None
                     model.sim.set_poses(f + 1, pos, rot)   # poses of states f+1 .. f+S in one call
                     model.sim.forward_range(f, S)          # (re-sorts at f when it continues a rollout)
                     return model.get_obs(s + 1, pos.device)
@@ -124,10 +191,12 @@ class GradModel:
                 @staticmethod
                 def backward(ctx, *obs_grad):
                     s = ctx.s
-                    S, f = model.substeps, s * model.substeps
+                    S = model.substeps
+                    f = model._window_backward(s, lambda: model.sim.set_poses(1, *ctx.poses))
                     model.set_obs_grad(s + 1, *obs_grad)
                     model.sim.backward_range(f, S)
                     model._frontier = f
+                    model._window_backward_done(s)
                     gp, gr = model.sim.engine.get_pose_grads(f + 1, S, device=True)  # (S, E, nb, 3|4), on the device
                     return (None, gp.reshape(ctx.shapes[0]), gr.reshape(ctx.shapes[1])) + tuple(ctx.zero)
 
@@ -147,7 +216,7 @@ class GradModel:
                 @staticmethod
                 def forward(ctx, s, action, base, q, *past_obs):
                     sim = model.sim
-                    S, f, E, nh = model.substeps, s * model.substeps, sim.n_envs, sim.n_hands
+                    S, f, E, nh = model.substeps, model._window_forward(s), sim.n_envs, sim.n_hands
                     ctx.s, ctx.shapes = s, (action.shape, base.shape, q.shape)
                     ctx.zero = [torch.zeros_like(i) for i in past_obs]
                     a = action.detach().float().reshape(-1, nh, action.shape[-1]).expand(E, -1, -1).contiguous()
@@ -159,7 +228,7 @@ class GradModel:
                     ctx.inputs = (a, b, j)
                     nb_, nq_ = sim.device_fk.run(sim.engine, f, S, b, j, a, has_base_action=ctx.has_base)
                     sim.forward_range(f, S)
-                    if f + S < len(sim.base_pose):
+                    if not model.windowed and f + S < len(sim.base_pose):
                         sim.base_pose[f + S], sim.joint_rot[f + S] = (nb_[0], nq_[0]) if E == 1 else (nb_, nq_)
                     kin = (nb_[0], nq_[0]) if E == 1 else (nb_, nq_)
                     return model.get_obs(s + 1, action.device) + kin
@@ -167,12 +236,14 @@ class GradModel:
                 @staticmethod
                 def backward(ctx, *grads):
                     sim, s = model.sim, ctx.s
-                    S, f, E, nh = model.substeps, s * model.substeps, sim.n_envs, sim.n_hands
+                    S, E, nh = model.substeps, sim.n_envs, sim.n_hands
+                    a, b, j = ctx.inputs
+                    f = model._window_backward(s, lambda: sim.device_fk.run(sim.engine, 0, S, b, j, a, has_base_action=ctx.has_base))
                     obs_grad, g_nb, g_nq = grads[:-2], grads[-2], grads[-1]
                     model.set_obs_grad(s + 1, *obs_grad)
                     sim.backward_range(f, S)
                     model._frontier = f
-                    a, b, j = ctx.inputs
+                    model._window_backward_done(s)
                     ga, gb, gq = sim.device_fk.run_grad(sim.engine, f, S, b, j, a, g_nb.reshape(E, nh, 4, 4), g_nq.reshape(E, nh, -1), has_base_action=ctx.has_base)
 
                     def fit(g, shape):  # an input shared by all environments receives the sum of their gradients
@@ -194,13 +265,13 @@ class GradModel:
                 def forward(ctx, s, pos, rot):
                     ctx.s = s
                     ctx.shapes = (pos.shape, rot.shape)
-                    model.sim.set_pose(s * model.substeps, pos, rot)
+                    model.sim.set_pose(model._slot(s), pos, rot)
                     return model.get_obs(s, pos.device)
 
                 @staticmethod
                 def backward(ctx, *obs_grad):
                     s = ctx.s
-                    f = s * model.substeps
+                    f = model._slot(s)
                     model.set_obs_grad(s, *obs_grad)
                     gp, gr = model.sim.engine.get_pose_grads(f, 1, device=True)
                     return (None, gp.reshape(ctx.shapes[0]), gr.reshape(ctx.shapes[1]))
@@ -218,6 +289,6 @@ class GradModel:
             out = self.diff_forward_fk(s, action, *self.pos_rot, *past_obs)
             self.pos_rot = out[-2:]
             return out[:-2]
-        pos, rot, q_state = self.sim.compute_forward_kinematics(s * self.substeps, action, pos_rot=self.pos_rot)
+        pos, rot, q_state = self.sim.compute_forward_kinematics(0 if self.windowed else s * self.substeps, action, pos_rot=self.pos_rot)
         self.pos_rot = q_state
         return self.diff_forward(s, pos, rot, *past_obs)

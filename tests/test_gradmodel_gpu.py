@@ -282,3 +282,40 @@ def test_gradmodel_batched_environments():
     for e in range(E):
         assert abs(float(losses[e]) - singles[e][0]) < 1e-5 * max(1.0, abs(singles[e][0]))
         assert rel_l2(g[e], singles[e][1]) < 2e-3, (e, rel_l2(g[e], singles[e][1]))
+
+
+@pytest.mark.parametrize("E", [1, 2])
+def test_two_level_checkpointing_matches_full_checkpointing(E):
+    """Windowed GradModel (simulator with max_steps == substeps: per-substep checkpoints of ONE env step, boundary states kept as
+    device tensors, forward substeps re-run in the backward pass) against the GradModel that checkpoints every substep of the
+    rollout: same loss, same action gradients, over 6 env steps with observation gradients entering at every boundary."""
+    S_, STEPS_, n = 20, 6, 2500
+    sc = lift_scene(n, STEPS_, S_)
+    nb = sc["nb"]
+    scale = [[0.01] * 3 + [0.015] * 3] * nb
+    rng = np.random.default_rng(5)
+    a0 = np.float32(rng.uniform(-0.1, 0.1, (STEPS_, E, nb, 6)))
+    a0[..., 1] = 0.4
+    out = {}
+    for mode, max_steps in (("full", S_ * STEPS_), ("windowed", S_)):
+        sim = MPMSimulator(nb, ground_friction=sc["ground_friction"], gravity=tuple(sc["gravity"].reshape(3) / 30), n_particles=n, dx=sc["dx"],
+                           dt=sc["dt"], max_steps=max_steps, substeps=S_, yield_stress=50.0, n_envs=E)
+        sim.init_bodies(sc["tfsr"][:, 0], sc["tfsr"][:, 2], sc["tfsr"][:, 1], sc["tfsr"][:, 3], sc["args"], action_scales=scale, pos=sc["pos"][0], rot=sc["rot"][0])
+        sim.set_state(0, (sc["x"], sc["v"], sc["F"].reshape(-1, 3, 3), sc["C"].reshape(-1, 3, 3)) + tuple(np.r_[p, r] for p, r in zip(sc["pos"][0], sc["rot"][0])))
+        model = GradModel(sim, return_grid=())
+        assert model.windowed == (mode == "windowed")
+        model.zero_grad()
+        action = torch.tensor(a0 if E > 1 else a0[:, 0], device="cuda", requires_grad=True)
+        obs = model.get_obs(0, "cuda")
+        loss = 0.0
+        for j in range(STEPS_):
+            obs = model.forward(j, action[j], *obs)
+            loss = loss - obs[0][..., 1].mean() + 0.05 * obs[0][..., 3:6].square().mean() + 0.02 * obs[0][..., 6:].mean() + 0.1 * obs[1][..., :3].sum()
+        loss.backward()
+        out[mode] = (float(loss), action.grad.cpu().numpy().copy(), obs[0][..., :3].detach().cpu().numpy())
+        sim.engine.close()
+    assert abs(out["full"][0] - out["windowed"][0]) < 1e-5 * max(1.0, abs(out["full"][0]))
+    assert np.abs(out["full"][2] - out["windowed"][2]).max() < 1e-5
+    e, c = rel_l2(out["windowed"][1], out["full"][1]), cosine(out["windowed"][1], out["full"][1])
+    print(f"two-level checkpointing (E={E}): action-gradient rel-L2 {e:.3e} cos {c:.7f}")
+    assert e < 2e-3 and c > 0.99999, (e, c)
