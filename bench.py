@@ -74,23 +74,48 @@ def workload_scene(name, seed=0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons of THIS rank's GPU sampled while the timed region runs: NVML in-process (the library behind
+    nvidia-smi; one cheap query every 100 ms), falling back to the nvidia-smi command line.  Spawning nvidia-smi from all eight
+    ranks ten times a second serialises on the driver and showed up as lost throughput at N=8, hence NVML first."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.source = index, [], False, "nvidia-smi"
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(index).uuid)).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n, h = self.nvml, self.handle
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(reasons_fn(h))
+        return [str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)),
+                str(n.nvmlDeviceGetPowerUsage(h) / 1000.0)] + ["Active" if mask & bit else "Not Active" for _, bit in self.REASONS]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.samples.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.1 if self.nvml is not None else 0.5)
 
     def summary(self):
         if not self.samples:
@@ -101,7 +126,7 @@ class ClockSampler(threading.Thread):
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def measured_peak():
@@ -290,7 +315,7 @@ def e2e_gradmodel(args, sc, S, world, stream):
     d2h = sum(t.numel() * 4 for t in (hgrad, hloss))
 
     def step():
-        sim.engine.set_state(0, hx, hv, hF, hC)                   # H2D + cell sort (host buffers are pinned; waits for the copies)
+        sim.engine.set_state(0, hx, hv, hF, hC, non_blocking=True)   # H2D + cell sort (pinned buffers; the step's final synchronize covers the copies)
         model.zero_grad()
         action = hact.to("cuda", non_blocking=True).requires_grad_(True)
         obs = model.get_obs(0, "cuda")
@@ -409,7 +434,7 @@ def make_hand_batch(E, T, S_env, stream):
     nb = len(tables.prim_type)
     cfg = dict(n_particles=10000, E=5e3, nu=0.2, yield_stress=50.0, ground_friction=0.3, quality=1, max_steps=T * S_env, gravity=(0.0, -2.0, 0.0),
                fixed_base=False)
-    sim = HandSimulator(nb, {"tables": tables}, cfg=cfg, n_envs=E, grid_ckpt=False, stream=stream.cuda_stream)
+    sim = HandSimulator(nb, {"tables": tables}, cfg=cfg, n_envs=E, stream=stream.cuda_stream)   # grids: brick checkpoints (a dense pair per substep would be 215 GB)
     assert sim.substeps == S_env
     sim.init_bodies(tables.prim_type.astype(np.float32), np.full(nb, 666.0, np.float32), np.full(nb, 0.9, np.float32), np.zeros(nb, np.float32),
                     tables.prim_size, action_scales=[()] * nb)
@@ -443,7 +468,8 @@ def run_E(args, rank, world, local):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     hstate = [pin(sc[k]) for k in ("x", "v", "F", "C")]                   # ONE environment's initial state; tiled on the device
     hact = pin(act_shared)
-    hnoise = pin(noise[first:first + E_local])
+    hnoise = pin(noise)
+    passes_local = range(first // sub, (first + E_local) // sub)         # engine passes of `sub` environments this rank owns
     packed = torch.zeros(1 + T * 26, dtype=torch.float32, device="cuda")  # [sum of losses | d sum / d shared action]
     hout = torch.empty_like(packed, device="cpu").pin_memory()
     state_dev = [None]
@@ -460,18 +486,18 @@ def run_E(args, rank, world, local):
             obs = model.forward(j, a[:, j], *obs)
         return -obs[0][..., 1].mean(1).sum()
 
-    def step(host_io):
+    def step(host_io, passes=passes_local, collective=True):
         if host_io or state_dev[0] is None:   # end to end: the initial state comes from the host every step
             state_dev[0] = [t.to("cuda", non_blocking=True)[None].expand(sub, -1, -1).contiguous() for t in hstate]
         action = (hact.to("cuda", non_blocking=True) if host_io else act_dev).clone().requires_grad_(True)
         total = 0.0
-        for b in range(E_local // sub):
+        for b in passes:
             loss = one_pass(b, action)
             loss.backward()
             total = total + loss.detach()
         packed[0] = total
         packed[1:] = action.grad.reshape(-1)
-        if world > 1:   # NCCL over NVLink: loss and action gradients only
+        if world > 1 and collective:   # NCCL over NVLink: loss and action gradients only
             import torch.distributed as dist
             dist.all_reduce(packed)
         if host_io:
@@ -506,6 +532,24 @@ def run_E(args, rank, world, local):
     barrier_sync(world)
     dt = max_over_ranks(time.perf_counter() - t0, world)
     units = float(E_total) * n * T * S_env
+    # the same 512 environments on ONE GPU (rank 0 alone, after the timed region, the other ranks idle at the barrier): the
+    # denominator of strong scaling for this workload, measured in the same run on the same box
+    one_gpu = None
+    if world > 1:
+        if rank == 0:
+            all_passes = range(E_total // sub)
+            step(False, all_passes, False)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            f0.record(stream)
+            for _ in range(2):
+                step(False, all_passes, False)
+            f1.record(stream)
+            torch.cuda.synchronize()
+            ms1 = f0.elapsed_time(f1) / 2
+            one_gpu = {"value": units / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1, "steps": 2,
+                       "note": "all 512 environments on rank 0's GPU alone (same process and engine, 8 passes of 64), other ranks idle"}
+        barrier_sync(world)
     out = None
     if rank == 0:
         peak, src = measured_peak()
@@ -521,7 +565,9 @@ def run_E(args, rank, world, local):
                        "path": "HandSimulator.set_state(host state) -> GradModel.get_obs/forward x10 -> loss.backward() -> all-reduce -> loss + action gradients to host"},
                "roofline": {"bound": "hbm", "achieved": round((ALG_BYTES_FWD + ALG_BYTES_BWD) * value / world / 1e9, 1), "peak": peak, "unit": "GB/s",
                             "frac": round((ALG_BYTES_FWD + ALG_BYTES_BWD) * value / world / 1e9 / peak, 4), "traffic": None, "peak_source": src,
-                            "note": "path figure (520 B per particle-substep) over the whole step incl. observations, FK and re-sorts; grids are replayed in the adjoint (no room for 400 grid checkpoints per pass)"}}
+                            "note": "path figure (520 B per particle-substep) over the whole step incl. observations, FK and re-sorts; grids of the active bricks are checkpointed per substep (brick checkpoints), nothing is replayed in the adjoint"}}
+        if one_gpu is not None:
+            out["one_gpu_same_workload"] = one_gpu
     sim.engine.close()
     return out
 

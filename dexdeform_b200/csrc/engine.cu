@@ -423,19 +423,14 @@ __global__ void __launch_bounds__(kT) k_g2p_grad(KP kp, const float *__restrict_
   plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
 }
 
-DD_DEV float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // grid_op_v2_grad (integrator.cu:779-1057) without the stored per-body velocities
 // cand: bodies that can touch this node's brick at all (superset of the contact mask); zero_gv / zero_m: clear the node's
 // entry of ggrid_v / grid after it has been consumed, so the next substep finds zeros without a separate memset pass
+// mm_ck: where this node's (mv, m) of the substep is stored when it does not come from the dense grid (brick checkpoints), else null
 DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, int cy, int cz, float4 *__restrict__ grid,
                            float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, const BodyTables &bt, float4 *gpos, float4 *grot,
-                           float4 *gnpos, float4 *gnrot, unsigned long long cand, bool zero_gv, bool zero_m) {
-  float4 mm = inr ? grid[node] : make_float4(0.f, 0.f, 0.f, 0.f);
+                           float4 *gnpos, float4 *gnrot, unsigned long long cand, bool zero_gv, bool zero_m, const float4 *mm_ck = nullptr, bool use_ck = false) {
+  float4 mm = !inr ? make_float4(0.f, 0.f, 0.f, 0.f) : !use_ck ? grid[node] : mm_ck ? *mm_ck : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 gvn = inr ? ggrid_v[node] : make_float4(0.f, 0.f, 0.f, 0.f);  // both node loads in flight together (cold HBM in the adjoint sweep)
   if (inr && zero_m) grid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
   bool live = inr && mm.w > 1e-12;
@@ -1442,13 +1437,27 @@ DD_DEV unsigned long long stage_bodies(GridSm &sm, const KP &kp, const BodyTable
 
 // zero_next: the (distinct) scatter target of the NEXT substep, cleared here so that no separate zeroing pass is needed;
 // zero_self: clear this substep's (m, mv) after use (forward-only mode with a single grid buffer)
+// Brick checkpoints (BrickCk): when one dense grid pair per substep does not fit in HBM (many environments, long rollouts), the
+// forward pass keeps (mv, m) and v_out of the ACTIVE bricks only, 64 nodes per brick, indexed by the brick's position in the
+// segment's active list (the list only grows inside a segment, so positions are stable); `cap` bricks per substep.  The adjoint
+// reads (mv, m) from there and writes v_out back into the dense working grid one substep ahead (see k_grid_grad_b).
+struct BrickCk {
+  float4 *m, *v;   // this substep's bricks (already offset), or null
+  int *n;          // bricks stored for this substep
+  int cap;
+  int *status;     // bit 0: a substep had more active bricks than `cap`
+};
 __global__ void __launch_bounds__(kT, 4) k_grid_b(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *__restrict__ grid,
-                                               float4 *__restrict__ grid_v, BodyTables bt, float4 *__restrict__ zero_next, int zero_self) {
+                                               float4 *__restrict__ grid_v, BodyTables bt, float4 *__restrict__ zero_next, int zero_self, BrickCk ck) {
   __shared__ GridSm sm;
   pdl_launch_dependents();
   stage_shapes(sm, kp, bt);  // (shape tables are never written by a kernel)
   pdl_wait();
   const int nactive = cnt[1], grp = threadIdx.x >> 6, g = threadIdx.x & 63;
+  if (ck.m && blockIdx.x == 0 && threadIdx.x == 0) {
+    *ck.n = min(nactive, ck.cap);
+    if (nactive > ck.cap) atomicOr(ck.status, 1);
+  }
   for (int blk = blockIdx.x; blk * 4 < nactive; blk += gridDim.x) {
     if (blk != (int)blockIdx.x) __syncthreads();  // the previous iteration is done with the staged poses
     int t = blk * kT + threadIdx.x;
@@ -1462,8 +1471,11 @@ __global__ void __launch_bounds__(kT, 4) k_grid_b(KP kp, const int *__restrict__
     float4 mm = grid[node];
     if (zero_next) zero_next[node] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (zero_self) grid[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 *ckv = nullptr;
+    if (ck.m && (t >> 6) < ck.cap) { ck.m[t] = mm; ckv = ck.v + t; }
     if (!(mm.w > 1e-12)) {
       grid_v[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ckv) *ckv = make_float4(0.f, 0.f, 0.f, 0.f);
       continue;
     }
     V3 v = v3(mm.x, mm.y, mm.z) * (1.f / mm.w) + kp.dt * v3(kp.g0, kp.g1, kp.g2);
@@ -1477,17 +1489,34 @@ __global__ void __launch_bounds__(kT, 4) k_grid_b(KP kp, const int *__restrict__
     }
     v = apply_bc(v, gx_, gy_, gz_, kp);
     grid_v[node] = make_float4(v.x, v.y, v.z, 0.f);
+    if (ckv) *ckv = make_float4(v.x, v.y, v.z, 0.f);
+  }
+}
+// v_out of a substep from its brick checkpoint back into the dense working grid (first adjoint substep of a range or of a segment;
+// in between k_grid_grad_b does it for the substep below on its way)
+__global__ void __launch_bounds__(kT) k_restore_bricks(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, const float4 *__restrict__ ck_v,
+                                                       const int *__restrict__ ck_n, float4 *__restrict__ grid_v) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int total = cnt[1] * 64, stored = *ck_n * 64;
+  for (int t = blockIdx.x * kT + threadIdx.x; t < total; t += gridDim.x * kT) {
+    int env, x, y, z;
+    grid_v[brick_node(active[t >> 6], t & 63, kp, env, x, y, z)] = t < stored ? ck_v[t] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
 __global__ void __launch_bounds__(kT, 4) k_grid_grad_b(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *__restrict__ grid,
                                                     float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos,
-                                                    float4 *grot, float4 *gnpos, float4 *gnrot, int zero_m) {
+                                                    float4 *grot, float4 *gnpos, float4 *gnrot, int zero_m, BrickCk ck, BrickCk below, float4 *__restrict__ grid_v) {
+  // ck: this substep's brick checkpoint ((mv, m) is read from it instead of `grid`); below: the checkpoint of the substep the
+  // adjoint visits next, whose v_out this kernel puts back into the dense `grid_v` (nobody reads grid_v between the gather of
+  // this substep, which has completed, and the gather of the next one)
   __shared__ GridSm sm;
   pdl_launch_dependents();
   stage_shapes(sm, kp, bt);  // (shape tables are never written by a kernel)
   pdl_wait();
   const int nactive = cnt[1], grp = threadIdx.x >> 6, g = threadIdx.x & 63;
+  const int stored = ck.m ? *ck.n * 64 : 0, stored_below = below.v ? *below.n * 64 : 0;
   for (int blk = blockIdx.x; blk * 4 < nactive; blk += gridDim.x) {
     if (blk != (int)blockIdx.x) __syncthreads();
     int t = blk * kT + threadIdx.x;
@@ -1497,7 +1526,8 @@ __global__ void __launch_bounds__(kT, 4) k_grid_grad_b(KP kp, const int *__restr
     unsigned long long cand = stage_bodies(sm, kp, bt, inr, brick, grp, g, view);
     int env = 0, x = 0, y = 0, z = 0, node = 0;
     if (inr) node = brick_node(brick, g, kp, env, x, y, z);
-    grid_grad_body(kp, node, inr, env, x, y, z, grid, ggrid_v, ggrid, view, gpos, grot, gnpos, gnrot, cand, true, zero_m != 0);
+    if (inr && below.v) grid_v[node] = t < stored_below ? below.v[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    grid_grad_body(kp, node, inr, env, x, y, z, grid, ggrid_v, ggrid, view, gpos, grot, gnpos, gnrot, cand, true, zero_m != 0, t < stored ? ck.m + t : nullptr, ck.m != nullptr);
   }
 }
 
@@ -1760,49 +1790,106 @@ __global__ void k_copy_poses(int n, const float4 *__restrict__ ps, const float4 
   if (i < n) { pd[i] = ps[i]; rd[i] = rs[i]; }
 }
 
-// compute_dist (integrator.cu:188-237) on the engine layout; dist is (E*N, nb) in ORIGINAL particle order
-__global__ void __launch_bounds__(kT) k_dist(KP kp, const int *__restrict__ perm, const float *__restrict__ slot, BodyTables bt, float *dist,
-                                             const float *__restrict__ gdist, float *gslot, float4 *gpos, float4 *grot, int need_grad) {
+// compute_dist (integrator.cu:188-237) on the engine layout, fused with the observation GradModel.get_obs assembles from it
+// (mpm/torch_wrapper.py:46-66): row `perm[p]` of `out` (ORIGINAL particle order, `ld` floats per row) receives
+// [x | v |] dist_0 .. dist_{nb-1}; WITH_XV = false writes the distances only (ld = nb: dd_sim_compute_dist).
+template <bool WITH_XV>
+__global__ void __launch_bounds__(kT) k_obs(KP kp, const int *__restrict__ perm, const float *__restrict__ slot, BodyTables bt, float *__restrict__ out, int ld) {
   int p = blockIdx.x * kT + threadIdx.x;
-  bool live = p < kp.EN;
-  int env = live ? p / kp.N : 0, src = live ? perm[p] : 0;
-  V3 xp = vzero();
+  if (p >= kp.EN) return;
+  int env = p / kp.N;
+  float4 a = plane4(slot, kp.EN, 0)[p];
+  V3 xp = v3(a.x, a.y, a.z);
+  float *o = out + (size_t)perm[p] * ld;
+  if (WITH_XV) {
+    float4 b = plane4(slot, kp.EN, 1)[p];
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y;
+    o += 6;
+  }
+  for (int b = 0; b < kp.nb; ++b) {
+    int pb = env * kp.nb + b;
+    o[b] = shape_sdf(q4f(bt.tfsr[b]), q4f(bt.args[b]), xform_inv(v3f(bt.pos[pb]), q4f(bt.rot[pb]), xp));
+  }
+}
+// Adjoint of k_obs: row perm[p] of `g` (ld floats) holds [gx | gv |] gdist.  gx, gv are added to the gradient slot; the distance
+// gradients go back to the particle position and the body poses.  A body none of whose 32 distance gradients in the warp is
+// non-zero is skipped (observation gradients of a rollout are mostly exact zeros: torch hands zeros_like for every past
+// observation), the 7 pose-gradient components of a body are reduced with a transposing butterfly (9 shuffles) into per-block
+// shared-memory sums, and a block issues one global atomic per touched (body, component) at its end.
+constexpr int kMaxBodiesObs = 64;
+template <bool WITH_XV>
+__global__ void __launch_bounds__(kT) k_obs_grad(KP kp, const int *__restrict__ perm, const float *__restrict__ slot, BodyTables bt, const float *__restrict__ g, int ld,
+                                                 float *gslot, float4 *gpos, float4 *grot) {
+  __shared__ float acc[kMaxBodiesObs * 8];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int p = blockIdx.x * kT + threadIdx.x;
+  const bool live = p < kp.EN;
+  const int first = blockIdx.x * kT, last = min(first + kT, kp.EN) - 1;
+  const bool block_one_env = first / kp.N == last / kp.N && kp.nb <= kMaxBodiesObs;  // sums of the whole block belong to one environment
+  for (int i = threadIdx.x; i < kp.nb * 8 && block_one_env; i += kT) acc[i] = 0.f;
+  __syncthreads();
+  const int env = live ? p / kp.N : last / kp.N;
+  const float *row = g + (size_t)(live ? perm[p] : 0) * ld;
+  V3 xp = vzero(), g_x = vzero(), g_v = vzero();
   if (live) {
     float4 a = plane4(slot, kp.EN, 0)[p];
     xp = v3(a.x, a.y, a.z);
+    if (WITH_XV) { g_x = v3(row[0], row[1], row[2]); g_v = v3(row[3], row[4], row[5]); row += 6; }
   }
-  V3 g_x = vzero();
+  const int env0 = __shfl_sync(full, env, 0);
+  const bool warp_one_env = __all_sync(full, env == env0);
   for (int b = 0; b < kp.nb; ++b) {
+    float gd = live ? row[b] : 0.f;
+    if (!__any_sync(full, gd != 0.f)) continue;
     int pb = env * kp.nb + b;
     V3 bx = v3f(bt.pos[pb]);
     Q4 bq = q4f(bt.rot[pb]), tfsr = q4f(bt.tfsr[b]), sargs = q4f(bt.args[b]);
-    V3 gxb = xform_inv(bx, bq, xp);
-    if (!need_grad) {
-      if (live) dist[(size_t)src * kp.nb + b] = shape_sdf(tfsr, sargs, gxb);
-    } else {
-      V3 g_bx = vzero();
-      Q4 g_bq;
-      g_bq.w = g_bq.x = g_bq.y = g_bq.z = 0.f;
-      if (live) xform_inv_adj(bx, bq, xp, shape_grad(tfsr, sargs, gxb) * gdist[(size_t)src * kp.nb + b], g_bx, g_bq, g_x);
-      float r[7] = {g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z};
-      int env0 = __shfl_sync(0xffffffffu, env, 0);
-      if (__all_sync(0xffffffffu, !live || env == env0)) {  // whole warp in one environment: reduce, one atomic set
+    V3 g_bx = vzero();
+    Q4 g_bq;
+    g_bq.w = g_bq.x = g_bq.y = g_bq.z = 0.f;
+    if (gd != 0.f) xform_inv_adj(bx, bq, xp, shape_grad(tfsr, sargs, xform_inv(bx, bq, xp)) * gd, g_bx, g_bq, g_x);
+    float r[8] = {g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z, 0.f};
+    if (warp_one_env) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) r[i] = warp_sum(r[i]);
-        if ((threadIdx.x & 31) == 0 && live) {
-          atomicAdd(&gpos[pb].x, r[0]); atomicAdd(&gpos[pb].y, r[1]); atomicAdd(&gpos[pb].z, r[2]);
-          atomicAdd(&grot[pb].x, r[3]); atomicAdd(&grot[pb].y, r[4]); atomicAdd(&grot[pb].z, r[5]); atomicAdd(&grot[pb].w, r[6]);
+      for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {  // afterwards lanes 4 c .. 4 c + 3 hold partial sums of component c
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          float send = hi ? r[i] : r[i + half], keep = hi ? r[i + half] : r[i];
+          r[i] = keep + __shfl_xor_sync(full, send, off);
         }
-      } else if (live) {
-        atomicAdd(&gpos[pb].x, r[0]); atomicAdd(&gpos[pb].y, r[1]); atomicAdd(&gpos[pb].z, r[2]);
-        atomicAdd(&grot[pb].x, r[3]); atomicAdd(&grot[pb].y, r[4]); atomicAdd(&grot[pb].z, r[5]); atomicAdd(&grot[pb].w, r[6]);
       }
+      r[0] += __shfl_xor_sync(full, r[0], 2);
+      r[0] += __shfl_xor_sync(full, r[0], 1);
+      const int comp = lane >> 2;
+      if ((lane & 3) == 0 && comp < 7 && r[0] != 0.f) {
+        if (block_one_env) atomicAdd(&acc[b * 8 + comp], r[0]);
+        else atomicAdd(comp < 3 ? &gpos[env0 * kp.nb + b].x + comp : &grot[env0 * kp.nb + b].x + (comp - 3), r[0]);
+      }
+    } else if (gd != 0.f) {  // a warp that straddles two environments (N not a multiple of 32)
+      atomicAdd(&gpos[pb].x, r[0]); atomicAdd(&gpos[pb].y, r[1]); atomicAdd(&gpos[pb].z, r[2]);
+      atomicAdd(&grot[pb].x, r[3]); atomicAdd(&grot[pb].y, r[4]); atomicAdd(&grot[pb].z, r[5]); atomicAdd(&grot[pb].w, r[6]);
     }
   }
-  if (need_grad && live) {
-    float4 *o = plane4(gslot, kp.EN, 0) + p;
-    float4 t = *o;
-    *o = make_float4(t.x + g_x.x, t.y + g_x.y, t.z + g_x.z, t.w);
+  if (live) {
+    float4 *o0 = plane4(gslot, kp.EN, 0) + p;
+    float4 t = *o0;
+    *o0 = make_float4(t.x + g_x.x, t.y + g_x.y, t.z + g_x.z, t.w + g_v.x);
+    if (WITH_XV) {
+      float4 *o1 = plane4(gslot, kp.EN, 1) + p;
+      float4 u = *o1;
+      *o1 = make_float4(u.x + g_v.y, u.y + g_v.z, u.z, u.w);
+    }
+  }
+  __syncthreads();
+  if (block_one_env) {
+    const int e = first / kp.N;
+    for (int i = threadIdx.x; i < kp.nb * 8; i += kT) {
+      int b = i >> 3, comp = i & 7;
+      float v = acc[i];
+      if (comp < 7 && v != 0.f) atomicAdd(comp < 3 ? &gpos[e * kp.nb + b].x + comp : &grot[e * kp.nb + b].x + (comp - 3), v);
+    }
   }
 }
 
@@ -1904,8 +1991,20 @@ struct dd_sim {
   float4 *mat0_pool = nullptr;
   float *yield_pool = nullptr;
   int4 *chunks_pool = nullptr;
-  float4 *gridck = nullptr, *gridvck = nullptr;  // max_steps * E * G each when grid checkpoints are on
+  float4 *gridck = nullptr, *gridvck = nullptr;  // max_steps * E * G each when (dense) grid checkpoints are on
   bool grid_ckpt = false;
+  float4 *brick_m = nullptr, *brick_v = nullptr;  // brick checkpoints: max_steps * brick_cap * 64 each (see BrickCk)
+  int *brick_n = nullptr, *status = nullptr;
+  int brick_cap = 0;
+  bool brick_ckpt = false;
+  BrickCk bck(int f) const {
+    BrickCk c = {nullptr, nullptr, nullptr, 0, nullptr};
+    if (brick_ckpt && f >= 0 && f < slots - 1) {
+      size_t o = (size_t)f * brick_cap * 64;
+      c.m = brick_m + o; c.v = brick_v + o; c.n = brick_n + f; c.cap = brick_cap; c.status = status;
+    }
+    return c;
+  }
   float *mat_aos = nullptr;  // (mass | vol | mu_lam_yield) in the caller's order, re-packed for every new ordering
   bool have_material = false;
   float *stage = nullptr;    // 24 * EN floats (x|v|F|C in original AoS order) or E*N*nb for dist
@@ -1964,7 +2063,7 @@ void launch_hot(dd_sim *s, K kernel, int grid, int block, size_t smem, cudaStrea
 using Mark = std::function<void(const char *)>;
 inline void mark(const Mark *m, const char *name) { if (m) (*m)(name); }
 int fwd_launches(const dd_sim *s) { return 3; }
-int bwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? (s->grid_ckpt ? 3 : 5) : 5; }
+int bwd_launches(const dd_sim *s) { return s->cfg.tile_mode ? (s->grid_ckpt || s->brick_ckpt ? 3 : 5) : 5; }
 constexpr int kBuildLaunches = 16;  // kernels of one segment build (sort, compaction, chunk tables, gather)
 
 template <int SVD>
@@ -1978,7 +2077,7 @@ void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk =
     launch_hot(s, k_p2g_tile<SVD, true>, s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * kSmemP2G, st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->G(f), s->counters + 4);
     mark(mk, "p2g_tile (svd+return map+scatter)");
     float4 *zn = (s->grid_ckpt && f + 1 < s->slots - 1) ? s->G(f + 1) : nullptr;
-    launch_hot(s, k_grid_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1);
+    launch_hot(s, k_grid_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->G(f), s->GV(f), s->tables(f), zn, s->grid_ckpt ? 0 : 1, s->bck(f));
     mark(mk, "grid_b (grid update + contact)");
     if (s->g2p_tiled) launch_hot(s, k_g2p_tile, s->tile_blocks(s->pb_g2p, s->w_g2p), 32 * s->w_g2p, s->w_g2p * kSmemG2P, st, kp, sg.view(), cur, nxt, s->GV(f), s->counters + 4);
     else k_g2p<<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, cur, nxt, s->GV(f));
@@ -1992,7 +2091,7 @@ void enqueue_forward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk =
   s->launches += fwd_launches(s);
 }
 template <int SVD>
-void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk = nullptr) {
+void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk = nullptr, bool restore_here = true, bool restore_below = false) {
   const KP &kp = s->kp;
   const Segment &sg = s->segs[s->seg_of(f)];
   float *cur = s->pslot(s->phys_cur(f)), *nxt = s->pslot(s->phys_cur(f) + 1);
@@ -2001,13 +2100,20 @@ void enqueue_backward_substep(dd_sim *s, int f, cudaStream_t st, const Mark *mk 
   float4 *gp = s->gpos + (size_t)f * ep, *gr = s->grot + (size_t)f * ep, *gnp = s->gpos + (size_t)(f + 1) * ep, *gnr = s->grot + (size_t)(f + 1) * ep;
   if (s->cfg.tile_mode) {
     // invariant: ggrid_v is zero on the active bricks (k_grid_grad_b clears what it consumes)
-    if (!s->grid_ckpt) {  // no room for grid checkpoints: re-run scatter and grid update like the reference does
+    BrickCk none = {nullptr, nullptr, nullptr, 0, nullptr};
+    if (s->brick_ckpt) {  // v_out of this substep back into the dense working grid, unless the substep above has already done it
+      if (restore_here) {
+        launch_hot(s, k_restore_bricks, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->bck(f).v, s->bck(f).n, s->grid_v);
+        s->launches += 1;
+      }
+    } else if (!s->grid_ckpt) {  // no grid checkpoints at all: re-run scatter and grid update like the reference does
       launch_hot(s, k_p2g_tile<SVD, false>, s->tile_blocks(s->pb_p2g, s->w_p2g), 32 * s->w_p2g, s->w_p2g * kSmemP2G, st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->grid, s->counters + 4);
-      launch_hot(s, k_grid_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->grid, s->grid_v, s->tables(f), nullptr, 0);
+      launch_hot(s, k_grid_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->grid, s->grid_v, s->tables(f), nullptr, 0, none);
     }
     launch_hot(s, k_g2p_grad_tile, s->tile_blocks(s->pb_g2pg, s->w_g2pg), 32 * s->w_g2pg, s->w_g2pg * kSmemG2PG, st, kp, sg.view(), cur, nxt, s->GV(f), gin, gout, s->ggrid_v, s->counters + 4);
     mark(mk, "g2p_grad_tile");
-    launch_hot(s, k_grid_grad_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt ? 0 : 1);
+    launch_hot(s, k_grid_grad_b, s->brick_blocks(), kT, 0, st, kp, sg.cnt, sg.active, s->G(f), s->ggrid_v, s->ggrid, s->tables(f), gp, gr, gnp, gnr, s->grid_ckpt || s->brick_ckpt ? 0 : 1,
+               s->bck(f), restore_below ? s->bck(f - 1) : none, s->grid_v);
     mark(mk, "grid_grad_b");
     if (s->p2gg_tiled) launch_hot(s, k_p2g_grad_tile<SVD>, s->tile_blocks(s->pb_p2gg, s->w_p2gg), 32 * s->w_p2gg, s->w_p2gg * (SVD == 1 ? kSmemP2GG : kSmemG2P), st, kp, sg.view(), cur, nxt, sg.mat0, sg.yield, s->ggrid, gin, gout, s->counters + 4);
     else k_p2g_grad<SVD><<<nblk(kp.EN), kT, 0, st>>>(kp, s->spos, cur, nxt, sg.mat0, sg.yield, s->ggrid, gin, gout);
@@ -2319,10 +2425,23 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
     size_t need = sizeof(float4) * eg * 2 * (size_t)cfg->max_steps, fr = 0, tot = 0;
     cudaMemGetInfo(&fr, &tot);
     bool want = cfg->grid_ckpt != 0;
-    if (want && need < (size_t)(0.6 * (double)fr)) {
+    DD_ALLOC(s->status, sizeof(int) * 4);
+    if (want && cfg->grid_ckpt != 2 && need < (size_t)(0.6 * (double)fr)) {
       s->grid_ckpt = true;
       DD_ALLOC(s->gridck, sizeof(float4) * eg * (size_t)cfg->max_steps);
       DD_ALLOC(s->gridvck, sizeof(float4) * eg * (size_t)cfg->max_steps);
+    } else if (want) {
+      // brick checkpoints: a fixed number of bricks per substep out of a fifth of the free memory (2 KB per brick and substep)
+      size_t per_brick = sizeof(float4) * 64 * 2 * (size_t)cfg->max_steps;
+      size_t cap = std::min<size_t>((size_t)s->NBtot, (size_t)(0.2 * (double)fr) / per_brick);
+      if (const char *e = getenv("DD_BRICK_CAP")) cap = std::min<size_t>(cap, (size_t)std::max(1, atoi(e)));  // (tests: force the overflow report)
+      if (cap >= 8) {
+        s->brick_ckpt = true;
+        s->brick_cap = (int)cap;
+        DD_ALLOC(s->brick_m, sizeof(float4) * 64 * cap * (size_t)cfg->max_steps);
+        DD_ALLOC(s->brick_v, sizeof(float4) * 64 * cap * (size_t)cfg->max_steps);
+        DD_ALLOC(s->brick_n, sizeof(int) * (size_t)cfg->max_steps);
+      }
     }
   }
   for (int k = 0; k < nseg; ++k) {
@@ -2355,7 +2474,7 @@ void dd_sim_destroy(dd_sim *s) {
   void *ptrs[] = {s->ckpt, s->grad[0], s->grad[1], s->gtmp, s->grid, s->grid_v, s->ggrid_v, s->ggrid, s->pos, s->rot, s->gpos, s->grot,
                   s->tfsr, s->args, s->cull, s->stage, s->keys, s->keys_alt, s->iota, s->sorted_idx, s->stor_idx, s->perm_tmp, s->cub_tmp, s->mat_aos,
                   s->chunks_tmp, s->chunk_src_tmp, s->chunk_src, s->chunk_sort, s->csort_tmp, s->head_pos, s->spos, s->head_flags, s->counters, s->sel_tmp,
-                  s->perm_pool, s->from_pool, s->mat0_pool, s->yield_pool, s->cnt_pool, s->chunks_pool, s->active_pool, s->flags_pool, s->gridck, s->gridvck};
+                  s->perm_pool, s->from_pool, s->mat0_pool, s->yield_pool, s->cnt_pool, s->chunks_pool, s->active_pool, s->flags_pool, s->gridck, s->gridvck, s->brick_m, s->brick_v, s->brick_n, s->status};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -2609,7 +2728,9 @@ int dd_sim_backward(dd_sim *s, int f0, int n, cudaStream_t st) {
   auto body = [&](cudaStream_t q) {
     for (int f = ft - 1; f >= f0; --f) {
       if (s->is_boundary(f + 1) && (f + 1 < ft || permute_top)) enqueue_grad_permute(s, s->seg_of(f + 1), (f + 1) & 1, q);
-      if (s->cfg.svd_mode == 0) enqueue_backward_substep<0>(s, f, q); else enqueue_backward_substep<1>(s, f, q);
+      // brick checkpoints: substep f restores v_out of substep f-1 on its way when both use the same active list
+      bool here = f == ft - 1 || s->seg_of(f) != s->seg_of(f + 1), below = s->brick_ckpt && f > f0 && s->seg_of(f - 1) == s->seg_of(f);
+      if (s->cfg.svd_mode == 0) enqueue_backward_substep<0>(s, f, q, nullptr, here, below); else enqueue_backward_substep<1>(s, f, q, nullptr, here, below);
     }
   };
   int rc = run_graphed(s, 1, f0, n, permute_top ? 1 : 0, st, body);
@@ -2654,6 +2775,7 @@ int dd_sim_add_pose_grads(dd_sim *s, int f, const float *gpos, const float *grot
   return 0;
 }
 
+// (a device destination is written directly; anything else goes through the staging buffer)
 int dd_sim_compute_dist(dd_sim *s, int f, float *dist, cudaStream_t st) {
   if (check_range(s, f, 0, "dd_sim_compute_dist")) return 1;
   if (s->kp.nb == 0) return 0;
@@ -2661,10 +2783,14 @@ int dd_sim_compute_dist(dd_sim *s, int f, float *dist, cudaStream_t st) {
   int p = 0, k = 0;
   if (pick_copy(s, f, &p, &k, "dd_sim_compute_dist")) return 1;
   size_t n = (size_t)s->kp.EN * s->kp.nb;
-  k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->tables(f), s->stage, nullptr, nullptr, nullptr, nullptr, 0);
+  const bool direct = on_device(dist);
+  if (!direct && n > s->stage_floats) return fail("dd_sim_compute_dist: too many bodies for the staging buffer; pass a device pointer");
+  k_obs<false><<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->tables(f), direct ? dist : s->stage, s->kp.nb);
   DD_CUDA(cudaGetLastError());
-  DD_CUDA(cudaMemcpyAsync(dist, s->stage, sizeof(float) * n, cudaMemcpyDefault, st));
-  if (finish_readback(st, {dist})) return 1;
+  if (!direct) {
+    DD_CUDA(cudaMemcpyAsync(dist, s->stage, sizeof(float) * n, cudaMemcpyDefault, st));
+    DD_CUDA(cudaStreamSynchronize(st));
+  }
   return 0;
 }
 
@@ -2676,9 +2802,39 @@ int dd_sim_compute_dist_grad(dd_sim *s, int f, const float *dist_grad, cudaStrea
   if (grad_copy(s, f, &p, &k, "dd_sim_compute_dist_grad")) return 1;
   if (!s->valid(p)) return fail("dd_sim_compute_dist_grad: state " + std::to_string(f) + " is not available");
   size_t n = (size_t)s->kp.EN * s->kp.nb, ep = (size_t)s->kp.E * s->kp.nb;
-  DD_CUDA(cudaMemcpyAsync(s->stage, dist_grad, sizeof(float) * n, cudaMemcpyDefault, st));
-  k_dist<<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->tables(f), nullptr, s->stage, s->grad[f & 1], s->gpos + (size_t)f * ep,
-                                        s->grot + (size_t)f * ep, 1);
+  const bool direct = on_device(dist_grad);
+  if (!direct) {
+    if (n > s->stage_floats) return fail("dd_sim_compute_dist_grad: too many bodies for the staging buffer; pass a device pointer");
+    DD_CUDA(cudaMemcpyAsync(s->stage, dist_grad, sizeof(float) * n, cudaMemcpyDefault, st));
+  }
+  k_obs_grad<false><<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->tables(f), direct ? dist_grad : s->stage, s->kp.nb, s->grad[f & 1],
+                                                   s->gpos + (size_t)f * ep, s->grot + (size_t)f * ep);
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// The particle observation of GradModel.get_obs (mpm/torch_wrapper.py:46-66) in one kernel: obs (E, N, 6 + nb) = [x | v | dist]
+// in the caller's particle order, written straight into DEVICE memory (no staging, no concatenation).
+int dd_sim_get_obs(dd_sim *s, int f, float *obs, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_get_obs")) return 1;
+  if (!obs || !on_device(obs)) return fail("dd_sim_get_obs: obs must be a device pointer (host callers: dd_sim_get_state + dd_sim_compute_dist)");
+  int p = 0, k = 0;
+  if (pick_copy(s, f, &p, &k, "dd_sim_get_obs")) return 1;
+  k_obs<true><<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->tables(f), obs, 6 + s->kp.nb);
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+// Its adjoint (GradModel.set_obs_grad, mpm/torch_wrapper.py:68-105): gobs[..., :3] and [..., 3:6] are added to the gradients of x
+// and v of state f, gobs[..., 6:] is back-propagated through the signed distances into x and the pose gradients of state f.
+int dd_sim_add_obs_grad(dd_sim *s, int f, const float *gobs, cudaStream_t st) {
+  if (check_range(s, f, 0, "dd_sim_add_obs_grad")) return 1;
+  if (!gobs || !on_device(gobs)) return fail("dd_sim_add_obs_grad: gobs must be a device pointer (host callers: dd_sim_add_state_grad + dd_sim_compute_dist_grad)");
+  int p = 0, k = 0;
+  if (grad_copy(s, f, &p, &k, "dd_sim_add_obs_grad")) return 1;
+  if (!s->valid(p)) return fail("dd_sim_add_obs_grad: state " + std::to_string(f) + " is not available");
+  size_t ep = (size_t)s->kp.E * s->kp.nb;
+  k_obs_grad<true><<<nblk(s->kp.EN), kT, 0, st>>>(s->kp, s->segs[k].perm, s->pslot(p), s->tables(f), gobs, 6 + s->kp.nb, s->grad[f & 1],
+                                                  s->gpos + (size_t)f * ep, s->grot + (size_t)f * ep);
   DD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -2774,7 +2930,14 @@ int dd_sim_segment_info(dd_sim *s, int f, int *out, cudaStream_t st) {
 
 int dd_sim_sync(dd_sim *s, cudaStream_t st) {
   if (!s) return fail("dd_sim_sync: null simulator");
+  int status = 0;
+  if (s->status) DD_CUDA(cudaMemcpyAsync(&status, s->status, sizeof(int), cudaMemcpyDeviceToHost, st));
   DD_CUDA(cudaStreamSynchronize(st));
+  if (status & 1) {
+    DD_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));
+    return fail("dd_sim_sync: a substep had more active bricks than the brick checkpoints hold (" + std::to_string(s->brick_cap) +
+                " per substep): gradients computed since the last sync are invalid; create the simulator with grid_ckpt = 0 (replay) or fewer max_steps");
+  }
   return 0;
 }
 

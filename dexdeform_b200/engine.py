@@ -41,7 +41,7 @@ class FusedSim:
         self.stream = stream  # raw cudaStream_t (int) or None for the legacy default stream
         cfg = dd_sim_config(self.E, self.N, self.nb, *self.grid_dim, self.max_steps, self.dx, self.dt, float(ground_friction),
                             float(ground_height), (ctypes.c_float * 3)(*[float(g) for g in gravity]), int(svd_mode), int(bool(use_graphs)),
-                            int(bool(sort_particles)), int(bool(tile_mode)), int(bool(grid_ckpt)), int(chunk_max), int(resort_interval))
+                            int(bool(sort_particles)), int(bool(tile_mode)), int(grid_ckpt), int(chunk_max), int(resort_interval))
         handle = ctypes.c_void_p()
         self._h = None
         self._check(self.lib.dd_sim_create(ctypes.byref(cfg), ctypes.byref(handle)))
@@ -94,10 +94,15 @@ class FusedSim:
         tfsr, args = np.ascontiguousarray(tfsr, np.float32), np.ascontiguousarray(args, np.float32)
         self._check(self.lib.dd_sim_set_bodies(self._h, _ptr(tfsr), _ptr(args)))
 
-    def set_state(self, f, x, v, F, C):
-        """(E, N, 3|9) arrays in the caller's particle order.  Starts a new particle order (cell sort) for f's segment."""
+    def set_state(self, f, x, v, F, C, non_blocking=False):
+        """(E, N, 3|9) arrays in the caller's particle order.  Starts a new particle order (cell sort) for f's segment.
+        ``non_blocking`` (pinned host tensors only, torch's ``copy_(non_blocking=True)`` contract): do not wait for the uploads --
+        the caller keeps the buffers alive and unchanged until the stream has passed them, and the host goes on enqueueing work
+        (kinematics, the substeps) while the copies run."""
         self._check(self.lib.dd_sim_set_state(self._h, f, _ptr(x), _ptr(v), _ptr(F), _ptr(C), self.stream))
         if _is_host(x, v, F, C):
+            if non_blocking and all(hasattr(a, "is_pinned") and a.is_pinned() for a in (x, v, F, C)):
+                return
             self.sync()  # host arrays may be released by the caller
 
     def roll(self, f_src):
@@ -190,6 +195,16 @@ class FusedSim:
         self._check(self.lib.dd_sim_compute_dist_grad(self._h, f, _ptr(dist_grad), self.stream))
         if _is_host(dist_grad):
             self.sync()
+
+    def get_obs(self, f):
+        """Particle observation of state f as one CUDA tensor (E, N, 6 + nb) = [x | v | dist] (mpm/torch_wrapper.py:46-66)."""
+        obs = self._empty((self.E, self.N, 6 + self.nb), True)
+        self._check(self.lib.dd_sim_get_obs(self._h, f, _ptr(obs), self.stream))
+        return obs
+
+    def add_obs_grad(self, f, gobs):
+        """Adjoint of get_obs: gobs is a contiguous CUDA tensor (E, N, 6 + nb) (mpm/torch_wrapper.py:68-105)."""
+        self._check(self.lib.dd_sim_add_obs_grad(self._h, f, _ptr(gobs), self.stream))
 
     def profile_substep(self, f, reps=5):
         """[(kernel label, ms)] for one forward + backward substep (needs a gradient seeded for state f+1)."""

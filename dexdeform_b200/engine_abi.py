@@ -35,6 +35,8 @@ ABI2 = {
     "dd_sim_add_pose_grads": (c_int, [P, c_int, P, P, S]),
     "dd_sim_compute_dist": (c_int, [P, c_int, P, S]),
     "dd_sim_compute_dist_grad": (c_int, [P, c_int, P, S]),
+    "dd_sim_get_obs": (c_int, [P, c_int, P, S]),
+    "dd_sim_add_obs_grad": (c_int, [P, c_int, P, S]),
     "dd_sim_compute_grid_mass": (c_int, [P, c_int, P, c_int, P, S]),
     "dd_sim_compute_grid_mass_grad": (c_int, [P, c_int, P, c_int, P, S]),
     "dd_sim_sync": (c_int, [P, S]),

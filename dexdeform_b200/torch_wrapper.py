@@ -95,14 +95,19 @@ class GradModel:
             return s * self.sim.substeps
         eng, S = self.sim.engine, self.sim.substeps
         if self._resident is not None and s == self._resident + 1:
+            self._save_boundary(self._resident)           # (saved only now: the last window of a rollout never needs a copy)
             eng.roll(S)                                   # state and poses of slot S become slot 0, re-sorted on the device
         elif not (self._resident is None and s == 0) and self._resident != s:
             raise RuntimeError("windowed GradModel: env steps must be run in order")
+        self._resident = s
+        return 0
+
+    def _save_boundary(self, s):
+        """Keep the first state of window ``s`` (slot 0) before the window is replaced: the backward pass restarts from it."""
+        eng = self.sim.engine
         st = eng.get_state(0, device=True)
         pos, rot = eng.get_poses(0, 1, device=True)
         self._boundary[s] = (st["x"], st["v"], st["F"], st["C"], pos, rot)
-        self._resident = s
-        return 0
 
     def _window_backward(self, s, replay):
         """Before the adjoint of env step ``s``: its checkpoints are in the simulator (re-running the forward substeps from the
@@ -111,6 +116,8 @@ class GradModel:
             return s * self.sim.substeps
         eng, S = self.sim.engine, self.sim.substeps
         if self._resident != s:
+            if self._resident is not None and self._resident not in self._boundary:
+                self._save_boundary(self._resident)       # (a second backward pass over the same rollout may come back to it)
             x, v, F, C, pos, rot = self._boundary[s]
             eng.set_state(0, x, v, F, C)
             eng.set_poses(0, pos, rot)
@@ -129,6 +136,9 @@ class GradModel:
     def _window_backward_done(self, s):
         if not self.windowed:
             return
+        if s == 0:   # no window below: the gradient of the rollout's first state stays in the simulator (get_state_grad(0))
+            self._carry = None
+            return
         eng = self.sim.engine
         gp, gr = eng.get_pose_grads(0, 1, device=True)
         self._carry = (s, eng.get_state_grad(0, device=True), gp, gr)
@@ -136,15 +146,12 @@ class GradModel:
     def get_obs(self, s, device):
         sim, eng = self.sim, self.sim.engine
         f = self._slot(s)
-        st = eng.get_state(f, ("x", "v"), device=True)
-        parts = [st["x"], st["v"]]
         if sim.n_bodies:
-            parts.append(eng.compute_dist(f, device=True))
             pos, rot = eng.get_poses(f, 1, device=True)
             tool = torch.cat((pos[0], rot[0]), -1)
         else:
             tool = torch.zeros((sim.n_envs, 0, 7), device="cuda")
-        outputs = [self._squeeze(torch.cat(parts, -1)).to(device), self._squeeze(tool).to(device)]
+        outputs = [self._squeeze(eng.get_obs(f)).to(device), self._squeeze(tool).to(device)]   # [x | v | dist] in one kernel
         for i in self.return_grid:
             outputs.append(sim.compute_grid_mass(f, i, device=device))
         return tuple(outputs)
@@ -163,10 +170,7 @@ class GradModel:
             if idx < len(args) and args[idx] is not None:
                 sim.compute_grid_mass(f, i, backward_grad=args[idx])
         E, n, nb = sim.n_envs, sim.n_particles, sim.n_bodies
-        pg = particle_grad.detach().to("cuda", torch.float32).reshape(E, n, 6 + nb)
-        if nb:
-            eng.compute_dist_grad(f, pg[..., 6:].contiguous())
-        eng.add_state_grad(f, gx=pg[..., :3].contiguous(), gv=pg[..., 3:6].contiguous())
+        eng.add_obs_grad(f, particle_grad.detach().to("cuda", torch.float32).reshape(E, n, 6 + nb).contiguous())
         if nb:
             c = tool_grad.detach().to("cuda", torch.float32).reshape(E, nb, 7)
             eng.add_pose_grads(f, gpos=c[..., :3].contiguous(), grot=c[..., 3:].contiguous())

@@ -136,7 +136,9 @@ typedef struct {
   int use_graphs;      /* capture forward/backward ranges into CUDA graphs, cached per (f0, n) */
   int sort_particles;  /* dd_sim_set_state re-orders particles by (env, 4^3-cell brick, cell); results are returned in the caller's order */
   int tile_mode;       /* 1: warp-private shared-memory tiles for the scatters + grid kernels on active bricks only; 0: global reductions on the dense grid */
-  int grid_ckpt;       /* 1: keep every substep's grid in HBM when it fits, so the adjoint does not replay scatter + grid update */
+  int grid_ckpt;       /* grids for the adjoint, so that it does not replay scatter + grid update: 0 none (replay); 1 one dense grid pair per
+                          substep when that fits in HBM, else the ACTIVE bricks of every substep only ("brick checkpoints", a fixed
+                          number of bricks per substep; dd_sim_sync reports a substep that needed more); 2 brick checkpoints always */
   int chunk_max;       /* particles per warp-chunk in tile mode (0 = choose from the problem size) */
   int resort_interval; /* tile mode: re-sort the particles on the device every this many substeps inside dd_sim_forward (0 = only in
                           dd_sim_set_state).  States at multiples of the interval are stored in both orders; the adjoint permutes
@@ -165,6 +167,11 @@ int dd_sim_get_pose_grads(dd_sim *sim, int f0, int count, float *gpos, float *gr
 int dd_sim_add_pose_grads(dd_sim *sim, int f, const float *gpos, const float *grot, cudaStream_t stream);
 int dd_sim_compute_dist(dd_sim *sim, int f, float *dist, cudaStream_t stream);   /* (E, N, nb) */
 int dd_sim_compute_dist_grad(dd_sim *sim, int f, const float *dist_grad, cudaStream_t stream);
+/* GradModel.get_obs / set_obs_grad (mpm/torch_wrapper.py:46-105) without the host round trip and the concatenation: obs and gobs are
+ * DEVICE arrays (E, N, 6 + nb) = [x | v | dist] in the caller's particle order.  dd_sim_add_obs_grad adds gobs[..., :6] to the gradient
+ * of (x, v) of state f and back-propagates gobs[..., 6:] through the signed distances (into x and the pose gradients of state f). */
+int dd_sim_get_obs(dd_sim *sim, int f, float *obs, cudaStream_t stream);
+int dd_sim_add_obs_grad(dd_sim *sim, int f, const float *gobs, cudaStream_t stream);
 /* density-grid observation of object `id` (-1: all particles) and its adjoint; ids (E*N ints, original order) may be NULL for id == -1 */
 int dd_sim_compute_grid_mass(dd_sim *sim, int f, const int *ids, int id, float *out, cudaStream_t stream);
 int dd_sim_compute_grid_mass_grad(dd_sim *sim, int f, const int *ids, int id, const float *grid_m_grad, cudaStream_t stream);

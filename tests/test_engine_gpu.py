@@ -153,6 +153,37 @@ def test_engine_vs_oracle_and_env_batching(oracle_lib):
     dist = array(dtype=float32, length=1200 * 5, library=oracle_lib)
     a1.compute_dist(a1.states[S], dist, dist, 0)
     assert np.abs(d[1] - dist.download().reshape(1200, 5)).max() < 2e-6
+    # fused observation [x | v | dist] and its adjoint (dd_sim_get_obs / dd_sim_add_obs_grad): bit-identical to the parts, adjoint against
+    # the oracle.  1200 particles per environment: blocks and warps straddle environments; body 1 and a range of particles receive
+    # exact zeros (the skipped paths of k_obs_grad).
+    import torch
+    obs = sim.get_obs(S).cpu().numpy()
+    assert np.array_equal(obs[..., :3], state["x"]) and np.array_equal(obs[..., 3:6], state["v"]) and np.array_equal(obs[..., 6:], d)
+    rng = np.random.default_rng(5)
+    gobs = np.float32(rng.normal(size=(E, 1200, 11)))
+    gobs[:, :, 6 + 1] = 0.0
+    gobs[:, 300:900, 6:] = 0.0
+    sim.zero_grad(S)
+    sim.add_obs_grad(S, torch.tensor(gobs, device="cuda"))
+    g = sim.get_state_grad(S, ("x", "v"))
+    gp, gr = sim.get_pose_grads(S, 1)
+    dg = array(dtype=float32, length=1200 * 5, library=oracle_lib)
+    dg.upload(np.ascontiguousarray(gobs[1, :, 6:]).reshape(-1))
+    for k in ("x_grad", "body_pos_grad", "body_rot_grad"):
+        a1.states[S][k].zero(a1.stream)
+    a1.compute_dist(a1.states[S], dist, dg, 1)
+    ref = a1.get(S, "x_grad", "body_pos_grad", "body_rot_grad")
+    assert np.abs(g["x"][1] - (ref["x_grad"] + gobs[1, :, :3])).max() < 1e-5
+    assert np.array_equal(g["v"][1], gobs[1, :, 3:6])
+    assert np.abs(gp[0, 1] - ref["body_pos_grad"]).max() < 2e-4 * max(1.0, np.abs(ref["body_pos_grad"]).max())
+    assert np.abs(gr[0, 1] - ref["body_rot_grad"]).max() < 2e-4 * max(1.0, np.abs(ref["body_rot_grad"]).max())
+    assert np.all(gp[0, :, 1] == 0.0) and np.all(gr[0, :, 1] == 0.0)
+    # the separate entry points share the kernel: same numbers
+    sim.zero_grad(S)
+    sim.add_state_grad(S, gx=np.ascontiguousarray(gobs[..., :3]), gv=np.ascontiguousarray(gobs[..., 3:6]))
+    sim.compute_dist_grad(S, np.ascontiguousarray(gobs[..., 6:]))
+    g2 = sim.get_state_grad(S, ("x", "v"))
+    assert np.abs(g2["x"] - g["x"]).max() < 1e-6 and np.array_equal(g2["v"], g["v"])
     sim.close()
 
 
@@ -303,6 +334,40 @@ def test_recompute_mode_matches_checkpoint_mode():
     for k in ("x", "v", "F", "C"):
         assert_close_rows(b["grad"][k][0], a["grad"][k][0], 1e-4, k + "_grad")
     assert a["launches"] == 6 * S + 1 and b["launches"] == 8 * S + 1
+
+
+@pytest.mark.parametrize("interval,graphs,E", [(0, True, 1), (4, True, 2), (5, False, 1)])
+def test_brick_checkpoints_match_dense_grid_checkpoints(interval, graphs, E):
+    """grid_ckpt=2: (mv, m) and v_out of the active bricks only, per substep (what a 64-environment, 400-substep rollout can afford)
+    against one dense grid pair per substep: same forward, and an adjoint that differs only in the order of floating-point
+    reductions.  The block moves ~0.5 cells per substep, so bricks are activated on the fly inside a segment (the list the
+    checkpoints are indexed by grows) and, with an interval, the ordering changes in the middle of the backward sweep."""
+    S = 12
+    sc = make_scene(3000, 32, box_center=(0.4, 0.35, 0.5), box_width=(0.14, 0.1, 0.14), steps=S, perturb=0.02, nb=4, seed=17, ground_friction=0.3)
+    sc["v"][:] = np.array([160.0, -60.0, 90.0], np.float32) * (1.0 + 0.02 * np.random.default_rng(1).normal(size=(3000, 3)).astype(np.float32))
+    seedg = loss_seed(3000, 6)
+    a = run_engine(sc, S, seedg, E=E, use_graphs=graphs, resort_interval=interval, grid_ckpt=1)
+    b = run_engine(sc, S, seedg, E=E, use_graphs=graphs, resort_interval=interval, grid_ckpt=2)
+    nseg = (S + interval - 1) // interval if interval else 1
+    assert b["launches"] == a["launches"] + nseg   # one stand-alone restore per segment, everything else rides on the grid adjoint
+    for k in ("x", "v", "F", "C"):
+        assert rel_err(b["state"][k], a["state"][k]) < (1e-4 if k == "C" else 2e-5), k   # (same kernels; the order of the grid reductions varies from run to run)
+        assert_close_rows(b["grad"][k].reshape(-1, b["grad"][k].shape[-1]), a["grad"][k].reshape(-1, a["grad"][k].shape[-1]), 1e-3, k + "_grad")
+    # (12 substeps at half a cell per substep: two runs of the SAME configuration differ by ~1.5e-4 in the worst rows)
+    assert np.abs(b["gpos"] - a["gpos"]).max() < 2e-3 * max(np.abs(a["gpos"]).max(), 1.0)
+    assert np.abs(b["grot"] - a["grot"]).max() < 2e-3 * max(np.abs(a["grot"]).max(), 1.0)
+
+
+def test_brick_checkpoint_overflow_is_reported(monkeypatch):
+    monkeypatch.setenv("DD_BRICK_CAP", "8")
+    S = 2
+    sc = make_scene(3000, 32, box_width=(0.2, 0.2, 0.2), steps=S, perturb=0.02, on_floor=True, seed=3, nb=2)
+    sim = FusedSim.from_scene(sc, max_steps=S, grid_ckpt=2)
+    sim.forward(0, S)
+    with pytest.raises(EngineError, match="more active bricks"):
+        sim.sync()
+    sim.sync()   # reported once
+    sim.close()
 
 
 @pytest.mark.parametrize("n,E,chunk_max", [(4, 1, 32), (36, 2, 32), (1000, 3, 32), (5000, 1, 96), (5000, 2, 0)])
