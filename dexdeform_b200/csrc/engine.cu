@@ -48,7 +48,7 @@ constexpr int kT = 256;
 #define DD_LB_P2G_TILE 5
 #endif
 #ifndef DD_LB_G2PG_TILE
-#define DD_LB_G2PG_TILE 4
+#define DD_LB_G2PG_TILE 3
 #endif
 #ifndef DD_LB_G2PG_SCATTER
 #define DD_LB_G2PG_SCATTER 6
@@ -57,7 +57,7 @@ constexpr int kT = 256;
 #define DD_LB_G2P_TILE 5
 #endif
 #ifndef DD_LB_P2GG_TILE
-#define DD_LB_P2GG_TILE 4
+#define DD_LB_P2GG_TILE 3
 #endif
 #ifndef DD_LB_P2G_GRAD
 #define DD_LB_P2G_GRAD 2
