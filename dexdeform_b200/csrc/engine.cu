@@ -45,7 +45,7 @@ int fail(const std::string &msg) { g_last_error = msg; return 1; }
 constexpr int kT = 256;
 // occupancy knobs (min resident blocks per SM) -- tuned with ncu, see profiles/
 #ifndef DD_LB_P2G_TILE
-#define DD_LB_P2G_TILE 5
+#define DD_LB_P2G_TILE 4
 #endif
 #ifndef DD_LB_G2PG_TILE
 #define DD_LB_G2PG_TILE 3
@@ -134,6 +134,11 @@ DD_DEV float4 lds_v4_if(unsigned a, bool pred) {
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4]; }" : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w) : "r"(a), "r"((int)pred) DD_TILE_CLOBBER);
   return r;
+}
+// Same, into a register quadruple the caller carries from update to update: lanes whose predicate is false keep whatever they
+// had (finite garbage that is never stored), so no zero-initialisation is issued per update (three instructions of sixteen).
+DD_DEV void lds_v4_into(float4 &r, unsigned a, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4]; }" : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w) : "r"(a), "r"((int)pred) DD_TILE_CLOBBER);
 }
 DD_DEV void sts_v4_if(unsigned a, float4 v, bool pred) {
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.volatile.shared.v4.f32 [%0], {%1,%2,%3,%4}; }" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) DD_TILE_CLOBBER);
@@ -633,7 +638,7 @@ constexpr int kStageP2GG = 16;       // p2g_grad_tile (slots listed at P2ggStage
 constexpr int kQueueF4 = 8;          // deferred-lane queue: 32 ints per warp (DeferQueue)
 constexpr size_t kSmemP2G = (kTileN + kStageP2G * 32 + kQueueF4) * sizeof(float4);        // bytes per warp
 constexpr size_t kSmemG2PG = (2 * kTileN + kStageG2PG * 32 + kQueueF4) * sizeof(float4);
-constexpr size_t kSmemG2P = kTileN * sizeof(float4);
+constexpr size_t kSmemG2P = (kTileN + 32) * sizeof(float4);  // tile + one staged position per lane
 constexpr size_t kSmemP2GG = (kTileN + kStageP2GG * 32) * sizeof(float4);                 // fp32-SVD variant; the fp64 variant does not stage
 // a chunk is stored as R rows of 32 particles (the last row holds the remaining `last`); row j starts at start + 32 j
 struct ChunkGeom { int env, ox, oy, oz, start, cnt, R, last, bx, by, bz; unsigned lastmask; };
@@ -680,16 +685,24 @@ DD_DEV void cp_async4(float *smem_dst, const void *gsrc) {
 }
 DD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 DD_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// fill the 8^3 tile from a dense grid (swizzled slots); out-of-grid nodes read as zero
-DD_DEV void fill_tile(float4 *tile, const float4 *__restrict__ grid_env, const KP &kp, int ox, int oy, int oz, int lane, float4 *zero_too = nullptr) {
-  for (int n = lane; n < kTileN; n += 32) {
+// Fill of the 8^3 tile from a dense grid (swizzled slots) with asynchronous copies: no registers, all 16 copies of a lane in
+// flight at once; out-of-grid nodes are zero-filled by a copy of source size 0.  The caller waits for the group
+// (cp_async_wait_all + __syncwarp) before the first read.
+DD_DEV void cp_async16_zfill(float4 *smem_dst, const void *gsrc, unsigned src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+DD_DEV void fill_tile_async(float4 *tile, const float4 *__restrict__ grid_env, const KP &kp, int ox, int oy, int oz, int lane, float4 *zero_too = nullptr) {
+#pragma unroll
+  for (int n0 = 0; n0 < kTileN; n0 += 32) {
+    int n = n0 + lane;
     int txx = n >> 6, tyy = (n >> 3) & 7, tzz = n & 7;
     int nx = ox + txx, ny = oy + tyy, nz = oz + tzz;
     bool ok = (unsigned)nx < (unsigned)kp.gx && (unsigned)ny < (unsigned)kp.gy && (unsigned)nz < (unsigned)kp.gz;
     int slot = tile_slot(txx, tyy, tzz);
-    tile[slot] = ok ? __ldg(grid_env + (nx * kp.gy + ny) * kp.gz + nz) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cp_async16_zfill(tile + slot, ok ? grid_env + (nx * kp.gy + ny) * kp.gz + nz : grid_env, ok ? 16u : 0u);
     if (zero_too) zero_too[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  cp_async_commit();
 }
 // Persistent chunk loop of the tiled kernels: every warp pulls chunk indices from a ticket counter until the list is
 // drained, so a launch never ends with a nearly empty last wave.  sched[0] = next ticket, sched[1] = warps that have
@@ -699,6 +712,13 @@ DD_DEV int next_chunk(int *sched, int lane) {
   if (lane == 0) c = atomicAdd(sched, 1);
   return __shfl_sync(0xffffffffu, c, 0);
 }
+// A launch with no more chunks than warps needs no tickets at all: warp w takes list entry w.  (Small scenes: the atomic round
+// trip in front of a warp's only chunk was 4-10 % of the stall samples; 10k particles: 83 -> 95 M particle-substeps/s.  With
+// more chunks than warps the ticket for the first chunk stays: whichever warp is up first takes the largest chunk.)
+#define DD_CHUNK_LOOP(ci) \
+  const int gw_ = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); \
+  const bool few_ = nchunks <= (int)(gridDim.x * (blockDim.x >> 5)); \
+  for (int ci = few_ ? gw_ : next_chunk(sched, lane); ci < nchunks; ci = few_ ? nchunks : next_chunk(sched, lane))
 DD_DEV void chunks_done(int *sched, int lane) {
   if (lane == 0 && atomicAdd(sched + 1, 1) == (int)(gridDim.x * (blockDim.x >> 5)) - 1) { sched[0] = 0; sched[1] = 0; }
 }
@@ -960,6 +980,9 @@ __global__ void __launch_bounds__(kT, DD_LB_P2G_GRAD) k_p2g_grad(KP kp, const in
 // positions go to a small per-warp queue, and whenever 32 are waiting (and at the end of the kernel) every lane takes one,
 // reads its inputs back and sends its 27 contributions straight to the grid.  Half a percent of the particles collide after
 // a fresh sort, but a quarter of the rows hold one of them.
+#ifdef DD_COUNT_DEFER
+__device__ unsigned long long g_defer_count[2];  // (diagnostic build) deferred lanes, rows with a deferred lane
+#endif
 struct DeferQueue {
   int *slots;  // 32 ints of shared memory, private to the warp
   int n;       // warp-uniform
@@ -967,7 +990,13 @@ struct DeferQueue {
   DD_DEV void push(bool defer, int p, int lane, Flush flush) {
     unsigned dm = __ballot_sync(0xffffffffu, defer);
     if (dm == 0u) return;
+#ifdef DD_DROP_DEFERRED
+    return;  // (diagnostic build, WRONG results: what the direct path of the deferred lanes costs)
+#endif
     int k = __popc(dm);
+#ifdef DD_COUNT_DEFER
+    if (lane == 0) { atomicAdd(&g_defer_count[0], (unsigned long long)k); atomicAdd(&g_defer_count[1], 1ull); }
+#endif
     if (n + k > 32) flush();
     if (defer) slots[n + __popc(dm & ((1u << lane) - 1u))] = p;
     n += k;
@@ -1033,7 +1062,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     dq.n = 0;
   };
   // (no look-ahead across chunks: a warp that holds a chunk in reserve lengthens the tail of the launch -- measured)
-  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+  DD_CHUNK_LOOP(ci) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   stage_row(row_pos(cg, 0, lane));
   unsigned amask = chunk_active_mask(sg.flags, cg, kp, lane);
@@ -1069,27 +1098,80 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2G_TILE) k_p2g_tile(KP
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
-    bool mine = in_tile && (peers & ((1u << lane) - 1u)) == 0u;  // lowest lane of its cell in this row
+    const unsigned lower = peers & ((1u << lane) - 1u);
+    bool mine = in_tile && lower == 0u;  // lowest lane of its cell in this row
+    // Two lanes of a row in the same cell (dense scenes: fewer occupied cells in a brick than lanes; 3 % of the particles at
+    // config D, 12-16 % at 50 particles per cell): the SECOND lane of a cell does not go to the deferred queue -- its owner lane
+    // fetches its scatter parameters (22 shuffles, only in rows that have such a pair) and adds both contributions in one
+    // read-modify-write.  Third and further lanes of a cell, and lanes outside the tile, are deferred as before.
+    bool second = in_tile && __popc(lower) == 1;
+    const unsigned higher = lane < 31 ? peers & ~((2u << lane) - 1u) : 0u;
+    const bool has_partner = mine && higher != 0u;
     if (!in_tile) { tx = ty = tz = 0; }
+#ifdef DD_NO_PAIRS
+    second = false;
+#endif
+    {
+      // byte address of the node at stencil offset (i, jj, k): row base + (i << 6 | jj << 3) * 16 (an immediate after unrolling)
+      // + the bank group rotated by 2 i + 4 jj + k; the eight rotations are formed once per row
+      const unsigned rowb = tbase + 16u * (unsigned)(tx << 6 | ty << 3);
+      const int g0 = tz + 4 * ty + 2 * tx;
+      unsigned rot[8];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      V3 vi = step_n(base, c0, i);
+      for (int r = 0; r < 8; ++r) rot[r] = rowb + (((unsigned)(g0 + r) & 7u) << 4);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef DD_NO_PAIRS
+      if (__any_sync(0xffffffffu, has_partner)) {
+        const int src = has_partner ? __ffs(higher) - 1 : lane;
+        auto get = [&](float v) { return __shfl_sync(0xffffffffu, v, src); };
+        V3 bB = v3(get(base.x), get(base.y), get(base.z)), c0B = v3(get(c0.x), get(c0.y), get(c0.z)), c1B = v3(get(c1.x), get(c1.y), get(c1.z)),
+           c2B = v3(get(c2.x), get(c2.y), get(c2.z));
+        float mB = get(m);
+        float wxB[3] = {get(wx[0]), get(wx[1]), get(wx[2])}, wyB[3] = {get(wy[0]), get(wy[1]), get(wy[2])}, wzB[3] = {get(wz[0]), get(wz[1]), get(wz[2])};
+        if (!has_partner) { wxB[0] = wxB[1] = wxB[2] = 0.f; }  // no partner: the second contribution is zero
 #pragma unroll
-      for (int jj = 0; jj < 3; ++jj) {
-        V3 vij = step_n(vi, c1, jj);
-        float wij = wx[i] * wy[jj];
+        for (int i = 0; i < 3; ++i) {
+          V3 vi = step_n(base, c0, i), viB = step_n(bB, c0B, i);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          V3 val = step_n(vij, c2, k);
-          float w = wij * wz[k];
-          unsigned a = tbase + 16u * (unsigned)tile_slot(tx + i, ty + jj, tz + k);
-          float4 t = lds_v4_if(a, mine);
-          t.x = fmaf(val.x, w, t.x); t.y = fmaf(val.y, w, t.y); t.z = fmaf(val.z, w, t.z); t.w = fmaf(m, w, t.w);
-          sts_v4_if(a, t, mine);
+          for (int jj = 0; jj < 3; ++jj) {
+            V3 vij = step_n(vi, c1, jj), vijB = step_n(viB, c1B, jj);
+            float wij = wx[i] * wy[jj], wijB = wxB[i] * wyB[jj];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              V3 val = step_n(vij, c2, k), valB = step_n(vijB, c2B, k);
+              float w = wij * wz[k], wB = wijB * wzB[k];
+              unsigned a = rot[(2 * i + 4 * jj + k) & 7] + 16u * (unsigned)(i << 6 | jj << 3);
+              lds_v4_into(t, a, mine);
+              t.x = fmaf(val.x, w, t.x); t.y = fmaf(val.y, w, t.y); t.z = fmaf(val.z, w, t.z); t.w = fmaf(m, w, t.w);
+              t.x = fmaf(valB.x, wB, t.x); t.y = fmaf(valB.y, wB, t.y); t.z = fmaf(valB.z, wB, t.z); t.w = fmaf(mB, wB, t.w);
+              sts_v4_if(a, t, mine);
+            }
+          }
+        }
+      } else
+#endif
+      {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          V3 vi = step_n(base, c0, i);
+#pragma unroll
+          for (int jj = 0; jj < 3; ++jj) {
+            V3 vij = step_n(vi, c1, jj);
+            float wij = wx[i] * wy[jj];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              V3 val = step_n(vij, c2, k);
+              float w = wij * wz[k];
+              unsigned a = rot[(2 * i + 4 * jj + k) & 7] + 16u * (unsigned)(i << 6 | jj << 3);
+              lds_v4_into(t, a, mine);
+              t.x = fmaf(val.x, w, t.x); t.y = fmaf(val.y, w, t.y); t.z = fmaf(val.z, w, t.z); t.w = fmaf(m, w, t.w);
+              sts_v4_if(a, t, mine);
+            }
+          }
         }
       }
     }
-    dq.push(act && !mine, p, lane, flush_queue);  // shares its cell with a lower lane of the row, or has left the tile
+    dq.push(act && !mine && !second, p, lane, flush_queue);  // third lane of a cell in this row, or has left the tile
   }
   __syncwarp();
   for (int n = lane; n < kTileN; n += 32) {  // flush, and leave the tile zeroed for the next chunk
@@ -1156,6 +1238,8 @@ __device__ __noinline__ void g2pg_direct(const KP &kp, int p, const float *__res
     }
   }
 }
+// (Measured and rejected, round 2: a block of two warps per chunk sharing the read-only velocity tile, each warp with its own
+// adjoint tile and every second row -- 14 instead of 11 warps per SM, but two flushes per chunk: 88 -> 92 us at config D.)
 __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_tile(KP kp, SegView sg, const float *__restrict__ cur,
                                                                       const float *__restrict__ nxt, const float4 *__restrict__ grid_v,
                                                                       const float *__restrict__ gin, float *__restrict__ gout,
@@ -1185,11 +1269,12 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     dq.n = 0;
   };
   // (no look-ahead across chunks: a warp that holds a chunk in reserve lengthens the tail of the launch -- measured)
-  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+  DD_CHUNK_LOOP(ci) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   stage_row(row_pos(cg, 0, lane));
   size_t goff = (size_t)cg.env * kp.G;
-  fill_tile(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
+  fill_tile_async(tv, grid_v + goff, kp, cg.ox, cg.oy, cg.oz, lane, tg);
+  cp_async_wait_all();
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
     bool act = lane_on(cg, j, lane);
@@ -1208,13 +1293,55 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
     bool in_tile = act && (unsigned)tx <= 5u && (unsigned)ty <= 5u && (unsigned)tz <= 5u;  // (every brick this stencil needs was activated by the forward pass)
     unsigned key = in_tile ? (unsigned)(tx << 6 | ty << 3 | tz) : 0x1000u + lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
-    bool mine = in_tile && (peers & ((1u << lane) - 1u)) == 0u;  // lowest lane of its cell in this row: scatters into the tile
+    const unsigned lower = peers & ((1u << lane) - 1u);
+    bool mine = in_tile && lower == 0u;  // lowest lane of its cell in this row: scatters into the tile
+    bool second = in_tile && __popc(lower) == 1;  // second lane of its cell: its owner adds its contribution (see k_p2g_tile)
+    const unsigned higher = lane < 31 ? peers & ~((2u << lane) - 1u) : 0u;
+    const bool has_partner = mine && higher != 0u;
+#ifdef DD_NO_PAIRS
+    second = false;
+#endif
     if (!in_tile) { tx = ty = tz = 0; }
     V3 gxs = vzero();
     const float4 *tvrow = tv + (tx << 6 | ty << 3);
     unsigned growb = gbase + 16u * (unsigned)(tx << 6 | ty << 3);
     int g0 = tz + 4 * ty + 2 * tx;
     // the gather half (read-only tile, every lane) and the scatter of the lanes that own their cell in this row
+#ifndef DD_NO_PAIRS
+    if (__any_sync(0xffffffffu, has_partner)) {
+      const int src = has_partner ? __ffs(higher) - 1 : lane;
+      auto get = [&](float v) { return __shfl_sync(0xffffffffu, v, src); };
+      V3 h0B = v3(get(h0.x), get(h0.y), get(h0.z)), H0B = v3(get(H0.x), get(H0.y), get(H0.z)), H1B = v3(get(H1.x), get(H1.y), get(H1.z)),
+         H2B = v3(get(H2.x), get(H2.y), get(H2.z));
+      float wxB[3] = {get(wx[0]), get(wx[1]), get(wx[2])}, wyB[3] = {get(wy[0]), get(wy[1]), get(wy[2])}, wzB[3] = {get(wz[0]), get(wz[1]), get(wz[2])};
+      if (!has_partner) { wxB[0] = wxB[1] = wxB[2] = 0.f; }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        V3 hi_ = step_n(h0, H0, i), hiB = step_n(h0B, H0B, i);
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+          V3 hij = step_n(hi_, H1, jj), hijB = step_n(hiB, H1B, jj);
+          float wij = wx[i] * wy[jj], a1 = ex[i] * wy[jj], a2 = wx[i] * ey[jj], wijB = wxB[i] * wyB[jj];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            V3 h = step_n(hij, H2, k), hB = step_n(hijB, H2B, k);
+            float w = wij * wz[k], wB = wijB * wzB[k];
+            int so = (i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7);
+            float4 t = tvrow[so];
+            unsigned ga = growb + 16u * (unsigned)so;
+            float4 o = lds_v4_if(ga, mine);
+            o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
+            o.x = fmaf(wB, hB.x, o.x); o.y = fmaf(wB, hB.y, o.y); o.z = fmaf(wB, hB.z, o.z);
+            sts_v4_if(ga, o, mine);
+            float qn = t.x * h.x + t.y * h.y + t.z * h.z;
+            float tt = wz[k] * qn, uu = ez[k] * qn;
+            gxs.x = fmaf(a1, tt, gxs.x); gxs.y = fmaf(a2, tt, gxs.y); gxs.z = fmaf(wij, uu, gxs.z);
+          }
+        }
+      }
+    } else
+#endif
+    {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       V3 hi_ = step_n(h0, H0, i);
@@ -1229,7 +1356,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
           int so = (i << 6 | jj << 3) + ((g0 + 2 * i + 4 * jj + k) & 7);
           float4 t = tvrow[so];
           unsigned ga = growb + 16u * (unsigned)so;
-          float4 o = lds_v4_if(ga, mine);
+          float4 o = lds_v4_if(ga, mine);  // (carrying one register quadruple across the updates, as k_p2g_tile does, only adds moves here)
           o.x = fmaf(w, h.x, o.x); o.y = fmaf(w, h.y, o.y); o.z = fmaf(w, h.z, o.z);
           sts_v4_if(ga, o, mine);
           float qn = t.x * h.x + t.y * h.y + t.z * h.z;
@@ -1237,6 +1364,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
           gxs.x = fmaf(a1, tt, gxs.x); gxs.y = fmaf(a2, tt, gxs.y); gxs.z = fmaf(wij, uu, gxs.z);
         }
       }
+    }
     }
     if (!in_tile) gxs = vzero();
     if (act && !in_tile) {  // left the tile since the last sort (rare): gather from the grid, rolled
@@ -1253,7 +1381,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2PG_TILE) k_g2p_grad_t
             gxs += v3(pick(d0, d1, d2, i, 0) * wyj * wzk, wxi * pick(d0, d1, d2, jj, 1) * wzk, wxi * wyj * pick(d0, d1, d2, k, 2)) * qn;
           }
     }
-    dq.push(act && !mine, p, lane, flush_queue);
+    dq.push(act && !mine && !second, p, lane, flush_queue);
     V3 gx = in.gx + gxs - (kp.inv_dx * s4) * mul_t(in.gC, in.nvel);  // sum_n w_n v_n is the velocity g2p stored in the next slot
     if (act) plane4(gout, kp.EN, 0)[p] = make_float4(gx.x, gx.y, gx.z, 0.f);
   }
@@ -1313,10 +1441,11 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_P2GG_TILE) k_p2g_grad_t
   pdl_wait();
   const int nchunks = sg.cnt[0];
   const int4 *__restrict__ chunks = sg.chunks;
-  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+  DD_CHUNK_LOOP(ci) {
     ChunkGeom cg = chunk_geom(chunks[ci], kp);
     if (STAGED) { int p0 = row_pos(cg, 0, lane); stager.stage1(p0); stager.stage2(p0); }
-    fill_tile(tile, ggrid + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
+    fill_tile_async(tile, ggrid + (size_t)cg.env * kp.G, kp, cg.ox, cg.oy, cg.oz, lane);
+    cp_async_wait_all();
     __syncwarp();
     for (int j = 0; j < cg.R; ++j) {
       if (STAGED) {
@@ -1341,22 +1470,36 @@ __global__ void __launch_bounds__(32 * kTileWarps, DD_LB_G2P_TILE) k_g2p_tile(KP
                                                                  float *__restrict__ nxt, const float4 *__restrict__ grid_v, int *sched) {
   extern __shared__ float4 dd_smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *tile = dd_smem + warp * kTileN;
+  float4 *tile = dd_smem + warp * (kTileN + 32), *xst = tile + kTileN + lane;
   pdl_launch_dependents();
   pdl_wait();
   const int nchunks = sg.cnt[0];
   const int4 *__restrict__ chunks = sg.chunks;
   V3 hi = v3(((float)kp.gx - 3.f) * kp.dx, ((float)kp.gy - 3.f) * kp.dx, ((float)kp.gz - 3.f) * kp.dx);
   float lo = kp.gh * kp.dx;
-  for (int ci = next_chunk(sched, lane); ci < nchunks; ci = next_chunk(sched, lane)) {
+  DD_CHUNK_LOOP(ci) {
   ChunkGeom cg = chunk_geom(chunks[ci], kp);
   const float4 *genv = grid_v + (size_t)cg.env * kp.G;
-  fill_tile(tile, genv, kp, cg.ox, cg.oy, cg.oz, lane);
+#ifndef DD_G2P_NO_STAGE_X
+  cp_async16(xst, plane4(cur, kp.EN, 0) + row_pos(cg, 0, lane));  // (joins the group of the tile fill)
+#endif
+  fill_tile_async(tile, genv, kp, cg.ox, cg.oy, cg.oz, lane);
+  cp_async_wait_all();
   __syncwarp();
   for (int j = 0; j < cg.R; ++j) {
+#ifndef DD_G2P_NO_STAGE_X
+    // the position of the lane's particle of the NEXT row is copied into shared memory while this row is gathered (the plain
+    // load at the top of the row was 27 % of the kernel's stall samples); idle lanes of a short last row shadow a valid particle
+    cp_async_wait_all();
+    float4 a = *xst;
+    if (j + 1 < cg.R) { cp_async16(xst, plane4(cur, kp.EN, 0) + row_pos(cg, j + 1, lane)); cp_async_commit(); }
+    if (!lane_on(cg, j, lane)) continue;
+    int p = row_pos(cg, j, lane);
+#else
     if (!lane_on(cg, j, lane)) continue;
     int p = row_pos(cg, j, lane);
     float4 a = ldg_stream(plane4(cur, kp.EN, 0) + p);
+#endif
     V3 x = v3(a.x, a.y, a.z);
     Stencil st = make_stencil_safe(x, kp);
     float wx[3] = {st.w0.x, st.w1.x, st.w2.x}, wy[3] = {st.w0.y, st.w1.y, st.w2.y}, wz[3] = {st.w0.z, st.w1.z, st.w2.z};
@@ -2481,6 +2624,9 @@ void dd_sim_destroy(dd_sim *s) {
 }
 
 long long dd_sim_launch_count(dd_sim *s) { return s ? s->launches : 0; }
+#ifdef DD_COUNT_DEFER
+extern "C" void dd_debug_defer_counts(unsigned long long *out) { cudaDeviceSynchronize(); cudaMemcpyFromSymbol(out, g_defer_count, 16); }
+#endif
 
 int dd_sim_set_material(dd_sim *s, const float *mass, const float *vol, const float *mu_lam_yield, cudaStream_t st) {
   if (!s || !mass || !vol || !mu_lam_yield) return fail("dd_sim_set_material: null argument");
