@@ -971,15 +971,16 @@ __global__ void __launch_bounds__(kT, DD_LB_P2G_GRAD) k_p2g_grad(KP kp, const in
 // since the last sort).  Inside a chunk lane l walks the sorted ranks [l*R, (l+1)*R), so the 32 particles of a round
 // sit in 32 different cells and their read-modify-writes on the tile never collide; the storage order is the
 // round-major transpose of that assignment, which keeps every global load coalesced.  Collisions that do occur
-// (dense cells, drift) are detected with match.any and serialised.  The tile is flushed with one vector reduction per
-// touched node instead of one per (particle, node).
+// (dense cells, drift) are detected with match.any: the second lane of a cell is absorbed by its owner lane (pairs, see
+// k_p2g_tile), further lanes take the deferred queue below.  The tile is flushed with one vector reduction per touched node
+// instead of one per (particle, node).  The slack for drift is one node on the high side of every axis (tile origin =
+// brick origin - 1: a fresh stencil base sits at tile coordinate 0..4, the tile takes 0..5).
 
-// Lanes that cannot use the tile in their row -- a lane whose cell is also the cell of a lower lane of the same row (the
-// read-modify-write of the row would lose one of the two updates), or whose stencil has left the tile since the last sort --
-// are not served inside the row loop (a second dependent pass of 27 updates for one or two lanes of the warp): their storage
-// positions go to a small per-warp queue, and whenever 32 are waiting (and at the end of the kernel) every lane takes one,
-// reads its inputs back and sends its 27 contributions straight to the grid.  Half a percent of the particles collide after
-// a fresh sort, but a quarter of the rows hold one of them.
+// Lanes that cannot use the tile in their row -- the THIRD and further lanes of a cell in a row (the second one is absorbed by
+// the cell's owner lane, see "pairs" in k_p2g_tile), or a lane whose stencil has left the tile since the last sort -- are not
+// served inside the row loop: their storage positions go to a small per-warp queue, and whenever 32 are waiting (and at the end
+// of the kernel) every lane takes one, reads its inputs back and sends its 27 contributions straight to the grid.  Measured
+// (-DDD_COUNT_DEFER): 0.5 % of the particles at config D, 3-4 % in the dense 10k-particle scenes (before the pairs: 3.3 % / 16 %).
 #ifdef DD_COUNT_DEFER
 __device__ unsigned long long g_defer_count[2];  // (diagnostic build) deferred lanes, rows with a deferred lane
 #endif
