@@ -1939,20 +1939,38 @@ __global__ void k_copy_poses(int n, const float4 *__restrict__ ps, const float4 
 // [x | v |] dist_0 .. dist_{nb-1}; WITH_XV = false writes the distances only (ld = nb: dd_sim_compute_dist).
 template <bool WITH_XV>
 __global__ void __launch_bounds__(kT) k_obs(KP kp, const int *__restrict__ perm, const float *__restrict__ slot, BodyTables bt, float *__restrict__ out, int ld) {
+  // Rows of up to 32 floats go through shared memory: a lane computes the row of ITS particle, then the warp writes the 32 rows one
+  // after the other, lane l the l-th float -- contiguous 4 ld-byte segments instead of ld scalar stores per lane into 32 different
+  // rows of the caller's particle order (1M particles x 25 floats: 164 -> 75 us).
+  __shared__ float rows[kT / 32][32][33];
   int p = blockIdx.x * kT + threadIdx.x;
-  if (p >= kp.EN) return;
-  int env = p / kp.N;
-  float4 a = plane4(slot, kp.EN, 0)[p];
-  V3 xp = v3(a.x, a.y, a.z);
-  float *o = out + (size_t)perm[p] * ld;
-  if (WITH_XV) {
-    float4 b = plane4(slot, kp.EN, 1)[p];
-    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y;
-    o += 6;
+  const bool live = p < kp.EN;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool staged = ld <= 32;
+  float *srow = rows[w][lane];
+  int target = 0;
+  if (live) {
+    int env = p / kp.N;
+    float4 a = plane4(slot, kp.EN, 0)[p];
+    V3 xp = v3(a.x, a.y, a.z);
+    target = perm[p];
+    float *o = staged ? srow : out + (size_t)target * ld;
+    if (WITH_XV) {
+      float4 b = plane4(slot, kp.EN, 1)[p];
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y;
+      o += 6;
+    }
+    for (int b = 0; b < kp.nb; ++b) {
+      int pb = env * kp.nb + b;
+      o[b] = shape_sdf(q4f(bt.tfsr[b]), q4f(bt.args[b]), xform_inv(v3f(bt.pos[pb]), q4f(bt.rot[pb]), xp));
+    }
   }
-  for (int b = 0; b < kp.nb; ++b) {
-    int pb = env * kp.nb + b;
-    o[b] = shape_sdf(q4f(bt.tfsr[b]), q4f(bt.args[b]), xform_inv(v3f(bt.pos[pb]), q4f(bt.rot[pb]), xp));
+  if (!staged) return;
+  __syncwarp();
+  const unsigned livemask = __ballot_sync(0xffffffffu, live);
+  for (int r = 0; r < 32; ++r) {
+    int trg = __shfl_sync(0xffffffffu, target, r);
+    if ((livemask >> r & 1u) && lane < ld) out[(size_t)trg * ld + lane] = rows[w][r][lane];
   }
 }
 // Adjoint of k_obs: row perm[p] of `g` (ld floats) holds [gx | gv |] gdist.  gx, gv are added to the gradient slot; the distance
@@ -1974,7 +1992,7 @@ __global__ void __launch_bounds__(kT) k_obs_grad(KP kp, const int *__restrict__ 
   for (int i = threadIdx.x; i < kp.nb * 8 && block_one_env; i += kT) acc[i] = 0.f;
   __syncthreads();
   const int env = live ? p / kp.N : last / kp.N;
-  const float *row = g + (size_t)(live ? perm[p] : 0) * ld;
+  const float *row = g + (size_t)(live ? perm[p] : 0) * ld;  // (staging the rows through shared memory as k_obs does: 87 -> 99 us at 1M particles)
   V3 xp = vzero(), g_x = vzero(), g_v = vzero();
   if (live) {
     float4 a = plane4(slot, kp.EN, 0)[p];
