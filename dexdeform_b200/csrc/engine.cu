@@ -62,6 +62,9 @@ constexpr int kT = 256;
 #ifndef DD_LB_P2G_GRAD
 #define DD_LB_P2G_GRAD 2
 #endif
+#ifndef DD_LB_GRID_GRAD
+#define DD_LB_GRID_GRAD 3  // blocks of k_grid_grad_b per SM (80 registers; 4 blocks = 64 registers spill 96 B in the contact adjoint: 10k scene 49 -> 47 us, 64 x 10k 64 -> 58)
+#endif
 constexpr int kPlaneFloats = 45;  // 16 (x,v,C + pad) + 9 (F) + 4 (quaternion of V) + 16 (constitutive checkpoint: affine, sigma, quaternion of U)
 
 struct KP {            // kernel parameters shared by all kernels
@@ -512,18 +515,32 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
     if (gx_ > kp.gx - bound && vv.x > 0) gv.x = 0;
     if (gx_ < bound && vv.x < 0) gv.x = 0;
   }
-  // bodies in reverse; all lanes take part in the warp reductions
+  // Bodies in reverse.  Every lane walks ITS OWN contact list (highest body first), so one trip of the loop runs the stage adjoint
+  // of up to 32 different (node, body) pairs: the trip count is the longest list of a node (1-3), not the size of the union of the
+  // warp's bodies (up to nb where a hand closes over a few nodes).  The pose gradients of a trip are then reduced once per distinct
+  // body of that trip; all lanes take part in those warp reductions.
+  const int lane_ = threadIdx.x & 31;
+  const int wenv = __shfl_sync(0xffffffffu, env_, 0);  // a warp never straddles two environments (G is a multiple of 64)
+#ifdef DD_UNION_LOOP  // (round-2 formulation, kept for A/B timing: one trip per body of the warp's union)
   unsigned long long wmask = mask;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wmask |= __shfl_xor_sync(0xffffffffu, wmask, o);
   while (wmask) {
-    int b = 63 - __clzll((long long)wmask);
+    const int b = 63 - __clzll((long long)wmask);
     wmask &= ~(1ull << b);
+    const bool has = live && (mask >> b & 1ull);
+#else
+  unsigned long long rem = live ? mask : 0ull;
+  while (__any_sync(0xffffffffu, rem != 0ull)) {
+    const bool has = rem != 0ull;
+    const int b = has ? 63 - __clzll((long long)rem) : -1;
+    if (has) rem &= ~(1ull << b);
+#endif
     V3 g_bx = vzero(), g_np = vzero();
     Q4 g_bq, g_nq;
     g_bq.w = g_bq.x = g_bq.y = g_bq.z = 0.f;
     g_nq = g_bq;
-    if (live && (mask >> b & 1ull)) {
+    if (has) {
       // input velocity of stage b: kept from the forward replay for the first kStageStack contacts of this node, otherwise
       // re-derived by replaying the contacting bodies before it
       V3 v = v0;
@@ -579,34 +596,39 @@ DD_DEV void grid_grad_body(const KP &kp, int node, bool inr, int env_, int cx, i
       V3 g_tmp = vzero();
       xform_inv_adj(bx, bq, gx, g_gxb, g_bx, g_bq, g_tmp);
     }
-    // NOTE: a warp may straddle two environments only if G is not a multiple of 32; grids are multiples of 4^3
     // Warp totals of the 14 pose-gradient components with a transposing butterfly: at every stage a lane hands half of its values
     // to its partner and keeps the other half, so 16 shuffles (8 + 4 + 2 + 1 + 1) replace 14 x 5; afterwards the even lane 2 i holds
     // the warp total of component i and adds it with ONE atomic (14 lanes in parallel instead of 14 atomics issued by lane 0).
-    float r[16] = {g_np.x, g_np.y, g_np.z, g_nq.w, g_nq.x, g_nq.y, g_nq.z, g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z, 0.f, 0.f};
-    const int lane_ = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, has);
+    while (todo) {
+      const int bs = __shfl_sync(0xffffffffu, b, __ffs(todo) - 1);
+      const bool mem = has && b == bs;
+      todo &= ~__ballot_sync(0xffffffffu, mem);
+      float r[16] = {g_np.x, g_np.y, g_np.z, g_nq.w, g_nq.x, g_nq.y, g_nq.z, g_bx.x, g_bx.y, g_bx.z, g_bq.w, g_bq.x, g_bq.y, g_bq.z, 0.f, 0.f};
 #pragma unroll
-    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-      const bool hi = (lane_ & off) != 0;
+      for (int c = 0; c < 14; ++c) r[c] = mem ? r[c] : 0.f;
 #pragma unroll
-      for (int i = 0; i < half; ++i) {
-        float send = hi ? r[i] : r[i + half], keep = hi ? r[i + half] : r[i];
-        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool hi = (lane_ & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          float send = hi ? r[i] : r[i + half], keep = hi ? r[i + half] : r[i];
+          r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
       }
-    }
-    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-    int wenv = __shfl_sync(0xffffffffu, env_, 0);  // a warp never straddles two environments
+      r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
 #ifndef DD_NO_POSE_ATOMICS
-    {
-      const int comp = lane_ >> 1, pb = wenv * kp.nb + b;
-      if (!(lane_ & 1) && comp < 14) {
-        float *dst = comp < 3 ? &gnpos[pb].x + comp : comp < 7 ? &gnrot[pb].x + (comp - 3) : comp < 10 ? &gpos[pb].x + (comp - 7) : &grot[pb].x + (comp - 10);
-        atomicAdd(dst, r[0]);
+      {
+        const int comp = lane_ >> 1, pb = wenv * kp.nb + bs;
+        if (!(lane_ & 1) && comp < 14) {
+          float *dst = comp < 3 ? &gnpos[pb].x + comp : comp < 7 ? &gnrot[pb].x + (comp - 3) : comp < 10 ? &gpos[pb].x + (comp - 7) : &grot[pb].x + (comp - 10);
+          atomicAdd(dst, r[0]);
+        }
       }
-    }
 #else
-    if (r[0] == 12345.f) gnpos[0].x = r[0] + (float)wenv;
+      if (r[0] == 12345.f) gnpos[0].x = r[0] + (float)(wenv + bs);
 #endif
+    }
   }
   if (inr) {
     if (live) {
@@ -1652,7 +1674,7 @@ __global__ void __launch_bounds__(kT) k_restore_bricks(KP kp, const int *__restr
   }
 }
 
-__global__ void __launch_bounds__(kT, 4) k_grid_grad_b(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *__restrict__ grid,
+__global__ void __launch_bounds__(kT, DD_LB_GRID_GRAD) k_grid_grad_b(KP kp, const int *__restrict__ cnt, const int *__restrict__ active, float4 *__restrict__ grid,
                                                     float4 *__restrict__ ggrid_v, float4 *__restrict__ ggrid, BodyTables bt, float4 *gpos,
                                                     float4 *grot, float4 *gnpos, float4 *gnrot, int zero_m, BrickCk ck, BrickCk below, float4 *__restrict__ grid_v) {
   // ck: this substep's brick checkpoint ((mv, m) is read from it instead of `grid`); below: the checkpoint of the substep the
