@@ -244,8 +244,9 @@ def test_tiled_path_follows_runaway_particles():
     # (C is the gradient of a nearly uniform 1500-per-second velocity field: its natural scale is |v| / dx, not its own size)
     c_scale = float(np.abs(a["state"]["v"]).max() * sc["inv_dx"])
     assert np.abs(st["C"] - a["state"]["C"]).max() < 2e-5 * c_scale
-    for k in ("x", "v", "F"):
-        assert rel_err(st[k], a["state"][k]) < 2e-5, (k, rel_err(st[k], a["state"][k]))
+    # (F: 1.2e-5 typical, 2.0-2.3e-5 in 2 runs of 80 -- the float-atomic order of the grid sums times dt |v| / dx = 4.8 cells per substep)
+    for k, tol in dict(x=2e-5, v=2e-5, F=5e-5).items():
+        assert rel_err(st[k], a["state"][k]) < tol, (k, rel_err(st[k], a["state"][k]))
     for k in ("x", "v"):
         assert_close_rows(gr[k][0], a["grad"][k][0], 5e-3, k + "_grad", frac=0.02)   # (summation order differs; |v| dx/dt = 4.8 amplifies rounding)
     # a second rollout from a new initial state reuses the engine: stale grid contents of the earlier run must not leak
@@ -255,8 +256,8 @@ def test_tiled_path_follows_runaway_particles():
     b = run_engine(sc, S, seedg, tile_mode=False, use_graphs=False, grid_ckpt=False)
     st = sim.get_state(S)
     assert np.abs(st["C"] - b["state"]["C"]).max() < 2e-5 * c_scale
-    for k in ("x", "v", "F"):
-        assert rel_err(st[k], b["state"][k]) < 2e-5, (k, rel_err(st[k], b["state"][k]))
+    for k, tol in dict(x=2e-5, v=2e-5, F=5e-5).items():
+        assert rel_err(st[k], b["state"][k]) < tol, (k, rel_err(st[k], b["state"][k]))
     sim.close()
 
 
@@ -300,8 +301,8 @@ def test_resort_in_pieces_and_stale_slots():
     g_mid = sim.get_state_grad(L, ("x",))["x"]
     sim.backward(0, L)
     gr = sim.get_state_grad(0)
-    for k in ("x", "v", "F", "C"):
-        assert_close_rows(gr[k][0], whole["grad"][k][0], 1e-4, k + "_grad")
+    for k in ("x", "v", "F", "C"):  # (two runs of the same engine: one yield-branch flip from the float-atomic order moves 5-6 rows by 6e-4, 3 runs in 60)
+        assert_close_rows(gr[k][0], whole["grad"][k][0], 1e-4, k + "_grad", frac=1e-2)
     assert np.isfinite(g_mid).all() and np.abs(g_mid).max() > 0
     gp, _ = sim.get_pose_grads(0, S + 1)
     assert np.abs(gp - whole["gpos"]).max() < 1e-3 * max(np.abs(whole["gpos"]).max(), 1.0)
