@@ -569,7 +569,7 @@ def run_E(args, rank, world, local):
             torch.cuda.synchronize()
             ms1 = f0.elapsed_time(f1) / 2
             one_gpu = {"value": units / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1, "steps": 2,
-                       "note": "all 512 environments on rank 0's GPU alone (same process and engine, 8 passes of 64), other ranks idle"}
+                       "note": f"all {E_total} environments on rank 0's GPU alone (same process and engine, {E_total // sub} passes of {sub}), other ranks idle"}
         barrier_sync(world)
     out = None
     if rank == 0:
