@@ -15,12 +15,15 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 grid = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 E = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-kw = {}
+kw, skw = {}, {}
 for a in sys.argv[5:]:
     k, v = a.split("=")
-    kw[k] = int(v)
+    if k.startswith("scene_"):
+        skw[k[6:]] = int(v)  # e.g. scene_nb=0: the same scene without primitives
+    else:
+        kw[k] = int(v)
 w = 0.4 if n >= 500000 else 0.09 * (n / 10000) ** (1 / 3)
-sc = make_scene(n, grid, box_center=(0.5, 0.3, 0.5), box_width=(w, w, w), steps=S, seed=0, hand_scale=6.0 if n >= 500000 else 1.5)
+sc = make_scene(n, grid, box_center=(0.5, 0.3, 0.5), box_width=(w, w, w), steps=S, seed=0, hand_scale=6.0 if n >= 500000 else 1.5, **skw)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 sim = FusedSim.from_scene(sc, n_envs=E, max_steps=S, stream=stream.cuda_stream, **kw)
