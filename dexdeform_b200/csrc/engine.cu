@@ -2619,10 +2619,18 @@ int dd_sim_create(const dd_sim_config *cfg, dd_sim **out) {
     // Particles per chunk (one warp, one tile).  Large chunks amortise the tile fill / flush (256 is the measured optimum at
     // config D); a batch that cannot give every resident warp about two chunks gets smaller ones, because a warp walks the
     // rows of its chunk one after the other and a nearly empty machine is then bound by that latency.
+    const char *ecm = getenv("DD_CHUNK_MAX");  // (tuning knob like DD_WPB_*: overrides the automatic choice, not the caller's)
     if (cfg->chunk_max > 0) s->chunk_max = cfg->chunk_max;
+    else if (ecm && atoi(ecm) >= 32) s->chunk_max = std::min(atoi(ecm), 512);
     else {
       int warps = std::max(1, s->pb_p2g * s->w_p2g), per_warp = kp.EN / warps;
       s->chunk_max = per_warp >= 256 ? 256 : std::min(256, std::max(64, (per_warp / 2 + 31) / 32 * 32));
+      // A batch that makes more than two scheduling waves of 256-particle chunks on the scatter kernel takes 320-particle chunks
+      // when that shortens the modelled launch, ceil(waves) x rows per chunk (chunks average ~0.94 of the maximum).  Measured on a
+      // pass of workload E: 128 x 10k particles 205.6 -> 198.9 ms; 64 x 10k (1.1 waves) and config D (1.9) are left at 256, where 320 is
+      // neutral / 1 % slower.
+      auto launch_rows = [&](int c) { double w = kp.EN / (0.94 * c) / warps; return std::ceil(w) * c; };
+      if (kp.EN / (0.94 * 256) / warps > 2.0 && launch_rows(320) < launch_rows(256)) s->chunk_max = 320;
     }
     s->occ_cap = std::min(kp.EN, s->NBtot);
     s->chunk_cap = kp.EN / s->chunk_max + s->occ_cap + 1;  // every occupied brick adds at most one partly filled chunk
